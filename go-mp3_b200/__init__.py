@@ -1,0 +1,429 @@
+"""go-mp3_b200 — B200 (sm_100a) MP3 Layer III decode engine behind go-mp3's API.
+
+This Python layer is a thin ctypes binding over the two C-ABI libraries built in-tree:
+
+* ``libmp3gpu.so``  (include/mp3gpu.h)  — the device engine: hand-written CUDA kernels for the
+  per-granule hot path (Huffman/scalefactors, requantise/stereo/reorder/alias, IMDCT, synthesis).
+* ``libmp3host.so`` (include/mp3host.h) — the host-side mirror of the reference's ``package mp3``
+  (``NewDecoder``, ``Decoder.Read/Seek/...``, ``DecodeBatch``): tag skipping, header sync, side
+  info, bit-reservoir resolution.  In the product this layer is Go + cgo;
+  no Go toolchain exists in the build image, so it is mirrored in C++.
+
+There is no CPU decode path and no fallback: if the libraries are missing, or no CUDA device is
+present, creating an :class:`Engine` raises.
+
+The directory name contains a hyphen, so the package is imported through
+``importlib`` (see ``__graft_entry__.load_package``) under the module name ``go_mp3_b200``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+MP3_OK = 0
+MP3_EOF = 1
+MP3_ERR_UNEXPECTED_EOF = -1
+MP3_ERR_SYNC_LIMIT = -2
+MP3_ERR_FREE_FORMAT = -3
+MP3_ERR_MPEG25 = -4
+MP3_ERR_LAYER = -5
+MP3_ERR_FRAMESIZE = -6
+MP3_ERR_MAINDATA_SIZE = -7
+MP3_ERR_ISPOS = -8
+MP3_ERR_SEEK_UNSUPPORTED = -11
+MP3_ERR_WHENCE = -12
+MP3_ERR_REF_PANIC = -14
+MP3_ERR_DEVICE = -50
+MP3_ERR_INVALID = -51
+
+TAP_IS, TAP_COUNT1, TAP_SCALEFAC, TAP_XR, TAP_HYBRID = 0, 1, 2, 3, 4
+PCM_BYTES_PER_GRANULE = 2304
+W2_VALID = 1 << 25
+W2_ZERO_STATE = 1 << 26
+
+
+class Mp3Error(RuntimeError):
+    def __init__(self, code: int, msg: str = ""):
+        self.code = code
+        super().__init__(msg or f"mp3 error {code}")
+
+
+class Unit(C.Structure):
+    """mp3gpu_unit (include/mp3gpu.h)."""
+    _fields_ = [("bit_start", C.c_uint64), ("buf_end_rel", C.c_int32), ("w0", C.c_uint32), ("w1", C.c_uint32),
+                ("w2", C.c_uint32), ("reserved", C.c_uint32 * 2)]
+
+
+UNIT_DTYPE = np.dtype([("bit_start", "<u8"), ("buf_end_rel", "<i4"), ("w0", "<u4"), ("w1", "<u4"), ("w2", "<u4"),
+                       ("r0", "<u4"), ("r1", "<u4")])
+assert UNIT_DTYPE.itemsize == 32 and C.sizeof(Unit) == 32
+
+
+class GpuOpts(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("wave_granules", C.c_uint32), ("keep_intermediates", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class GpuTimings(C.Structure):
+    _fields_ = [("k1_huffman_ms", C.c_float), ("k2_requant_ms", C.c_float), ("k3_imdct_ms", C.c_float),
+                ("k4_synth_ms", C.c_float), ("total_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
+                ("waves", C.c_uint32), ("launches", C.c_uint32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class EngineOpts(C.Structure):
+    _fields_ = [("device", C.c_int), ("host_threads", C.c_int), ("wave_granules", C.c_uint32),
+                ("chunk_frames", C.c_uint32), ("keep_intermediates", C.c_uint32), ("use_exact_library", C.c_uint32)]
+
+
+class StreamResult(C.Structure):
+    _fields_ = [("pcm_offset", C.c_int64), ("pcm_bytes", C.c_int64), ("sample_rate", C.c_int32),
+                ("status", C.c_int32), ("frames", C.c_int64)]
+
+
+class BatchTimings(C.Structure):
+    _fields_ = [("parse_s", C.c_double), ("gather_s", C.c_double), ("device_s", C.c_double), ("total_s", C.c_double),
+                ("main_data_bytes", C.c_uint64), ("n_granules", C.c_uint64), ("pcm_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class Parsed(C.Structure):
+    _fields_ = [("main_data", C.POINTER(C.c_uint8)), ("main_data_len", C.c_size_t), ("units", C.POINTER(Unit)),
+                ("n_granules", C.c_size_t), ("streams", C.POINTER(StreamResult)), ("n_streams", C.c_size_t)]
+
+
+def _lib_path(name: str) -> str:
+    p = os.path.join(_HERE, name)
+    if not os.path.exists(p):
+        raise ImportError(f"{p} is missing: build it with __graft_entry__.build() (make -C go-mp3_b200/csrc). "
+                          "There is no fallback path.")
+    return p
+
+
+_host = None
+_gpu = {}
+
+
+def host_lib() -> C.CDLL:
+    """libmp3host.so with prototypes set."""
+    global _host
+    if _host is not None:
+        return _host
+    L = C.CDLL(_lib_path("libmp3host.so"))
+    vp, i64, sz = C.c_void_p, C.c_int64, C.c_size_t
+    pp_u8 = C.POINTER(C.c_char_p)
+    L.mp3_engine_create.argtypes = [C.POINTER(EngineOpts), C.POINTER(vp)]
+    L.mp3_engine_create.restype = C.c_int
+    L.mp3_engine_destroy.argtypes = [vp]
+    L.mp3_engine_destroy.restype = None
+    L.mp3_engine_last_error.argtypes = [vp]
+    L.mp3_engine_last_error.restype = C.c_char_p
+    L.mp3_engine_gpu.argtypes = [vp]
+    L.mp3_engine_gpu.restype = vp
+    L.mp3_error_string.argtypes = [C.c_int]
+    L.mp3_error_string.restype = C.c_char_p
+    L.mp3_new_decoder.argtypes = [vp, C.c_void_p, sz, C.c_int, C.POINTER(C.c_int)]
+    L.mp3_new_decoder.restype = vp
+    L.mp3_decoder_free.argtypes = [vp]
+    L.mp3_decoder_free.restype = None
+    L.mp3_decoder_read.argtypes = [vp, C.c_void_p, sz, C.POINTER(C.c_int)]
+    L.mp3_decoder_read.restype = C.c_long
+    L.mp3_decoder_seek.argtypes = [vp, i64, C.c_int, C.POINTER(C.c_int)]
+    L.mp3_decoder_seek.restype = i64
+    for name in ("length", "bytes_per_frame", "duration_ns", "position_ns", "remaining_ns", "sample_position",
+                 "sample_count"):
+        f = getattr(L, "mp3_decoder_" + name)
+        f.argtypes = [vp]
+        f.restype = i64
+    L.mp3_decoder_sample_rate.argtypes = [vp]
+    L.mp3_decoder_sample_rate.restype = C.c_int
+    L.mp3_decoder_progress.argtypes = [vp]
+    L.mp3_decoder_progress.restype = C.c_double
+    for name in ("seek_to_sample", "skip", "seek_to_time"):
+        f = getattr(L, "mp3_decoder_" + name)
+        f.argtypes = [vp, i64]
+        f.restype = C.c_int
+    L.mp3_decode_batch.argtypes = [vp, pp_u8, C.POINTER(sz), sz, C.POINTER(StreamResult), C.POINTER(C.c_void_p),
+                                   C.POINTER(BatchTimings)]
+    L.mp3_decode_batch.restype = C.c_int
+    L.mp3_parse_streams.argtypes = [pp_u8, C.POINTER(sz), sz, C.c_int, C.POINTER(C.POINTER(Parsed))]
+    L.mp3_parse_streams.restype = C.c_int
+    L.mp3_parsed_free.argtypes = [C.POINTER(Parsed)]
+    L.mp3_parsed_free.restype = None
+    _host = L
+    return L
+
+
+def gpu_lib(exact: bool = False) -> C.CDLL:
+    """libmp3gpu.so (or the no-contraction build libmp3gpu_exact.so) with prototypes set."""
+    if exact in _gpu:
+        return _gpu[exact]
+    L = C.CDLL(_lib_path("libmp3gpu_exact.so" if exact else "libmp3gpu.so"))
+    vp, sz = C.c_void_p, C.c_size_t
+    L.mp3gpu_create.argtypes = [C.c_int, C.POINTER(GpuOpts), C.POINTER(vp)]
+    L.mp3gpu_create.restype = C.c_int
+    L.mp3gpu_destroy.argtypes = [vp]
+    L.mp3gpu_destroy.restype = None
+    L.mp3gpu_last_error.argtypes = [vp]
+    L.mp3gpu_last_error.restype = C.c_char_p
+    L.mp3gpu_decode.argtypes = [vp, vp, sz, vp, sz, vp]
+    L.mp3gpu_decode.restype = C.c_int
+    L.mp3gpu_decode_device.argtypes = [vp, vp, sz, vp, sz, vp]
+    L.mp3gpu_decode_device.restype = C.c_int
+    L.mp3gpu_host_alloc.argtypes = [sz]
+    L.mp3gpu_host_alloc.restype = vp
+    L.mp3gpu_host_free.argtypes = [vp]
+    L.mp3gpu_host_free.restype = None
+    L.mp3gpu_device_alloc.argtypes = [vp, sz]
+    L.mp3gpu_device_alloc.restype = vp
+    L.mp3gpu_device_free.argtypes = [vp, vp]
+    L.mp3gpu_device_free.restype = None
+    L.mp3gpu_copy_to_device.argtypes = [vp, vp, vp, sz]
+    L.mp3gpu_copy_to_device.restype = C.c_int
+    L.mp3gpu_copy_to_host.argtypes = [vp, vp, vp, sz]
+    L.mp3gpu_copy_to_host.restype = C.c_int
+    L.mp3gpu_synchronize.argtypes = [vp]
+    L.mp3gpu_synchronize.restype = C.c_int
+    L.mp3gpu_last_timings.argtypes = [vp, C.POINTER(GpuTimings)]
+    L.mp3gpu_last_timings.restype = C.c_int
+    L.mp3gpu_debug_read.argtypes = [vp, C.c_int, sz, sz, vp]
+    L.mp3gpu_debug_read.restype = C.c_int
+    L.mp3gpu_device_info.argtypes = [vp, C.c_char_p, sz, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.mp3gpu_device_info.restype = C.c_int
+    L.mp3gpu_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    L.mp3gpu_measure_fp32_peak.restype = C.c_int
+    _gpu[exact] = L
+    return L
+
+
+def error_string(code: int) -> str:
+    return host_lib().mp3_error_string(code).decode()
+
+
+# --------------------------------------------------------------------------------------------------
+# Host-only stage: parse + reservoir resolution (no GPU needed)
+# --------------------------------------------------------------------------------------------------
+class ParsedBatch:
+    """Result of the host stage for a batch of streams: main data M, unit descriptors, per-stream results."""
+
+    def __init__(self, main_data: np.ndarray, units: np.ndarray, streams: List[dict]):
+        self.main_data = main_data      # uint8, padded by 64 zero bytes (main_data_len excludes the pad)
+        self.units = units              # UNIT_DTYPE, 2 per granule
+        self.streams = streams
+        self.main_data_len = len(main_data) - 64
+        self.n_granules = len(units) // 2
+
+
+def _stream_args(streams: Sequence[bytes]):
+    n = len(streams)
+    arr = (C.c_char_p * max(n, 1))()
+    lens = (C.c_size_t * max(n, 1))()
+    for i, s in enumerate(streams):
+        arr[i] = s
+        lens[i] = len(s)
+    return arr, lens, n
+
+
+def _result_dict(r: StreamResult) -> dict:
+    return {"pcm_offset": r.pcm_offset, "pcm_bytes": r.pcm_bytes, "sample_rate": r.sample_rate, "status": r.status,
+            "frames": r.frames}
+
+
+def parse_streams(streams: Sequence[bytes], host_threads: int = 0) -> ParsedBatch:
+    """Host half of DecodeBatch: tags, headers, side info, reservoir -> bit-slices (mp3_parse_streams)."""
+    L = host_lib()
+    arr, lens, n = _stream_args(streams)
+    out = C.POINTER(Parsed)()
+    rc = L.mp3_parse_streams(arr, lens, n, host_threads, C.byref(out))
+    if rc != MP3_OK:
+        raise Mp3Error(rc, "mp3_parse_streams failed")
+    try:
+        p = out.contents
+        md = np.ctypeslib.as_array(p.main_data, shape=(p.main_data_len + 64,)).copy()
+        nu = p.n_granules * 2
+        if nu:
+            units = np.frombuffer(C.string_at(p.units, nu * 32), dtype=UNIT_DTYPE).copy()
+        else:
+            units = np.zeros(0, dtype=UNIT_DTYPE)
+        res = [_result_dict(p.streams[i]) for i in range(p.n_streams)]
+    finally:
+        L.mp3_parsed_free(out)
+    return ParsedBatch(md, units, res)
+
+
+# --------------------------------------------------------------------------------------------------
+# Device engine (mp3gpu.h) — used directly by bench.py and the stage-level parity tests
+# --------------------------------------------------------------------------------------------------
+class GpuEngine:
+    def __init__(self, device: int = 0, wave_granules: int = 0, keep_intermediates: bool = False, exact: bool = False):
+        self.lib = gpu_lib(exact)
+        self.ctx = C.c_void_p()
+        opts = GpuOpts(1, wave_granules, 1 if keep_intermediates else 0, 0)
+        rc = self.lib.mp3gpu_create(device, C.byref(opts), C.byref(self.ctx))
+        if rc != 0:
+            self.ctx = None
+            raise Mp3Error(rc, f"mp3gpu_create failed ({rc}): a CUDA device is required; there is no CPU path")
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.mp3gpu_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise Mp3Error(rc, self.lib.mp3gpu_last_error(self.ctx).decode())
+
+    def decode(self, main_data: np.ndarray, main_data_len: int, units: np.ndarray) -> np.ndarray:
+        """Host-buffer decode (mp3gpu_decode): returns int16 [n_granules*576, 2]."""
+        n_gr = len(units) // 2
+        pcm = np.empty((n_gr * 576, 2), dtype=np.int16)
+        main_data = np.ascontiguousarray(main_data)
+        units = np.ascontiguousarray(units)
+        self._check(self.lib.mp3gpu_decode(self.ctx, main_data.ctypes.data, main_data_len, units.ctypes.data, n_gr,
+                                           pcm.ctypes.data))
+        return pcm
+
+    def timings(self) -> dict:
+        t = GpuTimings()
+        self._check(self.lib.mp3gpu_last_timings(self.ctx, C.byref(t)))
+        return t.as_dict()
+
+    def tap(self, which: int, first: int, n: int) -> np.ndarray:
+        shapes = {TAP_IS: ((n, 2, 576), np.int16), TAP_COUNT1: ((n, 2), np.int32), TAP_SCALEFAC: ((n, 2, 64), np.uint8),
+                  TAP_XR: ((n, 2, 576), np.float32), TAP_HYBRID: ((n, 2, 576), np.float32)}
+        shape, dt = shapes[which]
+        out = np.zeros(shape, dtype=dt)
+        self._check(self.lib.mp3gpu_debug_read(self.ctx, which, first, n, out.ctypes.data))
+        return out
+
+    def device_info(self) -> dict:
+        name = C.create_string_buffer(256)
+        sm, maj, mnr = C.c_int(), C.c_int(), C.c_int()
+        self._check(self.lib.mp3gpu_device_info(self.ctx, name, 256, C.byref(sm), C.byref(maj), C.byref(mnr)))
+        return {"name": name.value.decode(), "sm_count": sm.value, "cc": f"{maj.value}.{mnr.value}"}
+
+    def fp32_peak_tflops(self) -> float:
+        v = C.c_double()
+        self._check(self.lib.mp3gpu_measure_fp32_peak(self.ctx, C.byref(v)))
+        return v.value
+
+
+# --------------------------------------------------------------------------------------------------
+# Host mirror of package mp3 (mp3host.h)
+# --------------------------------------------------------------------------------------------------
+class Engine:
+    """One GPU + the host stage.  Mirrors what the Go package holds as package-level state."""
+
+    def __init__(self, device: int = 0, host_threads: int = 0, wave_granules: int = 0, chunk_frames: int = 0,
+                 keep_intermediates: bool = False, exact: bool = False):
+        self.lib = host_lib()
+        self.h = C.c_void_p()
+        opts = EngineOpts(device, host_threads, wave_granules, chunk_frames, 1 if keep_intermediates else 0,
+                          1 if exact else 0)
+        rc = self.lib.mp3_engine_create(C.byref(opts), C.byref(self.h))
+        if rc != MP3_OK:
+            self.h = None
+            raise Mp3Error(rc, "mp3_engine_create failed: a CUDA device and libmp3gpu.so are required; "
+                               "there is no CPU decode path")
+        self.exact = exact
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mp3_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def new_decoder(self, data: bytes, seekable: bool = True) -> "Decoder":
+        return Decoder(self, data, seekable)
+
+    def decode_batch(self, streams: Sequence[bytes]) -> Tuple[List[dict], np.ndarray, dict]:
+        """DecodeBatch: returns (per-stream results, PCM bytes view (valid until the next call), timings)."""
+        arr, lens, n = _stream_args(streams)
+        res = (StreamResult * max(n, 1))()
+        base = C.c_void_p()
+        tm = BatchTimings()
+        rc = self.lib.mp3_decode_batch(self.h, arr, lens, n, res, C.byref(base), C.byref(tm))
+        if rc != MP3_OK:
+            raise Mp3Error(rc, self.lib.mp3_engine_last_error(self.h).decode())
+        total = int(tm.pcm_bytes)
+        if total:
+            pcm = np.ctypeslib.as_array(C.cast(base, C.POINTER(C.c_uint8)), shape=(total,))
+        else:
+            pcm = np.zeros(0, dtype=np.uint8)
+        return [_result_dict(res[i]) for i in range(n)], pcm, tm.as_dict()
+
+
+class Decoder:
+    """Drop-in mirror of *mp3.Decoder (decode.go): Read/Seek/SampleRate/Length/... over in-memory data."""
+
+    def __init__(self, engine: Engine, data: bytes, seekable: bool = True):
+        self.engine = engine
+        self.lib = engine.lib
+        self._data = bytes(data)  # must outlive the decoder
+        err = C.c_int(0)
+        self.h = self.lib.mp3_new_decoder(engine.h, self._data, len(self._data), 1 if seekable else 0, C.byref(err))
+        if not self.h:
+            raise Mp3Error(err.value, "NewDecoder: " + error_string(err.value))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mp3_decoder_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def read(self, n: int) -> Tuple[bytes, int]:
+        """Decoder.Read: returns (bytes, err) with err MP3_OK, MP3_EOF or a fatal code."""
+        buf = C.create_string_buffer(n)
+        err = C.c_int(0)
+        got = self.lib.mp3_decoder_read(self.h, buf, n, C.byref(err))
+        return buf.raw[:got], err.value
+
+    def read_all(self) -> Tuple[bytes, int]:
+        """io.ReadAll(d): (bytes, err) with err MP3_OK on clean EOF."""
+        chunks = []
+        while True:
+            b, err = self.read(1 << 20)
+            if not b:
+                return b"".join(chunks), (MP3_OK if err == MP3_EOF else err)
+            chunks.append(b)
+
+    def seek(self, offset: int, whence: int = 0) -> int:
+        err = C.c_int(0)
+        r = self.lib.mp3_decoder_seek(self.h, offset, whence, C.byref(err))
+        if err.value != MP3_OK:
+            raise Mp3Error(err.value, error_string(err.value))
+        return r
+
+    def sample_rate(self) -> int: return self.lib.mp3_decoder_sample_rate(self.h)
+    def length(self) -> int: return self.lib.mp3_decoder_length(self.h)
+    def bytes_per_frame(self) -> int: return self.lib.mp3_decoder_bytes_per_frame(self.h)
+    def duration_ns(self) -> int: return self.lib.mp3_decoder_duration_ns(self.h)
+    def position_ns(self) -> int: return self.lib.mp3_decoder_position_ns(self.h)
+    def remaining_ns(self) -> int: return self.lib.mp3_decoder_remaining_ns(self.h)
+    def progress(self) -> float: return self.lib.mp3_decoder_progress(self.h)
+    def sample_position(self) -> int: return self.lib.mp3_decoder_sample_position(self.h)
+    def sample_count(self) -> int: return self.lib.mp3_decoder_sample_count(self.h)
+
+    def _chk(self, rc):
+        if rc != MP3_OK:
+            raise Mp3Error(rc, error_string(rc))
+
+    def seek_to_sample(self, s: int): self._chk(self.lib.mp3_decoder_seek_to_sample(self.h, s))
+    def skip(self, delta_ns: int): self._chk(self.lib.mp3_decoder_skip(self.h, delta_ns))
+    def seek_to_time(self, t_ns: int): self._chk(self.lib.mp3_decoder_seek_to_time(self.h, t_ns))

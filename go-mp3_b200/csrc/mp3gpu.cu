@@ -1,0 +1,545 @@
+// mp3gpu.cu — C ABI (include/mp3gpu.h) of the B200 MP3 Layer III granule decode engine.
+// Context management, wave scheduling, host<->device pipelining, timing and debug taps.
+// The kernels are in kernels.cuh; constant tables are built by tables.cc.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mp3gpu.h"
+#include "kernels.cuh"
+#include "tables.h"
+
+using namespace mp3gpu;
+
+static_assert(sizeof(mp3gpu_unit) == 32, "mp3gpu_unit must be 32 bytes");
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                   \
+            return MP3GPU_E_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+namespace {
+constexpr int kTimingSlots = 64;  // per-kernel event pairs kept per call (waves beyond this are not timed individually)
+}
+
+struct mp3gpu_ctx {
+    int device = 0;
+    std::string err;
+    mp3gpu_opts opts{};
+    uint32_t wave = 0;
+    cudaStream_t s_compute = nullptr, s_in = nullptr, s_out = nullptr;
+    // tables
+    void *d_tab_blob = nullptr;
+    DeviceTables T{};
+    int lut_bytes = 0;
+    // workspace for one wave (+1 granule look-back where needed)
+    int16_t *d_is16 = nullptr;
+    uint32_t *d_meta = nullptr;
+    uint32_t *d_sfpack = nullptr;
+    float *d_xr_t = nullptr;   // (wave+1) granules
+    float *d_hyb[2] = {nullptr, nullptr};  // (wave+1) granules each
+    // staging for host-buffer calls
+    uint8_t *d_main = nullptr;
+    size_t d_main_cap = 0;
+    mp3gpu_unit *d_units = nullptr;
+    size_t d_units_cap = 0;
+    int16_t *d_pcm_ring[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_in[3]{}, ev_k[3]{}, ev_out[3]{};
+    // timing
+    cudaEvent_t ev_t[kTimingSlots][5]{};
+    cudaEvent_t ev_copy[4]{};
+    mp3gpu_timings last{};
+    // taps
+    size_t last_wave_granules = 0;
+    long long last_wave_first = 0;
+};
+
+static int upload_tables(mp3gpu_ctx *ctx) {
+    HostTables h;
+    try {
+        build_host_tables(h);
+    } catch (const std::exception &e) {
+        ctx->err = std::string("table build failed: ") + e.what();
+        return MP3GPU_E_INVALID;
+    }
+    CK(cudaMemcpyToSymbol(c_cos36, h.cos36, sizeof h.cos36));
+    CK(cudaMemcpyToSymbol(c_cos12, h.cos12, sizeof h.cos12));
+    CK(cudaMemcpyToSymbol(c_win, h.imdct_win, sizeof h.imdct_win));
+    CK(cudaMemcpyToSymbol(c_synth_n, h.synth_n, sizeof h.synth_n));
+    CK(cudaMemcpyToSymbol(c_synth_d, h.synth_d, sizeof h.synth_d));
+    // maindata.go:39-42
+    static const uint8_t slen[16][2] = {{0, 0}, {0, 1}, {0, 2}, {0, 3}, {3, 0}, {1, 1}, {1, 2}, {1, 3},
+                                        {2, 1}, {2, 2}, {2, 3}, {3, 1}, {3, 2}, {3, 3}, {4, 2}, {4, 3}};
+
+    // one blob for the per-lane tables
+    std::vector<uint8_t> blob;
+    auto put = [&](const void *p, size_t n) {
+        size_t off = (blob.size() + 255) & ~size_t(255);
+        blob.resize(off + n);
+        memcpy(blob.data() + off, p, n);
+        return off;
+    };
+    size_t o_pow2 = put(h.pow2q, sizeof h.pow2q);
+    size_t o_p34 = put(h.powtab34.data(), h.powtab34.size() * sizeof(double));
+    size_t o_lsl = put(h.line_sfb_long, sizeof h.line_sfb_long);
+    size_t o_lss = put(h.line_sfb_short, sizeof h.line_sfb_short);
+    size_t o_lws = put(h.line_win_short, sizeof h.line_win_short);
+    size_t o_rd = put(h.reorder_dst, sizeof h.reorder_dst);
+    size_t o_sl = put(h.sfb_long, sizeof h.sfb_long);
+    size_t o_ss = put(h.sfb_short, sizeof h.sfb_short);
+    size_t o_ns = put(h.nslen2, sizeof h.nslen2);
+    size_t o_lut = put(h.huff_lut.data(), h.huff_lut.size() * sizeof(uint16_t));
+    size_t o_rl = put(h.is_ratio_l, sizeof h.is_ratio_l);
+    size_t o_rr = put(h.is_ratio_r, sizeof h.is_ratio_r);
+    size_t o_pt = put(h.pretab, sizeof h.pretab);
+    size_t o_hd = put(h.huff_desc, sizeof h.huff_desc);
+    size_t o_s2 = put(h.sfsize_mpeg2, sizeof h.sfsize_mpeg2);
+    size_t o_s1 = put(slen, sizeof slen);
+    size_t o_cs = put(h.cs, sizeof h.cs);
+    size_t o_ca = put(h.ca, sizeof h.ca);
+    CK(cudaMalloc(&ctx->d_tab_blob, blob.size()));
+    CK(cudaMemcpy(ctx->d_tab_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    uint8_t *b = (uint8_t *)ctx->d_tab_blob;
+    ctx->T.pow2q = (const double *)(b + o_pow2);
+    ctx->T.powtab34 = (const double *)(b + o_p34);
+    ctx->T.line_sfb_long = b + o_lsl;
+    ctx->T.line_sfb_short = b + o_lss;
+    ctx->T.line_win_short = b + o_lws;
+    ctx->T.reorder_dst = (const uint16_t *)(b + o_rd);
+    ctx->T.sfb_long = (const uint16_t *)(b + o_sl);
+    ctx->T.sfb_short = (const uint16_t *)(b + o_ss);
+    ctx->T.nslen2 = (const uint16_t *)(b + o_ns);
+    ctx->T.huff_lut = (const uint16_t *)(b + o_lut);
+    ctx->T.is_ratio_l = (const float *)(b + o_rl);
+    ctx->T.is_ratio_r = (const float *)(b + o_rr);
+    ctx->T.pretab = b + o_pt;
+    ctx->T.huff_desc = (const uint32_t *)(b + o_hd);
+    ctx->T.sfsize_mpeg2 = b + o_s2;
+    ctx->T.slen_mpeg1 = b + o_s1;
+    ctx->T.cs = (const float *)(b + o_cs);
+    ctx->T.ca = (const float *)(b + o_ca);
+    ctx->T.huff_lut_n = (int)h.huff_lut.size();
+    ctx->T.pow2_off = kPow2Off;
+    ctx->lut_bytes = (int)(h.huff_lut.size() * sizeof(uint16_t));
+    return MP3GPU_OK;
+}
+
+extern "C" int mp3gpu_create(int device, const mp3gpu_opts *opts, mp3gpu_ctx **out) {
+    if (!out) return MP3GPU_E_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return MP3GPU_E_NO_DEVICE;
+    mp3gpu_ctx *ctx = new mp3gpu_ctx();
+    ctx->device = device;
+    if (opts) ctx->opts = *opts;
+    ctx->wave = ctx->opts.wave_granules ? ctx->opts.wave_granules : 262144u;
+    auto fail = [&](int rc) {
+        fprintf(stderr, "mp3gpu_create: %s\n", ctx->err.c_str());
+        mp3gpu_destroy(ctx);
+        return rc;
+    };
+    auto init = [&]() -> int {
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+        int rc = upload_tables(ctx);
+        if (rc) return rc;
+        const size_t W = ctx->wave;
+        CK(cudaMalloc(&ctx->d_is16, W * 2 * 576 * sizeof(int16_t)));
+        CK(cudaMalloc(&ctx->d_meta, W * 2 * sizeof(uint32_t)));
+        CK(cudaMalloc(&ctx->d_sfpack, W * 2 * 8 * sizeof(uint32_t)));
+        CK(cudaMalloc(&ctx->d_xr_t, (W + 1) * 2 * 576 * sizeof(float)));
+        CK(cudaMemset(ctx->d_xr_t, 0, 2 * 576 * sizeof(float)));
+        for (int c = 0; c < 2; c++) {
+            CK(cudaMalloc(&ctx->d_hyb[c], (W + 1) * 576 * sizeof(float)));
+            CK(cudaMemset(ctx->d_hyb[c], 0, 576 * sizeof(float)));
+        }
+        for (int i = 0; i < 3; i++) {
+            CK(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
+        }
+        for (int i = 0; i < kTimingSlots; i++)
+            for (int j = 0; j < 5; j++) CK(cudaEventCreate(&ctx->ev_t[i][j]));
+        for (int i = 0; i < 4; i++) CK(cudaEventCreate(&ctx->ev_copy[i]));
+        CK(cudaFuncSetAttribute(k_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->lut_bytes));
+        return MP3GPU_OK;
+    };
+    int rc = init();
+    if (rc) return fail(rc);
+    *out = ctx;
+    return MP3GPU_OK;
+}
+
+extern "C" void mp3gpu_destroy(mp3gpu_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(ctx->d_tab_blob);
+    cudaFree(ctx->d_is16);
+    cudaFree(ctx->d_meta);
+    cudaFree(ctx->d_sfpack);
+    cudaFree(ctx->d_xr_t);
+    cudaFree(ctx->d_hyb[0]);
+    cudaFree(ctx->d_hyb[1]);
+    cudaFree(ctx->d_main);
+    cudaFree(ctx->d_units);
+    for (int i = 0; i < 3; i++) {
+        cudaFree(ctx->d_pcm_ring[i]);
+        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+        if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
+        if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
+    }
+    for (int i = 0; i < kTimingSlots; i++)
+        for (int j = 0; j < 5; j++)
+            if (ctx->ev_t[i][j]) cudaEventDestroy(ctx->ev_t[i][j]);
+    for (int i = 0; i < 4; i++)
+        if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
+    if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    delete ctx;
+}
+
+extern "C" const char *mp3gpu_last_error(const mp3gpu_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+// Launch the four kernels for granules [first, first+n) of the submission on s_compute.
+// d_pcm_wave points at the PCM of granule `first`.  `slot` selects the timing events (or -1).
+static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, const mp3gpu_unit *d_units, long long first, int n,
+                       int16_t *d_pcm_wave, int slot) {
+    WaveBufs B;
+    B.is16 = ctx->d_is16;
+    B.meta = ctx->d_meta;
+    B.sfpack = ctx->d_sfpack;
+    B.xr_t = ctx->d_xr_t + 2 * 576;       // slot -1 lives in front
+    B.hyb[0] = ctx->d_hyb[0] + 576;
+    B.hyb[1] = ctx->d_hyb[1] + 576;
+    cudaStream_t s = ctx->s_compute;
+    if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][0], s));
+    {
+        int nu = 2 * n;
+        k_huffman<<<(nu + 127) / 128, 128, ctx->lut_bytes, s>>>(d_main, d_units, first * 2, nu, ctx->T, B);
+    }
+    if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][1], s));
+    k_requant<<<(n + kK2Warps - 1) / kK2Warps, kK2Warps * 32, 0, s>>>(d_units, first, n, ctx->T, B);
+    if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][2], s));
+    {
+        int runs = (n + kRun - 1) / kRun;
+        int items = runs * 2;
+        k_imdct<<<(items + kK3Warps - 1) / kK3Warps, kK3Warps * 32, 0, s>>>(d_units, first, n, B);
+    }
+    if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][3], s));
+    {
+        long long slots = (long long)n * 18;
+        int grid = (int)((slots + kK4Slots - 1) / kK4Slots);
+        k_synth<<<grid, kK4Threads, 0, s>>>(d_units, first, n, B, d_pcm_wave);
+    }
+    if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][4], s));
+    // Carry the look-back slots for the next wave: last granule's xr_t and hybrid rows -> slot -1.
+    CK(cudaMemcpyAsync(ctx->d_xr_t, B.xr_t + (size_t)(n - 1) * 2 * 576, 2 * 576 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    for (int c = 0; c < 2; c++)
+        CK(cudaMemcpyAsync(ctx->d_hyb[c], B.hyb[c] + (size_t)(n - 1) * 576, 576 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    CK(cudaGetLastError());
+    ctx->last.launches += 4;
+    ctx->last_wave_first = first;
+    ctx->last_wave_granules = (size_t)n;
+    return MP3GPU_OK;
+}
+
+static int collect_timings(mp3gpu_ctx *ctx, int nslots) {
+    float k[4] = {0, 0, 0, 0};
+    for (int i = 0; i < nslots; i++)
+        for (int j = 0; j < 4; j++) {
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, ctx->ev_t[i][j], ctx->ev_t[i][j + 1]));
+            k[j] += ms;
+        }
+    ctx->last.k1_huffman_ms = k[0];
+    ctx->last.k2_requant_ms = k[1];
+    ctx->last.k3_imdct_ms = k[2];
+    ctx->last.k4_synth_ms = k[3];
+    if (nslots > 0) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev_t[0][0], ctx->ev_t[nslots - 1][4]));
+        ctx->last.total_ms = ms;
+    }
+    return MP3GPU_OK;
+}
+
+extern "C" int mp3gpu_decode_device(mp3gpu_ctx *ctx, const uint8_t *d_main_data, size_t main_data_len,
+                                    const mp3gpu_unit *d_units, size_t n_granules, int16_t *d_pcm_out) {
+    if (!ctx) return MP3GPU_E_INVALID;
+    (void)main_data_len;
+    CK(cudaSetDevice(ctx->device));
+    ctx->last = mp3gpu_timings{};
+    if (n_granules == 0) return MP3GPU_OK;
+    int slot = 0;
+    for (size_t first = 0; first < n_granules; first += ctx->wave) {
+        int n = (int)std::min<size_t>(ctx->wave, n_granules - first);
+        int rc = launch_wave(ctx, d_main_data, d_units, (long long)first, n, d_pcm_out + first * 1152,
+                             slot < kTimingSlots ? slot : -1);
+        if (rc) return rc;
+        if (slot < kTimingSlots) slot++;
+        ctx->last.waves++;
+    }
+    CK(cudaStreamSynchronize(ctx->s_compute));
+    return collect_timings(ctx, slot);
+}
+
+template <typename T>
+static int ensure_cap(mp3gpu_ctx *ctx, T **p, size_t *cap, size_t need) {
+    if (*cap >= need) return MP3GPU_OK;
+    if (*p) CK(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    size_t want = need + need / 8 + 256;
+    CK(cudaMalloc(p, want));
+    *cap = want;
+    return MP3GPU_OK;
+}
+
+extern "C" int mp3gpu_decode(mp3gpu_ctx *ctx, const uint8_t *main_data, size_t main_data_len, const mp3gpu_unit *units,
+                             size_t n_granules, int16_t *pcm_out) {
+    if (!ctx) return MP3GPU_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    ctx->last = mp3gpu_timings{};
+    if (n_granules == 0) return MP3GPU_OK;
+    if (!main_data || !units || !pcm_out) {
+        ctx->err = "null pointer";
+        return MP3GPU_E_INVALID;
+    }
+    int rc = ensure_cap(ctx, &ctx->d_main, &ctx->d_main_cap, main_data_len + 64);
+    if (rc) return rc;
+    rc = ensure_cap(ctx, (uint8_t **)&ctx->d_units, &ctx->d_units_cap, n_granules * 2 * sizeof(mp3gpu_unit));
+    if (rc) return rc;
+    const size_t W = ctx->wave;
+    const size_t ring_bytes = std::min<size_t>(W, n_granules) * MP3GPU_PCM_BYTES_PER_GRANULE;
+    for (int i = 0; i < 3; i++)
+        if (!ctx->d_pcm_ring[i]) CK(cudaMalloc(&ctx->d_pcm_ring[i], W * MP3GPU_PCM_BYTES_PER_GRANULE));
+    (void)ring_bytes;
+
+    // Wave w needs main_data up to the end of its last unit's frame buffer.  Units are in stream
+    // order, so the byte ranges are monotonic; each wave uploads only the bytes not yet resident.
+    CK(cudaEventRecord(ctx->ev_copy[0], ctx->s_in));
+    size_t main_resident = 0;
+    int slot = 0;
+    int widx = 0;
+    for (size_t first = 0; first < n_granules; first += W, widx++) {
+        const int n = (int)std::min<size_t>(W, n_granules - first);
+        const int r = widx % 3;
+        // -- H2D on s_in
+        size_t need_end = main_resident;
+        if (first + n >= n_granules) {
+            need_end = main_data_len;
+        } else {
+            // buffer ends are monotonic in stream order: the last valid unit of the wave decides
+            for (size_t u = (first + n) * 2; u-- > first * 2;) {
+                if (!(units[u].w2 & MP3GPU_W2_VALID)) continue;
+                long long e = (long long)units[u].bit_start + units[u].buf_end_rel;
+                size_t eb = e > 0 ? (size_t)((e + 7) >> 3) : 0;
+                need_end = std::max(need_end, eb);
+                break;
+            }
+            need_end = std::min(need_end, main_data_len);
+        }
+        if (need_end > main_resident) {
+            CK(cudaMemcpyAsync(ctx->d_main + main_resident, main_data + main_resident, need_end - main_resident,
+                               cudaMemcpyHostToDevice, ctx->s_in));
+            main_resident = need_end;
+        }
+        CK(cudaMemcpyAsync(ctx->d_units + first * 2, units + first * 2, (size_t)n * 2 * sizeof(mp3gpu_unit),
+                           cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaEventRecord(ctx->ev_in[r], ctx->s_in));
+        // -- kernels on s_compute (wait for inputs and for the ring slot to be drained)
+        CK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_in[r], 0));
+        if (widx >= 3) CK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_out[r], 0));
+        rc = launch_wave(ctx, ctx->d_main, ctx->d_units, (long long)first, n, ctx->d_pcm_ring[r],
+                         slot < kTimingSlots ? slot : -1);
+        if (rc) return rc;
+        if (slot < kTimingSlots) slot++;
+        CK(cudaEventRecord(ctx->ev_k[r], ctx->s_compute));
+        // -- D2H on s_out
+        CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[r], 0));
+        if (widx == 0) CK(cudaEventRecord(ctx->ev_copy[2], ctx->s_out));
+        CK(cudaMemcpyAsync(pcm_out + first * 1152, ctx->d_pcm_ring[r], (size_t)n * MP3GPU_PCM_BYTES_PER_GRANULE,
+                           cudaMemcpyDeviceToHost, ctx->s_out));
+        CK(cudaEventRecord(ctx->ev_out[r], ctx->s_out));
+        ctx->last.waves++;
+    }
+    CK(cudaEventRecord(ctx->ev_copy[1], ctx->s_in));
+    CK(cudaEventRecord(ctx->ev_copy[3], ctx->s_out));
+    CK(cudaStreamSynchronize(ctx->s_in));
+    CK(cudaStreamSynchronize(ctx->s_compute));
+    CK(cudaStreamSynchronize(ctx->s_out));
+    rc = collect_timings(ctx, slot);
+    if (rc) return rc;
+    CK(cudaEventElapsedTime(&ctx->last.h2d_ms, ctx->ev_copy[0], ctx->ev_copy[1]));
+    CK(cudaEventElapsedTime(&ctx->last.d2h_ms, ctx->ev_copy[2], ctx->ev_copy[3]));
+    return MP3GPU_OK;
+}
+
+extern "C" void *mp3gpu_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void mp3gpu_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+extern "C" void *mp3gpu_device_alloc(mp3gpu_ctx *ctx, size_t bytes) {
+    if (!ctx) return nullptr;
+    cudaSetDevice(ctx->device);
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void mp3gpu_device_free(mp3gpu_ctx *ctx, void *p) {
+    if (!ctx || !p) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(p);
+}
+extern "C" int mp3gpu_copy_to_device(mp3gpu_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (!ctx) return MP3GPU_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return MP3GPU_OK;
+}
+extern "C" int mp3gpu_copy_to_host(mp3gpu_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (!ctx) return MP3GPU_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return MP3GPU_OK;
+}
+extern "C" int mp3gpu_synchronize(mp3gpu_ctx *ctx) {
+    if (!ctx) return MP3GPU_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    return MP3GPU_OK;
+}
+
+extern "C" int mp3gpu_last_timings(const mp3gpu_ctx *ctx, mp3gpu_timings *out) {
+    if (!ctx || !out) return MP3GPU_E_INVALID;
+    *out = ctx->last;
+    return MP3GPU_OK;
+}
+
+extern "C" int mp3gpu_debug_read(mp3gpu_ctx *ctx, int tap, size_t first, size_t n, void *host_out) {
+    if (!ctx || !host_out) return MP3GPU_E_INVALID;
+    if (first + n > ctx->last_wave_granules) {
+        ctx->err = "debug_read: range outside the last wave";
+        return MP3GPU_E_INVALID;
+    }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    std::vector<uint32_t> meta(n * 2);
+    CK(cudaMemcpy(meta.data(), ctx->d_meta + first * 2, n * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    switch (tap) {
+    case MP3GPU_TAP_IS: {
+        int16_t *o = (int16_t *)host_out;
+        CK(cudaMemcpy(o, ctx->d_is16 + first * 2 * 576, n * 2 * 576 * sizeof(int16_t), cudaMemcpyDeviceToHost));
+        for (size_t u = 0; u < n * 2; u++) {
+            size_t c1 = meta[u] & 0x3ff;
+            for (size_t i = c1; i < 576; i++) o[u * 576 + i] = 0;  // rzero region (huffman.go:130-134)
+        }
+        return MP3GPU_OK;
+    }
+    case MP3GPU_TAP_COUNT1: {
+        int32_t *o = (int32_t *)host_out;
+        for (size_t u = 0; u < n * 2; u++) o[u] = (int32_t)(meta[u] & 0x3ff);
+        return MP3GPU_OK;
+    }
+    case MP3GPU_TAP_SCALEFAC: {
+        std::vector<uint32_t> pk(n * 2 * 8);
+        CK(cudaMemcpy(pk.data(), ctx->d_sfpack + first * 2 * 8, pk.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        uint8_t *o = (uint8_t *)host_out;
+        for (size_t u = 0; u < n * 2; u++) {
+            for (int k = 0; k < 64; k++) o[u * 64 + k] = (uint8_t)((pk[u * 8 + (k >> 3)] >> (4 * (k & 7))) & 0xf);
+            o[u * 64 + 61] = (uint8_t)((meta[u] >> 10) & 1);
+        }
+        return MP3GPU_OK;
+    }
+    case MP3GPU_TAP_XR: {
+        std::vector<float> t(n * 2 * 576);
+        CK(cudaMemcpy(t.data(), ctx->d_xr_t + (first + 1) * 2 * 576, t.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        float *o = (float *)host_out;
+        for (size_t u = 0; u < n * 2; u++)
+            for (int m = 0; m < 18; m++)
+                for (int sb = 0; sb < 32; sb++) o[u * 576 + sb * 18 + m] = t[u * 576 + m * 32 + sb];
+        return MP3GPU_OK;
+    }
+    case MP3GPU_TAP_HYBRID: {
+        float *o = (float *)host_out;
+        std::vector<float> t(n * 576);
+        for (int c = 0; c < 2; c++) {
+            CK(cudaMemcpy(t.data(), ctx->d_hyb[c] + (first + 1) * 576, t.size() * sizeof(float), cudaMemcpyDeviceToHost));
+            for (size_t g = 0; g < n; g++)
+                for (int i = 0; i < 18; i++)
+                    for (int sb = 0; sb < 32; sb++) o[(g * 2 + c) * 576 + sb * 18 + i] = t[g * 576 + i * 32 + sb];
+        }
+        return MP3GPU_OK;
+    }
+    }
+    ctx->err = "debug_read: unknown tap";
+    return MP3GPU_E_INVALID;
+}
+
+extern "C" int mp3gpu_device_info(mp3gpu_ctx *ctx, char *name, size_t name_len, int *sm_count, int *cc_major, int *cc_minor) {
+    if (!ctx) return MP3GPU_E_INVALID;
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, ctx->device));
+    if (name && name_len) {
+        strncpy(name, p.name, name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    return MP3GPU_OK;
+}
+
+extern "C" int mp3gpu_measure_fp32_peak(mp3gpu_ctx *ctx, double *tflops) {
+    if (!ctx || !tflops) return MP3GPU_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, ctx->device));
+    const int blocks = p.multiProcessorCount * 8, threads = 256, iters = 4096;
+    float *d = nullptr;
+    CK(cudaMalloc(&d, (size_t)blocks * threads * sizeof(float)));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        CK(cudaEventRecord(a, ctx->s_compute));
+        k_fp32_peak<<<blocks, threads, 0, ctx->s_compute>>>(d, iters);
+        CK(cudaEventRecord(b, ctx->s_compute));
+        CK(cudaEventSynchronize(b));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        double flops = (double)blocks * threads * iters * 16.0 * 8.0 * 2.0;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    *tflops = best;
+    return MP3GPU_OK;
+}

@@ -1,0 +1,227 @@
+// tables.cc — see tables.h.
+#include "tables.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+
+namespace mp3gpu {
+
+namespace {
+typedef HuffCode huff_code_t;
+struct huff_table_desc_t {
+    const huff_code_t *codes;
+    int n;
+    int linbits;
+};
+#include "huff_codes.inc"
+#include "synth_window_k.inc"
+
+// consts.go:68-97, order [lsf][sfreq].
+const int kSfbLong[2][3][23] = {
+    {{0, 4, 8, 12, 16, 20, 24, 30, 36, 44, 52, 62, 74, 90, 110, 134, 162, 196, 238, 288, 342, 418, 576},
+     {0, 4, 8, 12, 16, 20, 24, 30, 36, 42, 50, 60, 72, 88, 106, 128, 156, 190, 230, 276, 330, 384, 576},
+     {0, 4, 8, 12, 16, 20, 24, 30, 36, 44, 54, 66, 82, 102, 126, 156, 194, 240, 296, 364, 448, 550, 576}},
+    {{0, 6, 12, 18, 24, 30, 36, 44, 54, 66, 80, 96, 116, 140, 168, 200, 238, 284, 336, 396, 464, 522, 576},
+     {0, 6, 12, 18, 24, 30, 36, 44, 54, 66, 80, 96, 114, 136, 162, 194, 232, 278, 332, 394, 464, 540, 576},
+     {0, 6, 12, 18, 24, 30, 36, 44, 54, 66, 80, 96, 116, 140, 168, 200, 238, 284, 336, 396, 464, 522, 576}}};
+const int kSfbShort[2][3][14] = {{{0, 4, 8, 12, 16, 22, 30, 40, 52, 66, 84, 106, 136, 192},
+                                  {0, 4, 8, 12, 16, 22, 28, 38, 50, 64, 80, 100, 126, 192},
+                                  {0, 4, 8, 12, 16, 22, 30, 42, 58, 78, 104, 138, 180, 192}},
+                                 {{0, 4, 8, 12, 18, 24, 32, 42, 56, 74, 100, 132, 174, 192},
+                                  {0, 4, 8, 12, 18, 26, 36, 48, 62, 80, 104, 136, 180, 192},
+                                  {0, 4, 8, 12, 18, 26, 36, 48, 62, 80, 104, 134, 174, 192}}};
+const int kPretab[22] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 3, 2, 0};
+const int kSfSizeMpeg2[3][6][4] = {
+    {{6, 5, 5, 5}, {6, 5, 7, 3}, {11, 10, 0, 0}, {7, 7, 7, 0}, {6, 6, 6, 3}, {8, 8, 5, 0}},
+    {{9, 9, 9, 9}, {9, 9, 12, 6}, {18, 18, 0, 0}, {12, 12, 12, 0}, {12, 9, 9, 6}, {15, 12, 9, 0}},
+    {{6, 9, 9, 9}, {6, 9, 12, 6}, {15, 18, 0, 0}, {6, 15, 12, 0}, {6, 12, 9, 6}, {6, 18, 9, 0}}};
+
+const long double kPiL = 3.14159265358979323846264338327950288L;
+
+// ---- Huffman LUT construction ------------------------------------------------
+struct LutBuilder {
+    std::vector<uint16_t> &lut;
+    size_t base;
+    const huff_code_t *codes;
+    int n;
+    explicit LutBuilder(std::vector<uint16_t> &l, const huff_code_t *c, int n_) : lut(l), base(l.size()), codes(c), n(n_) {}
+
+    // Fill a table of `bits` index bits for all codes whose first `plen` bits equal `prefix`.
+    void fill(size_t off, int bits, uint32_t prefix, int plen, int sub_cap) {
+        for (uint32_t idx = 0; idx < (1u << bits); idx++) {
+            // Is there a code of length <= plen+bits that is a prefix of (prefix,idx)?
+            int found = -1;
+            for (int i = 0; i < n; i++) {
+                int L = codes[i].hlen;
+                if (L <= plen || L > plen + bits) continue;
+                uint32_t full = (prefix << bits) | idx;            // plen+bits bits
+                if ((full >> (plen + bits - L)) == codes[i].hcod) { found = i; break; }
+            }
+            if (found >= 0) {
+                lut[base + off + idx] = (uint16_t)((codes[found].hlen << 8) | (codes[found].x << 4) | codes[found].y);
+                continue;
+            }
+            // Need a sub-table: longest remaining length among codes with this (plen+bits)-bit prefix.
+            uint32_t full = (prefix << bits) | idx;
+            int maxrem = 0;
+            for (int i = 0; i < n; i++) {
+                int L = codes[i].hlen;
+                if (L <= plen + bits) continue;
+                if ((codes[i].hcod >> (L - plen - bits)) == full) maxrem = std::max(maxrem, L - plen - bits);
+            }
+            if (maxrem == 0) throw std::runtime_error("huffman tree not complete");
+            int sb = std::min(maxrem, sub_cap);
+            size_t sub_off = lut.size() - base;
+            if (sub_off > 0xfff) throw std::runtime_error("huffman LUT too large");
+            lut.resize(lut.size() + (1u << sb), 0);
+            lut[base + off + idx] = (uint16_t)(0x8000u | ((uint32_t)(sb - 1) << 12) | (uint32_t)sub_off);
+            fill(sub_off, sb, full, plen + bits, sub_cap);
+        }
+    }
+};
+
+}  // namespace
+
+int huff_table_codes(int table_num, const HuffCode **codes, int *linbits) {
+    if (table_num < 0 || table_num > 33) return -1;
+    *codes = HUFF_TABLES[table_num].codes;
+    *linbits = HUFF_TABLES[table_num].linbits;
+    return HUFF_TABLES[table_num].n;
+}
+
+void build_host_tables(HostTables &t) {
+    // imdct.go:23-57
+    const double pi36 = (double)(kPiL / 36.0L), pi12 = (double)(kPiL / 12.0L);
+    float(*w)[36] = reinterpret_cast<float(*)[36]>(t.imdct_win);
+    for (int i = 0; i < 36; i++) w[0][i] = (float)std::sin(pi36 * ((double)i + 0.5));
+    for (int i = 0; i < 18; i++) w[1][i] = (float)std::sin(pi36 * ((double)i + 0.5));
+    for (int i = 18; i < 24; i++) w[1][i] = 1.0f;
+    for (int i = 24; i < 30; i++) w[1][i] = (float)std::sin(pi12 * ((double)i + 0.5 - 18.0));
+    for (int i = 30; i < 36; i++) w[1][i] = 0.0f;
+    for (int i = 0; i < 12; i++) w[2][i] = (float)std::sin(pi12 * ((double)i + 0.5));
+    for (int i = 12; i < 36; i++) w[2][i] = 0.0f;
+    for (int i = 0; i < 6; i++) w[3][i] = 0.0f;
+    for (int i = 6; i < 12; i++) w[3][i] = (float)std::sin(pi12 * ((double)i + 0.5 - 6.0));
+    for (int i = 12; i < 18; i++) w[3][i] = 1.0f;
+    for (int i = 18; i < 36; i++) w[3][i] = (float)std::sin(pi36 * ((double)i + 0.5));
+    // imdct.go:61-79
+    const double pi24 = (double)(kPiL / 24.0L), pi72 = (double)(kPiL / 72.0L);
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 12; j++)
+            t.cos12[i * 12 + j] = (float)std::cos(pi24 * (2.0 * (double)j + 1.0 + 6.0) * (2.0 * (double)i + 1.0));
+    for (int i = 0; i < 18; i++)
+        for (int j = 0; j < 36; j++)
+            t.cos36[i * 36 + j] = (float)std::cos(pi72 * (2.0 * (double)j + 1.0 + 18.0) * (2.0 * (double)i + 1.0));
+    // frame.go:490-497
+    const double pi64 = (double)(kPiL / 64.0L);
+    for (int i = 0; i < 64; i++)
+        for (int j = 0; j < 32; j++) t.synth_n[i * 32 + j] = (float)std::cos((double)((16 + i) * (2 * j + 1)) * pi64);
+    // frame.go:499-628: 9-decimal literals of k/65536
+    for (int i = 0; i < 512; i++) {
+        long long k = SYNTH_WINDOW_K[i];
+        long long a = k < 0 ? -k : k;
+        long long n = (a * 1000000000LL + 32768) / 65536;
+        char lit[40];
+        snprintf(lit, sizeof lit, "%s%lld.%09lld", k < 0 ? "-" : "", n / 1000000000LL, n % 1000000000LL);
+        t.synth_d[i] = strtof(lit, nullptr);
+    }
+    // frame.go:146-148,161-166: math.Pow(2.0, idx) with idx a multiple of 0.25
+    for (int k = 0; k < kPow2N; k++) t.pow2q[k] = std::pow(2.0, (double)(k - kPow2Off) * 0.25);
+    // frame.go:36-40
+    t.powtab34.resize(8207);
+    for (int i = 0; i < 8207; i++) t.powtab34[i] = std::pow((double)i, 4.0 / 3.0);
+    // frame.go:422-425 (decimal literals rounded once to float32)
+    const float cs[8] = {0.857493f, 0.881742f, 0.949629f, 0.983315f, 0.995518f, 0.999161f, 0.999899f, 0.999993f};
+    const float ca[8] = {-0.514496f, -0.471732f, -0.313377f, -0.181913f, -0.094574f, -0.040966f, -0.014199f, -0.003700f};
+    memcpy(t.cs, cs, sizeof cs);
+    memcpy(t.ca, ca, sizeof ca);
+    // frame.go:304-327: float32 division, as the reference does per band
+    const float isr[6] = {0.000000f, 0.267949f, 0.577350f, 1.000000f, 1.732051f, 3.732051f};
+    for (int p = 0; p < 6; p++) {
+        volatile float den = 1.0f + isr[p];
+        t.is_ratio_l[p] = isr[p] / den;
+        t.is_ratio_r[p] = 1.0f / den;
+    }
+    t.is_ratio_l[6] = 1.0f;
+    t.is_ratio_r[6] = 0.0f;
+    t.is_ratio_l[7] = 1.0f;  // unused (is_pos >= 7: no intensity processing)
+    t.is_ratio_r[7] = 1.0f;
+    memset(t.pretab, 0, sizeof t.pretab);
+    for (int i = 0; i < 22; i++) t.pretab[i] = (uint8_t)kPretab[i];
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 6; b++)
+            for (int c = 0; c < 4; c++) t.sfsize_mpeg2[a][b][c] = (uint8_t)kSfSizeMpeg2[a][b][c];
+
+    for (int lsf = 0; lsf < 2; lsf++)
+        for (int sf = 0; sf < 3; sf++) {
+            int cfg = lsf * 3 + sf;
+            memset(t.sfb_long[cfg], 0, sizeof t.sfb_long[cfg]);
+            memset(t.sfb_short[cfg], 0, sizeof t.sfb_short[cfg]);
+            for (int i = 0; i < 23; i++) t.sfb_long[cfg][i] = (uint16_t)kSfbLong[lsf][sf][i];
+            for (int i = 0; i < 14; i++) t.sfb_short[cfg][i] = (uint16_t)kSfbShort[lsf][sf][i];
+            for (int sfb = 0; sfb < 22; sfb++)
+                for (int i = kSfbLong[lsf][sf][sfb]; i < kSfbLong[lsf][sf][sfb + 1]; i++) t.line_sfb_long[cfg][i] = (uint8_t)sfb;
+            for (int sfb = 0; sfb < 13; sfb++) {
+                int s = kSfbShort[lsf][sf][sfb] * 3;
+                int wl = kSfbShort[lsf][sf][sfb + 1] - kSfbShort[lsf][sf][sfb];
+                for (int win = 0; win < 3; win++)
+                    for (int j = 0; j < wl; j++) {
+                        int i = s + win * wl + j;
+                        t.line_sfb_short[cfg][i] = (uint8_t)sfb;
+                        t.line_win_short[cfg][i] = (uint8_t)win;
+                        t.reorder_dst[cfg][i] = (uint16_t)(s + j * 3 + win);  // frame.go:291-296
+                    }
+            }
+        }
+    // maindata.go:54-81
+    memset(t.nslen2, 0, sizeof t.nslen2);
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 3; j++) t.nslen2[j + i * 3 + 500] = (uint16_t)(i | (j << 3) | (2 << 12) | (1 << 15));
+    for (int i = 0; i < 5; i++)
+        for (int j = 0; j < 5; j++)
+            for (int k = 0; k < 4; k++)
+                for (int l = 0; l < 4; l++) t.nslen2[l + k * 4 + j * 16 + i * 80] = (uint16_t)(i | (j << 3) | (k << 6) | (l << 9));
+    for (int i = 0; i < 5; i++)
+        for (int j = 0; j < 5; j++)
+            for (int k = 0; k < 4; k++) t.nslen2[k + j * 4 + i * 20 + 400] = (uint16_t)(i | (j << 3) | (k << 6) | (1 << 12));
+
+    // Huffman LUTs: one per distinct tree; tables sharing a tree share the LUT.
+    t.huff_lut.clear();
+    // entry 0..1: the "empty table" LUT (root bits 1, two zero-length zero leaves)
+    t.huff_lut.push_back(0);
+    t.huff_lut.push_back(0);
+    const uint32_t empty_desc = 0u | (1u << 16);
+    const huff_code_t *seen[34];
+    uint32_t seen_desc[34];
+    int nseen = 0;
+    for (int tab = 0; tab < 34; tab++) {
+        const huff_table_desc_t &d = HUFF_TABLES[tab];
+        if (d.codes == nullptr) {
+            t.huff_desc[tab] = empty_desc;
+            continue;
+        }
+        uint32_t desc = 0;
+        bool have = false;
+        for (int s = 0; s < nseen; s++)
+            if (seen[s] == d.codes) { desc = seen_desc[s]; have = true; }
+        if (!have) {
+            int maxlen = 0;
+            for (int i = 0; i < d.n; i++) maxlen = std::max(maxlen, (int)d.codes[i].hlen);
+            int root = std::min(maxlen, 8);
+            LutBuilder b(t.huff_lut, d.codes, d.n);
+            if (b.base > 0xffff) throw std::runtime_error("huffman LUT base overflow");
+            t.huff_lut.resize(t.huff_lut.size() + (1u << root), 0);
+            b.fill(0, root, 0, 0, 6);
+            desc = (uint32_t)b.base | ((uint32_t)root << 16);
+            seen[nseen] = d.codes;
+            seen_desc[nseen] = desc;
+            nseen++;
+        }
+        t.huff_desc[tab] = desc | ((uint32_t)d.linbits << 20);
+    }
+}
+
+}  // namespace mp3gpu

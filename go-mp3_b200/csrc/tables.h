@@ -1,0 +1,59 @@
+// tables.h — host-side construction of every constant table the device kernels use.
+//
+// Formulas follow the reference's table initialisers (paths relative to the reference root):
+//   internal/imdct/imdct.go:21-79      IMDCT windows and cosine tables
+//   internal/frame/frame.go:31-40      powtab34, pretab
+//   internal/frame/frame.go:304-306    isRatios;  :422-425 cs/ca
+//   internal/frame/frame.go:488-628    synthNWin, synthDtbl
+//   internal/maindata/maindata.go:39-81 scalefactor size tables, nSlen2
+//   internal/consts/consts.go:68-97    scalefactor band indices
+//   internal/huffman/huffman.go:23-346 Huffman code tables (here: ISO (x,y,hlen,hcod) form,
+//                                      expanded into multi-level lookup tables)
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace mp3gpu {
+
+constexpr int kPow2Off = 336;   // pow2q index = 4*idx + kPow2Off ; 4*idx in [-326, 45]
+constexpr int kPow2N = 400;
+constexpr int kNumCfg = 6;      // cfg = lsf*3 + sampling_frequency index
+
+// Huffman LUT entry (uint16):
+//   leaf : bit15 = 0, bits 8..12 = total code length (0..19), bits 4..7 = x, bits 0..3 = y
+//   link : bit15 = 1, bits 12..14 = (sub-table index bits - 1), bits 0..11 = sub-table offset
+//          relative to the tree's base
+// Table descriptor (uint32): bits 0..15 = LUT base offset, bits 16..19 = root index bits,
+// bits 20..23 = linbits.  Tables 0/4/14 (empty: huffman.go:354-356) map to a 2-entry
+// all-zero leaf table of length 0 so that they consume nothing.
+struct HostTables {
+    float cos36[18 * 36];
+    float cos12[6 * 12];
+    float imdct_win[4 * 36];
+    float synth_n[64 * 32];
+    float synth_d[512];
+    double pow2q[kPow2N];
+    std::vector<double> powtab34;  // 8207
+    float cs[8], ca[8];
+    float is_ratio_l[8], is_ratio_r[8];  // index = is_pos 0..6
+    uint8_t pretab[24];
+    uint16_t sfb_long[kNumCfg][24];
+    uint16_t sfb_short[kNumCfg][16];
+    uint8_t line_sfb_long[kNumCfg][576];
+    uint8_t line_sfb_short[kNumCfg][576];  // for window-major index i within short sfbs
+    uint8_t line_win_short[kNumCfg][576];
+    uint16_t reorder_dst[kNumCfg][576];
+    uint16_t nslen2[512];
+    uint8_t sfsize_mpeg2[3][6][4];
+    std::vector<uint16_t> huff_lut;
+    uint32_t huff_desc[34];
+};
+
+// Builds all tables.  Pure host code (libm); deterministic.
+void build_host_tables(HostTables &t);
+
+// Access to the raw ISO code list, for the stream synthesiser (encoder side).
+struct HuffCode { uint8_t x, y, hlen; uint32_t hcod; };
+int huff_table_codes(int table_num, const HuffCode **codes, int *linbits);
+
+}  // namespace mp3gpu

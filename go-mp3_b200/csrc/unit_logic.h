@@ -1,0 +1,412 @@
+// unit_logic.h — per-unit / per-line logic of K1 (scalefactors + Huffman) and K2 (requantise,
+// reorder, stereo, alias reduction), written as __host__ __device__ functions.
+//
+// The CUDA kernels in kernels.cuh call these from device code.  tests/hostemu compiles the very
+// same functions for the host so that `-m "not gpu"` tests can check the bit-level logic against
+// the oracle without a GPU.  The host build is test infrastructure only: no product entry point
+// calls it, and the C ABI has no CPU path.
+//
+// Reference being restated (paths relative to the reference root):
+//   internal/bits/bits.go:45-86, internal/huffman/huffman.go:348-419,
+//   internal/maindata/huffman.go:27-138, internal/maindata/maindata.go:119-288,
+//   internal/frame/frame.go:140-452
+#pragma once
+#include <stdint.h>
+
+#include "../../include/mp3gpu.h"
+
+#if defined(__CUDACC__)
+#define MP3_HD __host__ __device__ __forceinline__
+#else
+#define MP3_HD inline
+#endif
+
+namespace mp3gpu {
+
+// Tables indexed per lane (divergent): global memory on the device, plain memory in hostemu.
+struct DeviceTables {
+    const double *pow2q;            // [kPow2N], index 4*idx + pow2_off
+    const double *powtab34;         // [8207]
+    const uint8_t *line_sfb_long;   // [6][576]
+    const uint8_t *line_sfb_short;  // [6][576]
+    const uint8_t *line_win_short;  // [6][576]
+    const uint16_t *reorder_dst;    // [6][576]
+    const uint16_t *sfb_long;       // [6][24]
+    const uint16_t *sfb_short;      // [6][16]
+    const uint16_t *nslen2;         // [512]
+    const uint16_t *huff_lut;       // LUT entries (see tables.h)
+    const uint32_t *huff_desc;      // [34]
+    const float *is_ratio_l;        // [8]
+    const float *is_ratio_r;        // [8]
+    const uint8_t *pretab;          // [24]
+    const uint8_t *sfsize_mpeg2;    // [3][6][4]
+    const uint8_t *slen_mpeg1;      // [16][2]
+    const float *cs;                // [8]
+    const float *ca;                // [8]
+    int huff_lut_n;
+    int pow2_off;
+};
+
+// ---- side-info field accessors ---------------------------------------------------------------
+MP3_HD int u_p23len(uint32_t w0) { return (int)(w0 & 0xfff); }
+MP3_HD int u_bigval(uint32_t w0) { return (int)((w0 >> 12) & 0x1ff); }
+MP3_HD int u_ggain(uint32_t w0) { return (int)((w0 >> 21) & 0xff); }
+MP3_HD int u_winsw(uint32_t w0) { return (int)((w0 >> 29) & 1); }
+MP3_HD int u_btype(uint32_t w0) { return (int)((w0 >> 30) & 3); }
+MP3_HD int u_sfcomp(uint32_t w1) { return (int)(w1 & 0x1ff); }
+MP3_HD int u_tsel(uint32_t w1, int r) { return (int)((w1 >> (9 + 5 * r)) & 0x1f); }
+MP3_HD int u_reg0(uint32_t w1) { return (int)((w1 >> 24) & 0xf); }
+MP3_HD int u_reg1(uint32_t w1) { return (int)((w1 >> 28) & 0xf); }
+MP3_HD int u_sbg(uint32_t w2, int w) { return (int)((w2 >> (3 * w)) & 7); }
+MP3_HD int u_preflag(uint32_t w2) { return (int)((w2 >> 9) & 1); }
+MP3_HD int u_sfscale(uint32_t w2) { return (int)((w2 >> 10) & 1); }
+MP3_HD int u_c1tsel(uint32_t w2) { return (int)((w2 >> 11) & 1); }
+MP3_HD int u_scfsi(uint32_t w2) { return (int)((w2 >> 12) & 0xf); }
+MP3_HD int u_lsf(uint32_t w2) { return (int)((w2 >> 16) & 1); }
+MP3_HD int u_sfreq(uint32_t w2) { return (int)((w2 >> 17) & 3); }
+MP3_HD int u_mode(uint32_t w2) { return (int)((w2 >> 19) & 3); }
+MP3_HD int u_modeext(uint32_t w2) { return (int)((w2 >> 21) & 3); }
+MP3_HD int u_gr(uint32_t w2) { return (int)((w2 >> 23) & 1); }
+MP3_HD bool u_valid(uint32_t w2) { return (w2 & MP3GPU_W2_VALID) != 0; }
+MP3_HD bool u_zero(uint32_t w2) { return (w2 & MP3GPU_W2_ZERO_STATE) != 0; }
+MP3_HD int u_mixed(uint32_t w2) { return (int)((w2 >> 27) & 1); }
+
+MP3_HD int imin(int a, int b) { return a < b ? a : b; }
+
+// ---- rounding-exact float helpers (no contraction on either side) -----------------------------
+#if defined(__CUDA_ARCH__)
+MP3_HD float f_mul(float a, float b) { return __fmul_rn(a, b); }
+MP3_HD float f_add(float a, float b) { return __fadd_rn(a, b); }
+MP3_HD float f_sub(float a, float b) { return __fsub_rn(a, b); }
+MP3_HD float d_mul_to_f(double a, double b) { return __double2float_rn(__dmul_rn(a, b)); }
+MP3_HD uint32_t load_be32(const uint32_t *p) { return __byte_perm(__ldg(p), 0, 0x0123); }
+#else
+MP3_HD float f_mul(float a, float b) { volatile float r = a * b; return r; }
+MP3_HD float f_add(float a, float b) { volatile float r = a + b; return r; }
+MP3_HD float f_sub(float a, float b) { volatile float r = a - b; return r; }
+MP3_HD float d_mul_to_f(double a, double b) { volatile double r = a * b; return (float)r; }
+MP3_HD uint32_t load_be32(const uint32_t *p) { return __builtin_bswap32(*p); }
+#endif
+
+// ---- bit cursor with bits.go semantics ----------------------------------------------------------
+struct BitCursor {
+    const uint32_t *words;  // main_data viewed as aligned 32-bit words
+    uint64_t buf;           // MSB-first window; bits past `avail` (and past the buffer end) are 0
+    int avail;              // valid bits in buf
+    long long next_bit;     // absolute bit index of the next word to load
+    long long end_abs;      // absolute bit index one past the frame's logical buffer
+    int pos;                // logical position relative to bit_start (BitPos() rebased to part2Start)
+    int lim;                // max(buf_end_rel, 0): pos never advances past it (bits.go:46-49)
+
+    MP3_HD void init(const uint8_t *main_data, uint64_t bit_start, int buf_end_rel) {
+        words = reinterpret_cast<const uint32_t *>(main_data);
+        end_abs = (long long)bit_start + buf_end_rel;
+        lim = buf_end_rel > 0 ? buf_end_rel : 0;
+        pos = 0;
+        next_bit = (long long)(bit_start & ~31ull);
+        int o = (int)(bit_start & 31);
+        uint32_t w = load_word();
+        buf = ((uint64_t)w << 32) << o;
+        avail = 32 - o;
+    }
+    // Next aligned word in big-endian bit order, bits at/after end_abs forced to zero.
+    MP3_HD uint32_t load_word() {
+        long long rem = end_abs - next_bit;
+        uint32_t w = 0;
+        if (rem > 0) {
+            w = load_be32(words + (next_bit >> 5));
+            if (rem < 32) w &= ~(0xffffffffu >> (int)rem);
+        }
+        next_bit += 32;
+        return w;
+    }
+    MP3_HD void refill() {
+        if (avail <= 32) {
+            uint32_t w = load_word();
+            buf |= (uint64_t)w << (32 - avail);
+            avail += 32;
+        }
+    }
+    MP3_HD uint32_t peek(int n) const { return (uint32_t)(buf >> (64 - n)); }
+    // Bit()-style consumption (tree bits, sign bits): the cursor clamps at the buffer end.
+    MP3_HD void skip(int n) {
+        buf <<= n;
+        avail -= n;
+        pos = imin(pos + n, lim);
+    }
+    // Bits(n), bits.go:58-77: returns 0 WITHOUT advancing when the read would cross the end.
+    MP3_HD int bits(int n) {
+        if (n == 0) return 0;
+        if (pos + n > lim) return 0;
+        refill();
+        int v = (int)peek(n);
+        skip(n);
+        return v;
+    }
+    MP3_HD int bit() {
+        refill();
+        int v = (int)(buf >> 63);
+        skip(1);
+        return v;
+    }
+};
+
+MP3_HD uint32_t huff_lookup(const uint16_t *lut, uint32_t desc, const BitCursor &bc) {
+    uint32_t base = desc & 0xffff;
+    int rb = (int)((desc >> 16) & 0xf);
+    uint32_t e = lut[base + bc.peek(rb)];
+    int used = rb;
+    while (e & 0x8000u) {  // rare: code longer than the root index
+        int sb = (int)((e >> 12) & 7) + 1;
+        uint32_t idx = (e & 0xfff) + (uint32_t)((bc.buf << used) >> (64 - sb));
+        e = lut[base + idx];
+        used += sb;
+    }
+    return e;
+}
+
+// One big_values pair (huffman.go:404-416).  Returns x | y<<16 (int16 halves).
+MP3_HD uint32_t huff_pair(const uint16_t *lut, uint32_t desc, BitCursor &bc) {
+    bc.refill();
+    uint32_t e = huff_lookup(lut, desc, bc);
+    int len = (int)((e >> 8) & 0x1f);
+    int x = (int)((e >> 4) & 0xf), y = (int)(e & 0xf);
+    int linbits = (int)((desc >> 20) & 0xf);
+    bc.skip(len);
+    if (linbits != 0 && (x == 15 || y == 15)) {
+        if (x == 15) x += bc.bits(linbits);
+        if (x != 0 && bc.bit()) x = -x;
+        if (y == 15) y += bc.bits(linbits);
+        if (y != 0 && bc.bit()) y = -y;
+    } else {
+        int nx = x != 0, ny = y != 0;
+        uint32_t two = bc.peek(2);  // >= 13 valid bits remain after the tree bits
+        int sx = nx ? (int)(two >> 1) : 0;
+        int sy = ny ? (int)((nx ? two : (two >> 1)) & 1) : 0;
+        bc.skip(nx + ny);
+        x = sx ? -x : x;
+        y = sy ? -y : y;
+    }
+    return ((uint32_t)x & 0xffffu) | ((uint32_t)y << 16);
+}
+
+// One count1 quadruple (huffman.go:387-403): v, w, x, y each in {-1, 0, 1}.
+MP3_HD void huff_quad(const uint16_t *lut, uint32_t desc, BitCursor &bc, int &v, int &w, int &x, int &y) {
+    bc.refill();
+    uint32_t e = huff_lookup(lut, desc, bc);
+    int len = (int)((e >> 8) & 0x1f);
+    int q = (int)(e & 0xf);
+    bc.skip(len);  // <= 6 tree bits + 4 sign bits < 33 buffered bits: no refill needed below
+    v = (q >> 3) & 1;
+    w = (q >> 2) & 1;
+    x = (q >> 1) & 1;
+    y = q & 1;
+    uint32_t four = bc.peek(4);
+    int used = 0;
+    if (v) { if ((four >> (3 - used)) & 1) v = -1; used++; }
+    if (w) { if ((four >> (3 - used)) & 1) w = -1; used++; }
+    if (x) { if ((four >> (3 - used)) & 1) x = -1; used++; }
+    if (y) { if ((four >> (3 - used)) & 1) y = -1; used++; }
+    bc.skip(used);
+}
+
+MP3_HD void sf_put(uint32_t *pk, int n, int v) { pk[n >> 3] |= (uint32_t)v << (4 * (n & 7)); }
+MP3_HD int sf_nib(const uint32_t *pk, int n) { return (int)((pk[n >> 3] >> (4 * (n & 7))) & 0xf); }
+
+// Scalefactors of an MPEG-1 unit that reads all of them itself: gr 0, or gr 1 short blocks, or
+// gr 1 with no scfsi band set (maindata.go:204-232 and the read arms of :233-279).
+MP3_HD void sf_mpeg1_read_all(const DeviceTables &T, BitCursor &bc, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t *pk) {
+    int sfc = u_sfcomp(w1) & 15;
+    int slen1 = T.slen_mpeg1[sfc * 2], slen2 = T.slen_mpeg1[sfc * 2 + 1];
+    if (u_winsw(w0) == 1 && u_btype(w0) == 2) {
+        int sfb0 = 0;
+        if (u_mixed(w2)) {
+            for (int sfb = 0; sfb < 8; sfb++) sf_put(pk, sfb, bc.bits(slen1));
+            sfb0 = 3;
+        }
+        for (int sfb = sfb0; sfb < 12; sfb++) {
+            int nb = sfb < 6 ? slen1 : slen2;
+            for (int win = 0; win < 3; win++) sf_put(pk, 22 + sfb * 3 + win, bc.bits(nb));
+        }
+    } else {
+        for (int sfb = 0; sfb < 21; sfb++) sf_put(pk, sfb, bc.bits(sfb < 11 ? slen1 : slen2));
+    }
+}
+
+// K1 body for one unit.  `units` is the whole submission (absolute indexing): a gr-1 unit with
+// scfsi set re-reads gr 0's scalefactor bits (maindata.go:239-278, quirk Q14).
+// Outputs: pk[8] scalefactor nibbles (n = sfb for scalefac_l, 22 + sfb*3 + win for scalefac_s),
+// is_out[0..count1/2) packed int16 pairs, return value meta = count1 | preflag << 10.
+MP3_HD uint32_t huffman_unit(const DeviceTables &T, const uint16_t *lut, const uint32_t *huff_desc,
+                             const uint8_t *main_data, const mp3gpu_unit *units, long long unit_index,
+                             uint32_t *pk, uint32_t *is_out) {
+    const mp3gpu_unit u = units[unit_index];
+    const uint32_t w0 = u.w0, w1 = u.w1, w2 = u.w2;
+    BitCursor bc;
+    bc.init(main_data, u.bit_start, u.buf_end_rel);
+    for (int i = 0; i < 8; i++) pk[i] = 0;
+
+    // ---- part 2: scalefactors -------------------------------------------------------------
+    int preflag = u_preflag(w2);
+    if (u_lsf(w2)) {
+        // maindata.go:132-179
+        int slen = T.nslen2[u_sfcomp(w1)];
+        preflag = (slen >> 15) & 1;
+        int n = 0;
+        if (u_btype(w0) == 2) {
+            n++;
+            if (u_mixed(w2)) n++;
+        }
+        int d = (slen >> 12) & 7;
+        int idx = 0;
+        for (int i = 0; i < 4; i++) {
+            int num = slen & 7;
+            slen >>= 3;
+            int cnt = T.sfsize_mpeg2[(n * 6 + d) * 4 + i];
+            for (int k = 0; k < cnt; k++) {
+                int v = num > 0 ? bc.bits(num) : 0;
+                // long blocks fill scalefac_l[idx]; short fill scalefac_s[idx/3][idx%3] (maindata.go:169-179)
+                int nib = (n == 0) ? idx : 22 + idx;
+                if (nib < 64) sf_put(pk, nib, v);
+                idx++;
+            }
+        }
+    } else if (u_gr(w2) == 0 || (u_winsw(w0) == 1 && u_btype(w0) == 2) || u_scfsi(w2) == 0) {
+        sf_mpeg1_read_all(T, bc, w0, w1, w2, pk);
+    } else {
+        // gr 1, long-type block, at least one scfsi band set: those bands copy ScalefacL[0][ch]
+        // as gr 0's parse left it (zeros if gr 0 was short; sfb 0-7 only if gr 0 was mixed).
+        const mp3gpu_unit u0 = units[unit_index - 2];
+        uint32_t pk0[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        {
+            BitCursor b0;
+            b0.init(main_data, u0.bit_start, u0.buf_end_rel);
+            sf_mpeg1_read_all(T, b0, u0.w0, u0.w1, u0.w2, pk0);
+        }
+        int sfc = u_sfcomp(w1) & 15;
+        int slen1 = T.slen_mpeg1[sfc * 2], slen2 = T.slen_mpeg1[sfc * 2 + 1];
+        int scfsi = u_scfsi(w2);
+        for (int sfb = 0; sfb < 21; sfb++) {
+            int band = sfb < 6 ? 0 : (sfb < 11 ? 1 : (sfb < 16 ? 2 : 3));
+            int v;
+            if ((scfsi >> band) & 1)
+                v = sf_nib(pk0, sfb);
+            else
+                v = bc.bits(sfb < 11 ? slen1 : slen2);
+            sf_put(pk, sfb, v);
+        }
+    }
+
+    // ---- part 3: Huffman (maindata/huffman.go:27-138) ---------------------------------------
+    const int p23 = u_p23len(w0);
+    if (p23 == 0) return (uint32_t)preflag << 10;  // Q1: nothing decoded, Count1 stays 0
+    const int bit_pos_end = p23 - 1;               // part2Start is position 0 of this cursor
+    int r1h, r2h;                                  // region starts in PAIRS (all sfb boundaries are even)
+    if (u_winsw(w0) == 1 && u_btype(w0) == 2) {
+        r1h = 18;
+        r2h = 288;
+    } else {
+        const uint16_t *l = T.sfb_long + (u_lsf(w2) * 3 + u_sfreq(w2)) * 24;
+        int i = u_reg0(w1) + 1;  // <= 16 < 23
+        r1h = l[i] >> 1;
+        int j = u_reg0(w1) + u_reg1(w1) + 2;
+        r2h = j >= 23 ? 288 : (l[j] >> 1);
+    }
+    int nbig = u_bigval(w0);
+    if (nbig > 288) nbig = 288;  // the host rejects such frames (huffman.go:68-70); never reached
+    int k = 0;
+    {
+        uint32_t d0 = huff_desc[u_tsel(w1, 0)];
+        int e0 = imin(nbig, r1h);
+        for (; k < e0; k++) is_out[k] = huff_pair(lut, d0, bc);
+        uint32_t d1 = huff_desc[u_tsel(w1, 1)];
+        int e1 = imin(nbig, r2h);
+        for (; k < e1; k++) is_out[k] = huff_pair(lut, d1, bc);
+        uint32_t d2 = huff_desc[u_tsel(w1, 2)];
+        for (; k < nbig; k++) is_out[k] = huff_pair(lut, d2, bc);
+    }
+    int is_pos = nbig * 2;
+    {
+        uint32_t dq = huff_desc[32 + u_c1tsel(w2)];
+        while (is_pos <= 572 && bc.pos <= bit_pos_end) {
+            int v, w, x, y;
+            huff_quad(lut, dq, bc, v, w, x, y);
+            is_out[is_pos >> 1] = ((uint32_t)v & 0xffffu) | ((uint32_t)w << 16);
+            is_out[(is_pos >> 1) + 1] = ((uint32_t)x & 0xffffu) | ((uint32_t)y << 16);
+            is_pos += 4;
+        }
+    }
+    if (bc.pos > bit_pos_end + 1) is_pos -= 4;  // overshoot: drop the last quadruple (huffman.go:119-122)
+    if (is_pos < 0) is_pos = 0;
+    return (uint32_t)is_pos | ((uint32_t)preflag << 10);
+    // Lines >= count1 are zero by definition; K2 masks them instead of K1 writing zeros.
+}
+
+// ---- K2 per-line logic ---------------------------------------------------------------------------
+struct GranuleChan {  // decoded side info K2 needs for one channel
+    uint32_t w0, w1, w2;
+    int cnt1, preflag;
+    bool is_short, mixed;
+};
+MP3_HD GranuleChan make_chan(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t meta) {
+    GranuleChan c;
+    c.w0 = w0; c.w1 = w1; c.w2 = w2;
+    c.cnt1 = (int)(meta & 0x3ff);
+    c.preflag = (int)((meta >> 10) & 1);
+    c.is_short = u_winsw(w0) == 1 && u_btype(w0) == 2;
+    c.mixed = c.is_short && u_mixed(w2) != 0;
+    return c;
+}
+
+// Requantise line i (frame.go:140-255) and return its position after reorder (frame.go:257-302).
+// Lines at or above count1 hold 0 (rzero) and requantise to +0.0 exactly as the untouched zeros
+// of the reference do.
+MP3_HD float requant_line(const DeviceTables &T, int cfg, const GranuleChan &c, const uint32_t *pk, int i, int is_val, int *dst) {
+    const int mult = u_sfscale(c.w2) ? 4 : 2;  // 4 * sfMult
+    const int gg = u_ggain(c.w0) - 210;
+    int v = i < c.cnt1 ? is_val : 0;
+    int k4;
+    if (c.is_short && (!c.mixed || i >= 36)) {
+        int sfb = T.line_sfb_short[cfg * 576 + i], win = T.line_win_short[cfg * 576 + i];
+        k4 = gg - 8 * u_sbg(c.w2, win) - mult * sf_nib(pk, 22 + sfb * 3 + win);
+        *dst = T.reorder_dst[cfg * 576 + i];
+    } else {
+        int sfb = T.line_sfb_long[cfg * 576 + i];
+        k4 = gg - mult * (sf_nib(pk, sfb) + c.preflag * (int)T.pretab[sfb]);
+        *dst = i;
+    }
+    double a = T.powtab34[v < 0 ? -v : v];
+    return d_mul_to_f(T.pow2q[k4 + T.pow2_off], v < 0 ? -a : a);
+}
+
+// Intensity-stereo position of line i, or 7 if the line is not intensity coded.
+// Channel 0's block type and scalefactors decide (frame.go:312,340,385-419); the short-block
+// window index is taken from the pre-reorder layout although the data is already reordered
+// (frame.go:341-357) — kept as is.
+MP3_HD int intensity_pos(const DeviceTables &T, int cfg, const GranuleChan &c0, const uint32_t *pk0, int cnt1_r, int i) {
+    if (c0.is_short && (!c0.mixed || i >= 36)) {
+        int sfb = T.line_sfb_short[cfg * 576 + i];
+        if (sfb < 12 && (int)T.sfb_short[cfg * 16 + sfb] * 3 >= cnt1_r)
+            return sf_nib(pk0, 22 + sfb * 3 + T.line_win_short[cfg * 576 + i]);
+    } else {
+        int sfb = T.line_sfb_long[cfg * 576 + i];
+        if (sfb < (c0.mixed ? 8 : 21) && (int)T.sfb_long[cfg * 24 + sfb] >= cnt1_r) return sf_nib(pk0, sfb);
+    }
+    return 7;
+}
+
+// Number of alias-reduction butterflies for a channel (frame.go:427-440): 0, 8 or 248.
+MP3_HD int alias_butterflies(const GranuleChan &c) {
+    const bool mixed_flag = u_mixed(c.w2) == 1;
+    if (c.is_short && !mixed_flag) return 0;
+    return ((c.is_short && mixed_flag) ? 1 : 31) * 8;
+}
+MP3_HD void alias_butterfly(const float *cs, const float *ca, float *x, int b) {
+    int sb = (b >> 3) + 1, i = b & 7;
+    int li = 18 * sb - 1 - i, ui = 18 * sb + i;
+    float xl = x[li], xu = x[ui];
+    x[li] = f_sub(f_mul(xl, cs[i]), f_mul(xu, ca[i]));
+    x[ui] = f_add(f_mul(xu, cs[i]), f_mul(xl, ca[i]));
+}
+
+}  // namespace mp3gpu

@@ -1,0 +1,126 @@
+/*
+ * mp3host.h — C API of the host-side mirror of go-mp3's public package, above the mp3gpu C ABI.
+ *
+ * No Go toolchain exists in the build image, so the host layer that the product would write in Go
+ * (go-mp3_b200/go/mp3) is mirrored here in C++ with the same names, argument
+ * meaning and error behaviour as the reference's `package mp3`:
+ *
+ *   mp3.NewDecoder(r)            decode.go:361-388   -> mp3_new_decoder
+ *   (*Decoder).Read              decode.go:70-80     -> mp3_decoder_read
+ *   (*Decoder).Seek              decode.go:89-145    -> mp3_decoder_seek
+ *   SampleRate/Length/BytesPerFrame/Duration/Position/Remaining/Progress/
+ *   SamplePosition/SampleCount/SeekToSample/Skip/SeekToTime   decode.go:150-341
+ *   (new) DecodeBatch            north star          -> mp3_decode_batch
+ *
+ * The serial stream work stays on the host (tag skipping source.go:42-83, header sync
+ * frameheader.go:279-328, side info sideinfo.go:66-156, bit-reservoir resolution
+ * maindata.go:290-323); everything from "bit-slice" to PCM runs on the GPU through mp3gpu.h.
+ * There is no CPU decode path: without a CUDA device mp3_engine_create fails.
+ */
+#ifndef MP3HOST_H
+#define MP3HOST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "mp3gpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status / error codes.  > 0: end of stream; < 0: the reference's error values. */
+enum {
+    MP3_OK = 0,
+    MP3_EOF = 1,                   /* io.EOF */
+    MP3_ERR_UNEXPECTED_EOF = -1,   /* *consts.UnexpectedEOFError (mapped to io.EOF by readFrame, decode.go:52-56) */
+    MP3_ERR_SYNC_LIMIT = -2,       /* *frameheader.SyncSearchLimitError (mapped to io.EOF, decode.go:59-62) */
+    MP3_ERR_FREE_FORMAT = -3,      /* "mp3: free bitrate format is not supported..." frameheader.go:323-326 */
+    MP3_ERR_MPEG25 = -4,           /* "mp3: MPEG version 2.5 is not supported" frame.go:79-81 */
+    MP3_ERR_LAYER = -5,            /* "mp3: only layer3 ... is supported" frame.go:82-84 */
+    MP3_ERR_FRAMESIZE = -6,        /* "mp3: framesize = %d" sideinfo.go:72-74 */
+    MP3_ERR_MAINDATA_SIZE = -7,    /* "mp3: size = %d" maindata.go:291-293 */
+    MP3_ERR_ISPOS = -8,            /* "mp3: isPos was too big: %d" maindata/huffman.go:68-70 */
+    MP3_ERR_SEEK_UNSUPPORTED = -11,/* "mp3: seek not supported on non-seekable source" decode.go:291,323 */
+    MP3_ERR_WHENCE = -12,          /* "mp3: invalid whence" decode.go:104 */
+    MP3_ERR_REF_PANIC = -14,       /* input on which the reference panics (LSF mixed blocks, maindata.go:172-178) */
+    MP3_ERR_DEVICE = -50,          /* CUDA / engine failure (message from mp3_engine_last_error) */
+    MP3_ERR_INVALID = -51
+};
+
+typedef struct mp3_engine mp3_engine;   /* one GPU + host thread pool + pinned arenas */
+typedef struct mp3_decoder mp3_decoder; /* mirrors *mp3.Decoder */
+
+typedef struct mp3_engine_opts {
+    int device;              /* CUDA device ordinal */
+    int host_threads;        /* stream-parsing threads for DecodeBatch (0 = hardware concurrency) */
+    uint32_t wave_granules;  /* passed to mp3gpu_opts (0 = default) */
+    uint32_t chunk_frames;   /* Decoder decode-ahead per GPU call (0 = default 256) */
+    uint32_t keep_intermediates; /* passed to mp3gpu_opts */
+    uint32_t use_exact_library;  /* 1: load libmp3gpu_exact.so (no FMA contraction) instead of libmp3gpu.so */
+} mp3_engine_opts;
+
+int mp3_engine_create(const mp3_engine_opts *opts, mp3_engine **out);
+void mp3_engine_destroy(mp3_engine *e);
+const char *mp3_engine_last_error(const mp3_engine *e);
+mp3gpu_ctx *mp3_engine_gpu(mp3_engine *e); /* the underlying device engine (for taps / timings) */
+const char *mp3_error_string(int code);    /* the reference's error message for a status code */
+
+/* ---- Decoder: drop-in for *mp3.Decoder over an in-memory source ------------------------- */
+/* seekable = 0 models a plain io.Reader: Length() = -1 and the Seek* methods fail. The data
+ * must stay valid for the decoder's lifetime. On failure returns NULL and sets *err. */
+mp3_decoder *mp3_new_decoder(mp3_engine *e, const uint8_t *data, size_t len, int seekable, int *err);
+void mp3_decoder_free(mp3_decoder *d);
+/* Read: copies up to n bytes; returns the count (> 0) or 0 with *err = MP3_EOF or a fatal code. */
+long mp3_decoder_read(mp3_decoder *d, uint8_t *buf, size_t n, int *err);
+int64_t mp3_decoder_seek(mp3_decoder *d, int64_t offset, int whence, int *err);
+int mp3_decoder_sample_rate(const mp3_decoder *d);
+int64_t mp3_decoder_length(const mp3_decoder *d);
+int64_t mp3_decoder_bytes_per_frame(const mp3_decoder *d);
+int64_t mp3_decoder_duration_ns(const mp3_decoder *d);
+int64_t mp3_decoder_position_ns(const mp3_decoder *d);
+int64_t mp3_decoder_remaining_ns(const mp3_decoder *d);
+double mp3_decoder_progress(const mp3_decoder *d);
+int64_t mp3_decoder_sample_position(const mp3_decoder *d);
+int64_t mp3_decoder_sample_count(const mp3_decoder *d);
+int mp3_decoder_seek_to_sample(mp3_decoder *d, int64_t sample);
+int mp3_decoder_skip(mp3_decoder *d, int64_t delta_ns);
+int mp3_decoder_seek_to_time(mp3_decoder *d, int64_t t_ns);
+
+/* ---- DecodeBatch: many independent streams in one call ------------------------------------ */
+typedef struct mp3_stream_result {
+    int64_t pcm_offset;  /* byte offset of this stream's PCM in the batch PCM buffer */
+    int64_t pcm_bytes;   /* what io.ReadAll(NewDecoder(stream)) returns */
+    int32_t sample_rate; /* from the first frame (decode.go:377-381); 0 if the stream failed to open */
+    int32_t status;      /* MP3_OK: clean end of stream; < 0: NewDecoder/Read error of the reference */
+    int64_t frames;      /* frames decoded */
+} mp3_stream_result;
+
+typedef struct mp3_batch_timings {
+    double parse_s, gather_s, device_s, total_s;
+    uint64_t main_data_bytes, n_granules, pcm_bytes;
+} mp3_batch_timings;
+
+/* Decodes n streams.  PCM lands in an engine-owned pinned host buffer that stays valid until the
+ * next mp3_decode_batch / mp3_engine_destroy on this engine; *pcm_base receives its address. */
+int mp3_decode_batch(mp3_engine *e, const uint8_t *const *data, const size_t *lens, size_t n,
+                     mp3_stream_result *results, const uint8_t **pcm_base, mp3_batch_timings *timings);
+
+/* Host-only stage of DecodeBatch (no GPU): parse + reservoir resolution into caller-visible arrays.
+ * Used by tests (host logic) and by bench.py to stage device-resident inputs.  Buffers are owned by
+ * the engine-independent parse result; free with mp3_parsed_free. */
+typedef struct mp3_parsed {
+    uint8_t *main_data;     /* padded by 64 zero bytes */
+    size_t main_data_len;
+    mp3gpu_unit *units;     /* 2 * n_granules */
+    size_t n_granules;
+    mp3_stream_result *streams; /* pcm_offset/pcm_bytes/sample_rate/status/frames per stream */
+    size_t n_streams;
+} mp3_parsed;
+int mp3_parse_streams(const uint8_t *const *data, const size_t *lens, size_t n, int host_threads, mp3_parsed **out);
+void mp3_parsed_free(mp3_parsed *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,169 @@
+// hostemu.cc — TEST INFRASTRUCTURE ONLY.
+// Compiles the __host__ __device__ unit logic of K1/K2 (go-mp3_b200/csrc/unit_logic.h) for the CPU so
+// that `-m "not gpu"` tests can check the bit-level logic and the table construction against the oracle
+// without a GPU.  Nothing in the product links or loads this file; the C ABI has no CPU path.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../go-mp3_b200/csrc/tables.h"
+#include "../../go-mp3_b200/csrc/unit_logic.h"
+
+using namespace mp3gpu;
+
+namespace {
+HostTables *g_h = nullptr;
+DeviceTables g_T;
+const uint8_t kSlen[16][2] = {{0, 0}, {0, 1}, {0, 2}, {0, 3}, {3, 0}, {1, 1}, {1, 2}, {1, 3},
+                              {2, 1}, {2, 2}, {2, 3}, {3, 1}, {3, 2}, {3, 3}, {4, 2}, {4, 3}};
+void ensure() {
+    if (g_h) return;
+    g_h = new HostTables();
+    build_host_tables(*g_h);
+    HostTables &h = *g_h;
+    g_T.pow2q = h.pow2q;
+    g_T.powtab34 = h.powtab34.data();
+    g_T.line_sfb_long = &h.line_sfb_long[0][0];
+    g_T.line_sfb_short = &h.line_sfb_short[0][0];
+    g_T.line_win_short = &h.line_win_short[0][0];
+    g_T.reorder_dst = &h.reorder_dst[0][0];
+    g_T.sfb_long = &h.sfb_long[0][0];
+    g_T.sfb_short = &h.sfb_short[0][0];
+    g_T.nslen2 = h.nslen2;
+    g_T.huff_lut = h.huff_lut.data();
+    g_T.huff_desc = h.huff_desc;
+    g_T.is_ratio_l = h.is_ratio_l;
+    g_T.is_ratio_r = h.is_ratio_r;
+    g_T.pretab = h.pretab;
+    g_T.sfsize_mpeg2 = &h.sfsize_mpeg2[0][0][0];
+    g_T.slen_mpeg1 = &kSlen[0][0];
+    g_T.cs = h.cs;
+    g_T.ca = h.ca;
+    g_T.huff_lut_n = (int)h.huff_lut.size();
+    g_T.pow2_off = kPow2Off;
+}
+}  // namespace
+
+extern "C" {
+
+// K1 on the CPU: is16 [n][576] (zero-filled above count1), meta [n], scalefac [n][64] (as MP3GPU_TAP_SCALEFAC).
+void emu_huffman(const uint8_t *main_data, const mp3gpu_unit *units, long long n_units, int16_t *is16, uint32_t *meta,
+                 uint8_t *scalefac) {
+    ensure();
+    for (long long u = 0; u < n_units; u++) {
+        memset(is16 + u * 576, 0, 576 * sizeof(int16_t));
+        memset(scalefac + u * 64, 0, 64);
+        meta[u] = 0;
+        if (!u_valid(units[u].w2)) continue;
+        uint32_t pk[8];
+        uint32_t out[288 + 2];
+        memset(out, 0, sizeof out);
+        uint32_t m = huffman_unit(g_T, g_T.huff_lut, g_T.huff_desc, main_data, units, u, pk, out);
+        meta[u] = m;
+        int c1 = (int)(m & 0x3ff);
+        for (int i = 0; i < c1; i++) is16[u * 576 + i] = (int16_t)((out[i >> 1] >> (16 * (i & 1))) & 0xffff);
+        for (int k = 0; k < 64; k++) scalefac[u * 64 + k] = (uint8_t)sf_nib(pk, k);
+        scalefac[u * 64 + 61] = (uint8_t)((m >> 10) & 1);
+    }
+}
+
+// K2 on the CPU, same order of operations as k_requant: xr [n_granules][2][576] after
+// requantise + reorder + stereo + alias reduction, index sb*18+i.
+void emu_requant(const mp3gpu_unit *units, long long n_granules, const int16_t *is16, const uint32_t *meta,
+                 const uint8_t *scalefac, float *xr) {
+    ensure();
+    for (long long g = 0; g < n_granules; g++) {
+        const mp3gpu_unit *ug = units + g * 2;
+        float *x0 = xr + (g * 2) * 576, *x1 = x0 + 576;
+        memset(x0, 0, 2 * 576 * sizeof(float));
+        if (!u_valid(ug[0].w2)) continue;
+        const bool valid_b = u_valid(ug[1].w2);
+        const int cfg = u_lsf(ug[0].w2) * 3 + u_sfreq(ug[0].w2);
+        uint32_t pk[2][8];
+        memset(pk, 0, sizeof pk);
+        for (int ch = 0; ch < 2; ch++)
+            for (int k = 0; k < 61; k++) sf_put(pk[ch], k, scalefac[(g * 2 + ch) * 64 + k]);
+        GranuleChan c[2];
+        c[0] = make_chan(ug[0].w0, ug[0].w1, ug[0].w2, meta[g * 2]);
+        c[1] = make_chan(ug[1].w0, ug[1].w1, ug[1].w2, valid_b ? meta[g * 2 + 1] : 0u);
+        float *x[2] = {x0, x1};
+        for (int ch = 0; ch < 2; ch++) {
+            if (ch == 1 && !valid_b) break;
+            const int16_t *is = is16 + (g * 2 + ch) * 576;
+            for (int i = 0; i < 576; i++) {
+                int dst;
+                float r = requant_line(g_T, cfg, c[ch], pk[ch], i, i < c[ch].cnt1 ? (int)is[i] : 0, &dst);
+                x[ch][dst] = r;
+            }
+        }
+        if (valid_b && u_mode(c[0].w2) == 1) {
+            const int mode_ext = u_modeext(c[0].w2);
+            if (mode_ext & 2) {
+                const int max_pos = c[0].cnt1 > c[1].cnt1 ? c[0].cnt1 : c[1].cnt1;
+                const float inv_sqrt2 = 0.70710678118654752440f;
+                for (int i = 0; i < max_pos; i++) {
+                    float a = x0[i], b = x1[i];
+                    x0[i] = f_mul(f_add(a, b), inv_sqrt2);
+                    x1[i] = f_mul(f_sub(a, b), inv_sqrt2);
+                }
+            }
+            if (mode_ext & 1) {
+                for (int i = 0; i < 576; i++) {
+                    int is_pos = intensity_pos(g_T, cfg, c[0], pk[0], c[1].cnt1, i);
+                    if (is_pos < 7) {
+                        x0[i] = f_mul(x0[i], g_T.is_ratio_l[is_pos]);
+                        x1[i] = f_mul(x1[i], g_T.is_ratio_r[is_pos]);
+                    }
+                }
+            }
+        }
+        for (int ch = 0; ch < 2; ch++) {
+            if (ch == 1 && !valid_b) break;
+            const int nb = alias_butterflies(c[ch]);
+            for (int b = 0; b < nb; b++) alias_butterfly(g_T.cs, g_T.ca, x[ch], b);
+        }
+    }
+}
+
+// Table access for pinning the device tables against the oracle's.
+const float *emu_table(int which, int *n) {
+    ensure();
+    switch (which) {
+    case 0: *n = 18 * 36; return g_h->cos36;
+    case 1: *n = 6 * 12; return g_h->cos12;
+    case 2: *n = 4 * 36; return g_h->imdct_win;
+    case 3: *n = 64 * 32; return g_h->synth_n;
+    case 4: *n = 512; return g_h->synth_d;
+    }
+    *n = 0;
+    return nullptr;
+}
+const double *emu_powtab34(int *n) {
+    ensure();
+    *n = (int)g_h->powtab34.size();
+    return g_h->powtab34.data();
+}
+int emu_huff_lut_size() {
+    ensure();
+    return (int)g_h->huff_lut.size();
+}
+// Decode one code word of `table` from a bit string with the LUT path; returns bits consumed.
+int emu_huff_one(int table, const uint8_t *buf, int len_bytes, int *out4) {
+    ensure();
+    std::vector<uint8_t> padded((size_t)((len_bytes + 3) & ~3) + 64, 0);
+    memcpy(padded.data(), buf, (size_t)len_bytes);
+    BitCursor bc;
+    bc.init(padded.data(), 0, len_bytes * 8);
+    if (table < 32) {
+        uint32_t r = huff_pair(g_T.huff_lut, g_T.huff_desc[table], bc);
+        out4[0] = (int16_t)(r & 0xffff);
+        out4[1] = (int16_t)(r >> 16);
+        out4[2] = out4[3] = 0;
+    } else {
+        int v, w, x, y;
+        huff_quad(g_T.huff_lut, g_T.huff_desc[table], bc, v, w, x, y);
+        out4[0] = x; out4[1] = y; out4[2] = v; out4[3] = w;
+    }
+    return bc.pos;
+}
+}
