@@ -70,12 +70,12 @@ class GpuOpts(C.Structure):
 
 
 class GpuTimings(C.Structure):
-    _fields_ = [("k1_huffman_ms", C.c_float), ("k2_requant_ms", C.c_float), ("k3_imdct_ms", C.c_float),
-                ("k4_synth_ms", C.c_float), ("total_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
+    _fields_ = [("k1_huffman_ms", C.c_float), ("k_hybrid_ms", C.c_float), ("k_synth_ms", C.c_float), ("reserved_ms", C.c_float),
+                ("total_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("waves", C.c_uint32), ("launches", C.c_uint32)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved_ms"}
 
 
 class EngineOpts(C.Structure):
@@ -179,6 +179,12 @@ def gpu_lib(exact: bool = False) -> C.CDLL:
     L.mp3gpu_decode.restype = C.c_int
     L.mp3gpu_decode_device.argtypes = [vp, vp, sz, vp, sz, vp]
     L.mp3gpu_decode_device.restype = C.c_int
+    L.mp3gpu_decode_device_async.argtypes = [vp, vp, sz, vp, sz, vp]
+    L.mp3gpu_decode_device_async.restype = C.c_int
+    L.mp3gpu_event_record.argtypes = [vp, C.c_int]
+    L.mp3gpu_event_record.restype = C.c_int
+    L.mp3gpu_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
+    L.mp3gpu_event_elapsed_ms.restype = C.c_int
     L.mp3gpu_host_alloc.argtypes = [sz]
     L.mp3gpu_host_alloc.restype = vp
     L.mp3gpu_host_free.argtypes = [vp]
@@ -223,14 +229,35 @@ class ParsedBatch:
         self.n_granules = len(units) // 2
 
 
-def _stream_args(streams: Sequence[bytes]):
+class StreamBuffer:
+    """Many streams stored in one uint8 numpy buffer: stream i = buf[offsets[i] : offsets[i] + lens[i]]."""
+
+    def __init__(self, buf: np.ndarray, offsets: Sequence[int], lens: Sequence[int]):
+        self.buf, self.offsets, self.lens = buf, list(offsets), list(lens)
+
+    def __len__(self):
+        return len(self.offsets)
+
+    def stream(self, i: int) -> bytes:
+        return self.buf[self.offsets[i]:self.offsets[i] + self.lens[i]].tobytes()
+
+
+def _stream_args(streams):
+    """Pointer + length arrays for a list of bytes objects or a StreamBuffer.  Returns (ptrs, lens, n, keepalive)."""
     n = len(streams)
     arr = (C.c_char_p * max(n, 1))()
     lens = (C.c_size_t * max(n, 1))()
+    if isinstance(streams, StreamBuffer):
+        base = streams.buf.ctypes.data
+        ptrs = (C.c_void_p * max(n, 1))()
+        for i in range(n):
+            ptrs[i] = base + streams.offsets[i]
+            lens[i] = streams.lens[i]
+        return C.cast(ptrs, C.POINTER(C.c_char_p)), lens, n, (ptrs, streams.buf)
     for i, s in enumerate(streams):
         arr[i] = s
         lens[i] = len(s)
-    return arr, lens, n
+    return arr, lens, n, streams
 
 
 def _result_dict(r: StreamResult) -> dict:
@@ -241,7 +268,7 @@ def _result_dict(r: StreamResult) -> dict:
 def parse_streams(streams: Sequence[bytes], host_threads: int = 0) -> ParsedBatch:
     """Host half of DecodeBatch: tags, headers, side info, reservoir -> bit-slices (mp3_parse_streams)."""
     L = host_lib()
-    arr, lens, n = _stream_args(streams)
+    arr, lens, n, _keep = _stream_args(streams)
     out = C.POINTER(Parsed)()
     rc = L.mp3_parse_streams(arr, lens, n, host_threads, C.byref(out))
     if rc != MP3_OK:
@@ -251,7 +278,8 @@ def parse_streams(streams: Sequence[bytes], host_threads: int = 0) -> ParsedBatc
         md = np.ctypeslib.as_array(p.main_data, shape=(p.main_data_len + 64,)).copy()
         nu = p.n_granules * 2
         if nu:
-            units = np.frombuffer(C.string_at(p.units, nu * 32), dtype=UNIT_DTYPE).copy()
+            raw = np.ctypeslib.as_array(C.cast(p.units, C.POINTER(C.c_uint8)), shape=(nu * 32,))
+            units = raw.copy().view(UNIT_DTYPE)
         else:
             units = np.zeros(0, dtype=UNIT_DTYPE)
         res = [_result_dict(p.streams[i]) for i in range(p.n_streams)]
@@ -271,7 +299,9 @@ class GpuEngine:
         rc = self.lib.mp3gpu_create(device, C.byref(opts), C.byref(self.ctx))
         if rc != 0:
             self.ctx = None
-            raise Mp3Error(rc, f"mp3gpu_create failed ({rc}): a CUDA device is required; there is no CPU path")
+            why = {-1: "no CUDA device (there is no CPU path)", -2: "CUDA error", -3: "invalid tables/arguments (see stderr)",
+                   -4: "out of memory"}.get(rc, "unknown")
+            raise Mp3Error(rc, f"mp3gpu_create failed ({rc}): {why}")
 
     def close(self):
         if getattr(self, "ctx", None):
@@ -294,6 +324,35 @@ class GpuEngine:
         self._check(self.lib.mp3gpu_decode(self.ctx, main_data.ctypes.data, main_data_len, units.ctypes.data, n_gr,
                                            pcm.ctypes.data))
         return pcm
+
+    def decode_device(self, d_main: int, main_len: int, d_units: int, n_granules: int, d_pcm: int, sync: bool = True):
+        """Device-resident decode (raw device pointers, e.g. torch tensors' data_ptr())."""
+        f = self.lib.mp3gpu_decode_device if sync else self.lib.mp3gpu_decode_device_async
+        self._check(f(self.ctx, d_main, main_len, d_units, n_granules, d_pcm))
+
+    def decode_host(self, p_main: int, main_len: int, p_units: int, n_granules: int, p_pcm: int):
+        """Host-buffer decode with raw host pointers (pinned buffers from host_alloc make the copies asynchronous)."""
+        self._check(self.lib.mp3gpu_decode(self.ctx, p_main, main_len, p_units, n_granules, p_pcm))
+
+    def event_record(self, which: int):
+        self._check(self.lib.mp3gpu_event_record(self.ctx, which))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        self._check(self.lib.mp3gpu_event_elapsed_ms(self.ctx, a, b, C.byref(ms)))
+        return ms.value
+
+    def synchronize(self):
+        self._check(self.lib.mp3gpu_synchronize(self.ctx))
+
+    def host_alloc(self, nbytes: int) -> int:
+        p = self.lib.mp3gpu_host_alloc(nbytes)
+        if not p:
+            raise MemoryError(f"pinned host allocation of {nbytes} bytes failed")
+        return p
+
+    def host_free(self, p: int):
+        self.lib.mp3gpu_host_free(p)
 
     def timings(self) -> dict:
         t = GpuTimings()
@@ -352,7 +411,7 @@ class Engine:
 
     def decode_batch(self, streams: Sequence[bytes]) -> Tuple[List[dict], np.ndarray, dict]:
         """DecodeBatch: returns (per-stream results, PCM bytes view (valid until the next call), timings)."""
-        arr, lens, n = _stream_args(streams)
+        arr, lens, n, _keep = _stream_args(streams)
         res = (StreamResult * max(n, 1))()
         base = C.c_void_p()
         tm = BatchTimings()

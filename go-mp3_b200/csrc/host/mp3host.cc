@@ -36,7 +36,7 @@ struct GpuApi {
     int (*decode)(mp3gpu_ctx *, const uint8_t *, size_t, const mp3gpu_unit *, size_t, int16_t *) = nullptr;
     void *(*host_alloc)(size_t) = nullptr;
     void (*host_free)(void *) = nullptr;
-    int (*last_timings)(const mp3gpu_ctx *, mp3gpu_timings *) = nullptr;
+    int (*last_timings)(mp3gpu_ctx *, mp3gpu_timings *) = nullptr;
 };
 
 std::string self_dir() {

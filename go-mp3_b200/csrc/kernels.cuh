@@ -13,13 +13,13 @@
 //    parallelism is across units.  Code tables are multi-level LUTs staged in shared memory;
 //    the bit cursor reproduces bits.go's out-of-bounds rule (reads at/after the frame's logical
 //    buffer end return 0 and do not advance).
-//  * K3/K4 keep the reference's direct-form summation ORDER (m ascending / j ascending / tap
-//    ascending) and take their cosine/window coefficients as constant-bank operands of FFMA, so
-//    the inner loops are pure FFMA streams with no shared-memory or register traffic for the
-//    coefficient matrices.
-//  * Cross-granule state (IMDCT overlap `store`, synthesis `vVec`) is not carried serially:
-//    K3 recomputes the previous granule's second IMDCT half at the start of each run of
-//    granules; K4 recomputes the matrixing of the 15 preceding time slots (halo) per CTA.
+//  * K2 and K3 are fused into k_hybrid: one warp marches through a segment of consecutive granules
+//    and keeps the IMDCT overlap itself; a one-granule halo in front of every segment rebuilds it.
+//  * K4 is k_synth: thread-per-slot matrixing with compile-time (immediate) coefficients, then a
+//    warp-per-30-slots window pass with the V history in registers; a 16-slot halo per CTA.
+//    The reference's direct-form summation ORDER is kept (m / j / tap ascending).
+//  * Both kernels are kept small enough for the 32 KB L1.5 instruction cache: a fully fused
+//    K2+K3+K4 kernel was measured first and starved on instruction fetch (profiles/).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -44,22 +44,24 @@ __device__ __forceinline__ float mac(float a, float b, float sum) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Constant-bank tables (uniform access only; coefficients become FFMA c[bank][imm] operands)
+// Tables.  The IMDCT cosine/window tables are lane-uniform and compile-time (const_tables.inc,
+// generated at build time from tables.cc), so every IMDCT multiply-add is an FFMA with an
+// immediate operand: no constant-cache or shared-memory traffic for coefficients.
 // ------------------------------------------------------------------------------------------
-__constant__ float c_cos36[18 * 36];
-__constant__ float c_cos12[6 * 12];
-__constant__ float c_win[4 * 36];
-__constant__ float c_synth_n[64 * 32];
-__constant__ float c_synth_d[512];
+#include "const_tables.inc"
+__constant__ float c_win[4 * 36];  // per-lane window lookup, only for the rare mixed-flag + start/stop case (Q15)
 
-// Wave-local intermediate buffers.  Index j = local granule (g - wave_first); arrays that a
-// later kernel reads with a one-granule look-back (xr_t, hyb) have a valid slot at j = -1.
+// Wave-local intermediate buffers.  Index j = local granule (g - wave_first).  k_hybrid looks one
+// granule back (halo) and k_synth 16 time slots, so K1's outputs and hyb have valid look-back slots in
+// front, carried over from the previous wave.
 struct WaveBufs {
-    int16_t *is16;     // [nw][2][576]
-    uint32_t *meta;    // [nw][2]   bits 0..9 count1, bit 10 preflag (after LSF derivation)
-    uint32_t *sfpack;  // [nw][2][8] scalefactors as nibbles: n = sfb (long), 22 + sfb*3+win (short)
-    float *xr_t;       // [-1..nw)[2][18][32]  spectral lines, transposed: [m][sb] = xr[sb*18+m]
-    float *hyb[2];     // per channel: [-18..nw*18)[32]  subband samples, slot-major
+    int16_t *is16;     // [-2..nw)[2][576]
+    uint32_t *meta;    // [-2..nw)[2]   bits 0..9 count1, bit 10 preflag (after LSF derivation)
+    uint32_t *sfpack;  // [-2..nw)[2][8] scalefactors as nibbles: n = sfb (long), 22 + sfb*3+win (short)
+    float *hyb;        // [-1..nw)[2][18][32] subband samples (k_hybrid -> k_synth), one look-back granule in front
+    float *tap_xr;     // debug tap (opts.keep_intermediates): [nw][2][576] index sb*18+m, else nullptr
+    const float *synth_d;  // [512]     frame.go:499-628
+    unsigned int *work_counter;  // dynamic segment scheduler of k_hybrid
 };
 
 // ------------------------------------------------------------------------------------------
@@ -89,224 +91,272 @@ k_huffman(const uint8_t *__restrict__ main_data, const mp3gpu_unit *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------
-// K2: requantise + reorder + stereo + alias reduction.  One warp per granule (both channels).
+// k_hybrid = K2 + K3: one warp marches through a segment of consecutive granules (both channels).
+//
+//   K2  requantise + reorder + stereo + alias reduction      frame.go:140-452   lane = spectral line (mod 32)
+//   K3  IMDCT + window + overlap-add + frequency inversion   frame.go:454-486   lane = subband
+//
+// The IMDCT overlap `store` (frame.go:48) stays with the warp in shared memory.  A segment starts by
+// re-running the granule in front of it (halo) for its overlap output only, which recreates exactly
+// the state a linear decode has at that point; a granule flagged ZERO_STATE clears the state.
+// Output: subband samples hyb[g][ch][slot][sb] in global memory (2,304 B per granule-channel).
+//
+// The reference's summation orders are kept (m ascending), so the no-contraction build
+// (MP3GPU_EXACT) is bit-identical to the reference and the FFMA build differs only by fused
+// rounding.  Symmetries that hold BITWISE in the float32 tables are exploited:
+// cos36[m][17-p] = -cos36[m][p], cos36[m][53-p] = cos36[m][p] (and the 12-point analogues), which
+// halves the IMDCT multiply-adds with bit-identical results (negation is exact in IEEE 754).
 // ------------------------------------------------------------------------------------------
-constexpr int kK2Warps = 8;
+constexpr int kXrStride = 19;              // padded subband stride of the spectrum staging (conflict-free lane = subband reads)
+constexpr int kXrFloats = 32 * kXrStride;  // 608
 
-__global__ void __launch_bounds__(kK2Warps * 32)
-k_requant(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_granules, DeviceTables T, WaveBufs B) {
-    __shared__ float s_x[kK2Warps][2][576];
-    __shared__ uint32_t s_pk[kK2Warps][2][8];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int gl = blockIdx.x * kK2Warps + warp;
-    if (gl >= n_granules) return;
-    const mp3gpu_unit *ug = units + (first_granule + gl) * 2;
-    const bool valid_b = u_valid(ug[1].w2);
-    if (!u_valid(ug[0].w2)) return;  // a granule always has channel 0
-    const int cfg = u_lsf(ug[0].w2) * 3 + u_sfreq(ug[0].w2);
-    float(*x)[576] = s_x[warp];
-    if (lane < 16) s_pk[warp][lane >> 3][lane & 7] = B.sfpack[((size_t)gl * 2 + (lane >> 3)) * 8 + (lane & 7)];
-    GranuleChan c[2];
-    c[0] = make_chan(ug[0].w0, ug[0].w1, ug[0].w2, B.meta[gl * 2]);
-    c[1] = make_chan(ug[1].w0, ug[1].w1, ug[1].w2, valid_b ? B.meta[gl * 2 + 1] : 0u);
-    __syncwarp();
+__device__ __forceinline__ int xr_pad(int i) { return i + i / 18; }
 
-    // ---- requantise (frame.go:140-255) + reorder (frame.go:257-302) ----------------------
+// sum_{m=0..17} in[m] * cos36[m][P], m ascending from 0 (imdct.go:101-107); three outputs at a time for ILP
+template <int P0, int P1, int P2>
+__device__ __forceinline__ void dot36x3(const float (&in)[18], float &r0, float &r1, float &r2) {
+    float a = 0.0f, b = 0.0f, c = 0.0f;
 #pragma unroll
-    for (int ch = 0; ch < 2; ch++) {
-        if (ch == 1 && !valid_b) break;
-        const int16_t *is = B.is16 + ((size_t)gl * 2 + ch) * 576;
-        for (int i = lane; i < 576; i += 32) {
-            int dst;
-            float r = requant_line(T, cfg, c[ch], s_pk[warp][ch], i, i < c[ch].cnt1 ? (int)is[i] : 0, &dst);
-            x[ch][dst] = r;
+    for (int m = 0; m < 18; m++) {
+        a = mac(in[m], kCos36[m][P0], a);
+        b = mac(in[m], kCos36[m][P1], b);
+        c = mac(in[m], kCos36[m][P2], c);
+    }
+    r0 = a; r1 = b; r2 = c;
+}
+// sum_{m=0..5} in[i + 3m] * cos12[m][P]  (imdct.go:88-96)
+template <int I, int P>
+__device__ __forceinline__ float dot12(const float (&in)[18]) {
+    float sum = 0.0f;
+#pragma unroll
+    for (int m = 0; m < 6; m++) sum = mac(in[I + 3 * m], kCos12[m][P], sum);
+    return sum;
+}
+
+// Emits windowed IMDCT outputs of one subband: first-half outputs are overlap-added, frequency
+// inverted and written as subband samples hyb[i][lane]; second-half outputs become the new overlap.
+struct HybridSink {
+    float *hyb;   // global [18][32] (this granule-channel)
+    float *ov;    // shared [18][32] overlap state (this channel)
+    int lane;
+    bool first_half;  // false: only the overlap is wanted (halo granule)
+    __device__ __forceinline__ void first(int i, float windowed) const {
+        float v = __fadd_rn(windowed, ov[i * 32 + lane]);  // frame.go:474
+        if ((i & 1) && (lane & 1)) v = -v;                  // frame.go:480-486
+        hyb[i * 32 + lane] = v;
+    }
+    __device__ __forceinline__ void second(int i, float windowed) const { ov[i * 32 + lane] = windowed; }  // frame.go:475
+};
+
+// 36-point IMDCT + window (imdct.go:99-107).  The window row `bt` is a run-time value (warp-uniform except for
+// the mixed-flag quirk of frame.go:462-466), looked up in the constant bank; the cosines are immediates.
+__device__ __forceinline__ void imdct36_emit(const float (&in)[18], const HybridSink &k, int bt) {
+    const float *w = c_win + bt * 36;
+    if (k.first_half) {
+        float u[9];
+        dot36x3<0, 1, 2>(in, u[0], u[1], u[2]);
+        dot36x3<3, 4, 5>(in, u[3], u[4], u[5]);
+        dot36x3<6, 7, 8>(in, u[6], u[7], u[8]);
+#pragma unroll
+        for (int p = 0; p < 9; p++) {
+            k.first(p, __fmul_rn(u[p], w[p]));
+            k.first(17 - p, __fmul_rn(-u[p], w[17 - p]));  // cos36[m][17-p] == -cos36[m][p] bitwise
         }
     }
-    __syncwarp();
-
-    // ---- stereo (frame.go:362-420) --------------------------------------------------------
-    if (valid_b && u_mode(c[0].w2) == 1) {
-        const int mode_ext = u_modeext(c[0].w2);
-        if (mode_ext & 2) {
-            const int max_pos = c[0].cnt1 > c[1].cnt1 ? c[0].cnt1 : c[1].cnt1;
-            const float inv_sqrt2 = 0.70710678118654752440f;
-            for (int i = lane; i < max_pos; i += 32) {
-                float a = x[0][i], b = x[1][i];
-                x[0][i] = f_mul(f_add(a, b), inv_sqrt2);
-                x[1][i] = f_mul(f_sub(a, b), inv_sqrt2);
-            }
-            __syncwarp();
-        }
-        if (mode_ext & 1) {
-            for (int i = lane; i < 576; i += 32) {
-                int is_pos = intensity_pos(T, cfg, c[0], s_pk[warp][0], c[1].cnt1, i);
-                if (is_pos < 7) {
-                    x[0][i] = f_mul(x[0][i], T.is_ratio_l[is_pos]);
-                    x[1][i] = f_mul(x[1][i], T.is_ratio_r[is_pos]);
-                }
-            }
-            __syncwarp();
-        }
-    }
-
-    // ---- alias reduction (frame.go:427-452) + transposed store ---------------------------
+    // the second half overwrites the overlap that first() has just consumed
+    float v[9];
+    dot36x3<18, 19, 20>(in, v[0], v[1], v[2]);
+    dot36x3<21, 22, 23>(in, v[3], v[4], v[5]);
+    dot36x3<24, 25, 26>(in, v[6], v[7], v[8]);
 #pragma unroll
-    for (int ch = 0; ch < 2; ch++) {
-        if (ch == 1 && !valid_b) break;
-        const int nb = alias_butterflies(c[ch]);
-        for (int b = lane; b < nb; b += 32) alias_butterfly(T.cs, T.ca, x[ch], b);
-        __syncwarp();
-        float *o = B.xr_t + ((size_t)gl * 2 + ch) * 576;
-#pragma unroll
-        for (int m = 0; m < 18; m++) o[m * 32 + lane] = x[ch][lane * 18 + m];
+    for (int q = 0; q < 9; q++) {
+        k.second(q, __fmul_rn(v[q], w[18 + q]));
+        k.second(17 - q, __fmul_rn(v[q], w[35 - q]));      // cos36[m][53-p] == cos36[m][p] bitwise
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// K3: IMDCT + window + overlap-add + frequency inversion.
-// One thread per subband, one warp per (run of kRun granules, channel).
-// ------------------------------------------------------------------------------------------
-constexpr int kRun = 8;
-constexpr int kK3Warps = 4;
-
-// out[p] = sum_{m} in[m] * cos36[m][p], m ascending from 0 (imdct.go:101-107).
-template <int P0, int P1>
-__device__ __forceinline__ void imdct36_range(const float (&in)[18], float (&raw)[36]) {
-#pragma unroll
-    for (int p = P0; p < P1; p++) {
-        float sum = 0.0f;
-#pragma unroll
-        for (int m = 0; m < 18; m++) sum = mac(in[m], c_cos36[m * 36 + p], sum);
-        raw[p] = sum;
-    }
-}
-
-// Short blocks (imdct.go:86-98): three 12-point transforms, windowed and overlapped into out[6..29].
-__device__ __forceinline__ void imdct12_win(const float (&in)[18], float (&raw)[36]) {
+// Short blocks (imdct.go:86-98): three 12-point transforms, windowed and overlapped into out[6..29];
+// out[0..5] and out[30..35] stay 0.  raw[j] accumulates in window order i = 0, 1, 2 like the reference.
+__device__ __forceinline__ void imdct12_emit(const float (&in)[18], const HybridSink &k) {
+    float raw[36];
 #pragma unroll
     for (int p = 0; p < 36; p++) raw[p] = 0.0f;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
+        float s[12];
+        // cos12[m][5-p] == -cos12[m][p], cos12[m][17-p] == cos12[m][p] bitwise
+        const float a0 = i == 0 ? dot12<0, 0>(in) : i == 1 ? dot12<1, 0>(in) : dot12<2, 0>(in);
+        const float a1 = i == 0 ? dot12<0, 1>(in) : i == 1 ? dot12<1, 1>(in) : dot12<2, 1>(in);
+        const float a2 = i == 0 ? dot12<0, 2>(in) : i == 1 ? dot12<1, 2>(in) : dot12<2, 2>(in);
+        const float b0 = i == 0 ? dot12<0, 6>(in) : i == 1 ? dot12<1, 6>(in) : dot12<2, 6>(in);
+        const float b1 = i == 0 ? dot12<0, 7>(in) : i == 1 ? dot12<1, 7>(in) : dot12<2, 7>(in);
+        const float b2 = i == 0 ? dot12<0, 8>(in) : i == 1 ? dot12<1, 8>(in) : dot12<2, 8>(in);
+        s[0] = a0; s[1] = a1; s[2] = a2; s[3] = -a2; s[4] = -a1; s[5] = -a0;
+        s[6] = b0; s[7] = b1; s[8] = b2; s[9] = b2; s[10] = b1; s[11] = b0;
 #pragma unroll
-        for (int p = 0; p < 12; p++) {
-            float sum = 0.0f;
-#pragma unroll
-            for (int m = 0; m < 6; m++) sum = mac(in[i + 3 * m], c_cos12[m * 12 + p], sum);
-            raw[6 * i + p + 6] = mac(sum, c_win[2 * 36 + p], raw[6 * i + p + 6]);
-        }
+        for (int p = 0; p < 12; p++) raw[6 * i + p + 6] = mac(s[p], kWin[2][p], raw[6 * i + p + 6]);
     }
+    if (k.first_half) {
+#pragma unroll
+        for (int i = 0; i < 18; i++) k.first(i, raw[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 18; i++) k.second(i, raw[18 + i]);
 }
 
-template <int BT, int P0, int P1>
-__device__ __forceinline__ void win36(float (&raw)[36]) {
-#pragma unroll
-    for (int p = P0; p < P1; p++) raw[p] = __fmul_rn(raw[p], c_win[BT * 36 + p]);
+// IMDCT of one channel of one granule; lane = subband (frame.go:454-478).
+__device__ __forceinline__ void hybrid_channel(const float (&in)[18], const HybridSink &k, uint32_t w0, uint32_t w2, int lane) {
+    const bool winsw = u_winsw(w0) == 1;
+    int bt = winsw ? u_btype(w0) : 0;
+    // frame.go:462-466: with win_switch and mixed_block_flag set, subbands 0 and 1 use block type 0 whatever block_type says
+    if (winsw && u_mixed(w2) == 1 && lane < 2) bt = 0;
+    if (bt == 2) imdct12_emit(in, k);
+    else imdct36_emit(in, k, bt);
 }
 
-// Full windowed IMDCT of one subband for a granule with side info (w0, w1); lane = subband.
-// HALF = 0: all 36 outputs; HALF = 1: only raw[18..35] is needed (overlap halo).
-template <int HALF>
-__device__ __forceinline__ void imdct_granule(const float (&in)[18], float (&raw)[36], uint32_t w0, uint32_t w2, int lane) {
-    const int bt = u_btype(w0);
-    const bool winsw = u_winsw(w0) == 1, mixed = u_mixed(w2) == 1;
-    constexpr int P0 = HALF ? 18 : 0;
-    if (!(winsw && mixed)) {
-        // uniform across the warp
-        if (bt == 2) {
-            imdct12_win(in, raw);
-        } else {
-            imdct36_range<P0, 36>(in, raw);
-            if (bt == 0) win36<0, P0, 36>(raw);
-            else if (bt == 1) win36<1, P0, 36>(raw);
-            else win36<3, P0, 36>(raw);
-        }
-    } else {
-        // frame.go:462-466: subbands 0,1 use block type 0 whatever block_type says.
-        const int ebt = lane < 2 ? 0 : bt;
-        if (__any_sync(0xffffffffu, ebt != 2)) {
-            float r2[36];
-            imdct36_range<P0, 36>(in, r2);
-            if (ebt != 2) {
-#pragma unroll
-                for (int p = P0; p < 36; p++) raw[p] = __fmul_rn(r2[p], c_win[ebt * 36 + p]);
-            }
-        }
-        if (__any_sync(0xffffffffu, ebt == 2)) {
-            float r2[36];
-            imdct12_win(in, r2);
-            if (ebt == 2) {
-#pragma unroll
-                for (int p = 0; p < 36; p++) raw[p] = r2[p];
-            }
-        }
-    }
-}
+constexpr int kHybWarps = 4;
+constexpr int kHybSmemWords = 2 * kXrFloats + 2 * 18 * 32 + 16;  // per warp: staging, overlap, scalefactors
+constexpr int kHybSmemBytes = kHybWarps * kHybSmemWords * 4;
 
-__global__ void __launch_bounds__(kK3Warps * 32)
-k_imdct(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_granules, WaveBufs B) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int item = blockIdx.x * kK3Warps + warp;
-    const int ch = item & 1;
-    const int g0 = (item >> 1) * kRun;
-    if (g0 >= n_granules) return;
-    const int g1 = min(g0 + kRun, n_granules);
-    float st[18];
+template <bool TAPS>
+__global__ void __launch_bounds__(kHybWarps * 32)
+k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_granules, int seg_len, int n_segs,
+         DeviceTables T, WaveBufs B) {
+    extern __shared__ __align__(16) float s_dyn[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *const s_base = s_dyn + warp * kHybSmemWords;
+    float(*s_x)[kXrFloats] = reinterpret_cast<float(*)[kXrFloats]>(s_base);                 // spectrum staging
+    float(*s_ov)[18 * 32] = reinterpret_cast<float(*)[18 * 32]>(s_base + 2 * kXrFloats);   // IMDCT overlap (Frame.store)
+    uint32_t(*s_pk)[8] = reinterpret_cast<uint32_t(*)[8]>(s_base + 2 * kXrFloats + 2 * 18 * 32);
+
+    for (;;) {
+        int seg = 0;
+        if (lane == 0) seg = (int)atomicAdd(B.work_counter, 1u);
+        seg = __shfl_sync(0xffffffffu, seg, 0);
+        if (seg >= n_segs) break;
+        const int g0 = seg * seg_len;
+        const int g1 = min(g0 + seg_len, n_granules);
+        // overlap before the halo granule is irrelevant: the halo's second half replaces it
 #pragma unroll
-    for (int i = 0; i < 18; i++) st[i] = 0.0f;
-    {
-        // Overlap state entering the run: second IMDCT half of the previous granule, unless
-        // this granule starts from zero state or the previous one has no such channel.
-        const mp3gpu_unit *uc = units + (first_granule + g0) * 2 + ch;
-        if (!u_zero(uc->w2) && (first_granule + g0) > 0) {
-            const mp3gpu_unit *up = uc - 2;
-            if (u_valid(up->w2)) {
-                float in[18], raw[36];
-                const float *src = B.xr_t + ((long long)(g0 - 1) * 2 + ch) * 576;
+        for (int i = 0; i < 18; i++) { s_ov[0][i * 32 + lane] = 0.f; s_ov[1][i * 32 + lane] = 0.f; }
+
+        for (int g = g0 - 1; g < g1; g++) {
+            const long long G = first_granule + g;
+            if (G < 0) continue;
+            const mp3gpu_unit *ug = units + G * 2;
+            const uint32_t w0a = __ldg(&ug[0].w0), w1a = __ldg(&ug[0].w1), w2a = __ldg(&ug[0].w2);
+            const uint32_t w0b = __ldg(&ug[1].w0), w1b = __ldg(&ug[1].w1), w2b = __ldg(&ug[1].w2);
+            if (!u_valid(w2a)) continue;  // a granule always has channel 0
+            const bool valid_b = u_valid(w2b);
+            const bool need_first = g >= g0;  // the halo granule only contributes its overlap
+            if (u_zero(w2a)) {  // start of a stream / of a Seek: Frame.store is zero (frame.go:48)
 #pragma unroll
-                for (int m = 0; m < 18; m++) in[m] = src[m * 32 + lane];
-                imdct_granule<1>(in, raw, up->w0, up->w2, lane);
-#pragma unroll
-                for (int i = 0; i < 18; i++) st[i] = raw[18 + i];
+                for (int i = 0; i < 18; i++) { s_ov[0][i * 32 + lane] = 0.f; s_ov[1][i * 32 + lane] = 0.f; }
             }
-        }
-    }
-    for (int g = g0; g < g1; g++) {
-        const mp3gpu_unit *uc = units + (first_granule + g) * 2 + ch;
-        const uint32_t w0 = uc->w0, w2 = uc->w2;
-        if (u_zero(w2)) {
+            __syncwarp();
+
+            // ---------------- K2: requantise + reorder (frame.go:140-302) -------------------------------
+            const int cfg = u_lsf(w2a) * 3 + u_sfreq(w2a);
+            if (lane < 16) s_pk[lane >> 3][lane & 7] = __ldg(B.sfpack + ((long long)g * 2 + (lane >> 3)) * 8 + (lane & 7));
+            GranuleChan c[2];
+            c[0] = make_chan(w0a, w1a, w2a, __ldg(B.meta + (long long)g * 2));
+            c[1] = make_chan(w0b, w1b, w2b, valid_b ? __ldg(B.meta + (long long)g * 2 + 1) : 0u);
+            __syncwarp();
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ch++) {
+                if (ch == 1 && !valid_b) break;
+                const int16_t *is = B.is16 + ((long long)g * 2 + ch) * 576;
+#pragma unroll 3
+                for (int i = lane; i < 576; i += 32) {
+                    int dst;
+                    float r = requant_line(T, cfg, c[ch], s_pk[ch], i, i < c[ch].cnt1 ? (int)__ldg(is + i) : 0, &dst);
+                    s_x[ch][xr_pad(dst)] = r;
+                }
+            }
+            __syncwarp();
+            // ---------------- stereo (frame.go:362-420) -------------------------------------------------
+            if (valid_b && u_mode(w2a) == 1) {
+                const int mode_ext = u_modeext(w2a);
+                if (mode_ext & 2) {
+                    const int max_pos = c[0].cnt1 > c[1].cnt1 ? c[0].cnt1 : c[1].cnt1;
+                    const float inv_sqrt2 = 0.70710678118654752440f;
+                    for (int i = lane; i < max_pos; i += 32) {
+                        const int p = xr_pad(i);
+                        float a = s_x[0][p], b = s_x[1][p];
+                        s_x[0][p] = f_mul(f_add(a, b), inv_sqrt2);
+                        s_x[1][p] = f_mul(f_sub(a, b), inv_sqrt2);
+                    }
+                    __syncwarp();
+                }
+                if (mode_ext & 1) {
+                    for (int i = lane; i < 576; i += 32) {
+                        int is_pos = intensity_pos(T, cfg, c[0], s_pk[0], c[1].cnt1, i);
+                        if (is_pos < 7) {
+                            const int p = xr_pad(i);
+                            s_x[0][p] = f_mul(s_x[0][p], T.is_ratio_l[is_pos]);
+                            s_x[1][p] = f_mul(s_x[1][p], T.is_ratio_r[is_pos]);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            // ---------------- alias reduction (frame.go:427-452) ----------------------------------------
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ch++) {
+                if (ch == 1 && !valid_b) break;
+                const int nb = alias_butterflies(c[ch]);
+                for (int b = lane; b < nb; b += 32) {
+                    const int sb = (b >> 3) + 1, i = b & 7;
+                    const int li = 18 * sb - 1 - i + (sb - 1), ui = 18 * sb + i + sb;  // padded positions
+                    const float xl = s_x[ch][li], xu = s_x[ch][ui];
+                    s_x[ch][li] = f_sub(f_mul(xl, T.cs[i]), f_mul(xu, T.ca[i]));
+                    s_x[ch][ui] = f_add(f_mul(xu, T.cs[i]), f_mul(xl, T.ca[i]));
+                }
+            }
+            __syncwarp();
+
+            // ---------------- K3: IMDCT, lane = subband (frame.go:454-486) ------------------------------
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ch++) {
+                if (ch == 1 && !valid_b) break;
+                float in[18];
 #pragma unroll
-            for (int i = 0; i < 18; i++) st[i] = 0.0f;
-        }
-        if (!u_valid(w2)) {
-            // channel absent in this granule (mono): state restarts from zero afterwards
+                for (int m = 0; m < 18; m++) in[m] = s_x[ch][lane * kXrStride + m];
+                if (TAPS && need_first && B.tap_xr) {
+                    float *o = B.tap_xr + ((long long)g * 2 + ch) * 576 + lane * 18;
 #pragma unroll
-            for (int i = 0; i < 18; i++) st[i] = 0.0f;
-            continue;
-        }
-        float in[18], raw[36];
-        const float *src = B.xr_t + ((long long)g * 2 + ch) * 576;
-#pragma unroll
-        for (int m = 0; m < 18; m++) in[m] = src[m * 32 + lane];
-        imdct_granule<0>(in, raw, w0, w2, lane);
-        float *dst = B.hyb[ch] + (long long)g * 18 * 32 + lane;
-#pragma unroll
-        for (int i = 0; i < 18; i++) {
-            float v = __fadd_rn(raw[i], st[i]);  // frame.go:474
-            st[i] = raw[i + 18];                 // frame.go:475
-            if ((i & 1) && (lane & 1)) v = -v;   // frame.go:480-486
-            dst[i * 32] = v;
+                    for (int m = 0; m < 18; m++) o[m] = in[m];
+                }
+                HybridSink sink{B.hyb + ((long long)g * 2 + ch) * 576, s_ov[ch], lane, need_first};
+                hybrid_channel(in, sink, ch ? w0b : w0a, ch ? w2b : w2a, lane);
+            }
+            __syncwarp();
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// K4: polyphase synthesis.  One thread per time slot; CTA = kK4Threads consecutive slots of which
-// the first 16 are the V-history halo (matrixing only).
+// k_synth = K4: polyphase synthesis + int16 clamp/interleave (frame.go:630-688).
+//
+// CTA = 256 consecutive time slots of the wave (slot = granule*18 + t), the first 16 being the
+// V-history halo of the 240 output slots.
+//   Phase A (matrixing, frame.go:644-650): one THREAD per slot, both channels.  The 32 subband
+//     samples of the slot sit in registers and the cosine matrix is compile-time, so every
+//     multiply-add is an FFMA with an immediate coefficient.  Only the 33 rows that are unique
+//     are computed: synthNWin[32-i][j] == -synthNWin[i][j] (i = 1..16) and
+//     synthNWin[48+m][j] == synthNWin[48-m][j] (m = 1..15) hold BITWISE in the float32 table, and
+//     a sum of negated terms in the same order is the exact negation.  Row u of the slot goes to
+//     shared memory: U[0..16] = V[0..16], U[17..32] = V[33..48].
+//   Phase B (window, frame.go:651-678): one WARP per 30 consecutive output slots, lane = output
+//     index i, marching in time with the 15-slot V history in registers (circular, period 15) and
+//     D[32d + i] in registers; taps accumulate in the reference's order (d ascending).  Both
+//     channels are done together so the int16 pair is packed and stored as one coalesced word.
 // ------------------------------------------------------------------------------------------
-constexpr int kK4Threads = 128;
-constexpr int kK4Halo = 16;
-constexpr int kK4Slots = kK4Threads - kK4Halo;  // output slots per CTA
-constexpr int kVStride = 68;                    // floats per V row: 16-byte aligned, conflict-free for 128-bit LDS
+constexpr int kSynThreads = 256;
+constexpr int kSynHalo = 16;
+constexpr int kSynOut = kSynThreads - kSynHalo;  // 240 = 8 warps x 30 slots
+constexpr int kURow = 36;                        // floats per U row: 16-byte aligned, conflict-free 128-bit stores
+constexpr int kSynSmemBytes = 2 * kSynThreads * kURow * 4 + kSynThreads;
 
 __device__ __forceinline__ int pcm_from_float(float sum) {
     // frame.go:663-668: int(sum * 32767) truncates; Go on amd64 (CVTTSS2SQ) yields INT64_MIN for NaN / out of
@@ -317,97 +367,159 @@ __device__ __forceinline__ int pcm_from_float(float sum) {
     return max(-32767, min(32767, s));
 }
 
-__global__ void __launch_bounds__(kK4Threads)
+// NR consecutive rows of V for one slot: V[i] = sum_j N[i][j] * s[j], j ascending (frame.go:644-650)
+template <int R0, int NR>
+__device__ __forceinline__ void matrix_rows(const float (&s)[32], float *urow, int u0) {
+    float acc[NR];
+#pragma unroll
+    for (int r = 0; r < NR; r++) acc[r] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+#pragma unroll
+        for (int r = 0; r < NR; r++) acc[r] = mac(kSynthN[R0 + r][j], s[j], acc[r]);
+    }
+    if (NR == 4) {
+        *reinterpret_cast<float4 *>(urow + u0) = make_float4(acc[0], acc[1], acc[2], acc[3]);  // u0 % 4 == 0
+    } else {
+#pragma unroll
+        for (int r = 0; r < NR; r++) urow[u0 + r] = acc[r];
+    }
+}
+
+__device__ __forceinline__ void matrix_slot(const float *__restrict__ src, float *urow) {
+    float s[32];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + q);
+        s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
+    }
+    // rows 0..16 -> U[0..16]; rows 33..48 -> U[17..32]
+    matrix_rows<0, 4>(s, urow, 0);   matrix_rows<4, 4>(s, urow, 4);   matrix_rows<8, 4>(s, urow, 8);
+    matrix_rows<12, 4>(s, urow, 12); matrix_rows<16, 1>(s, urow, 16);
+    matrix_rows<33, 3>(s, urow, 17); matrix_rows<36, 4>(s, urow, 20); matrix_rows<40, 4>(s, urow, 24);
+    matrix_rows<44, 4>(s, urow, 28); matrix_rows<48, 1>(s, urow, 32);
+}
+
+template <int P>
+__device__ __forceinline__ float window_sum(const float (&A)[15], const float (&Bh)[15], const float (&dw)[16]) {
+    // out[i] = sum_d V_{t-d}[(d odd ? 32 : 0) + i] * D[32 d + i], d ascending (U construction, frame.go:651-661).
+    // Slot t-d lives at circular position (P - d) mod 15; A[P] already holds slot t, Bh[P] still holds slot t-15.
+    float sum = 0.0f;
+#pragma unroll
+    for (int d = 0; d < 16; d++) {
+        const int h = (P - d + 30) % 15;
+        sum = mac((d & 1) ? Bh[h] : A[h], dw[d], sum);
+    }
+    return sum;
+}
+
+struct SynLane {  // where lane i finds V[i] and V[32+i] in a U row, and with which sign
+    int ai, bi;
+    uint32_t sa, sb;  // sign-bit masks
+};
+
+// One slot of phase B at circular position P.  FAST: the caller has checked that this and the other 14 rows of the
+// block are plain stereo slots (both channels present, no state reset), so there are no flag tests at all.
+template <int P, bool FAST, bool WARMUP>
+__device__ __forceinline__ void synth_window_slot(const float *U0, const float *U1, const uint8_t *flags, int row, const SynLane &L,
+                                                  const float (&dw)[16], float (&A0)[15], float (&B0)[15], float (&A1)[15], float (&B1)[15],
+                                                  uint32_t *pcm32, long long sigma, long long n_slots, int lane) {
+    const int f = FAST ? 3 : flags[row];
+    if (!FAST && (f & 4)) {  // first slot of a ZERO_STATE granule: Frame.vVec is zero (frame.go:49)
+#pragma unroll
+        for (int i = 0; i < 15; i++) { A0[i] = B0[i] = A1[i] = B1[i] = 0.f; }
+    }
+    uint32_t pl = 0, pr = 0;
+    if (f & 1) {
+        const float a = __uint_as_float(__float_as_uint(U0[row * kURow + L.ai]) ^ L.sa);
+        const float b = __uint_as_float(__float_as_uint(U0[row * kURow + L.bi]) ^ L.sb);
+        A0[P] = a;
+        if (!WARMUP) pl = (uint32_t)pcm_from_float(window_sum<P>(A0, B0, dw)) & 0xffffu;
+        B0[P] = b;
+    }
+    if (f & 2) {
+        const float a = __uint_as_float(__float_as_uint(U1[row * kURow + L.ai]) ^ L.sa);
+        const float b = __uint_as_float(__float_as_uint(U1[row * kURow + L.bi]) ^ L.sb);
+        A1[P] = a;
+        if (!WARMUP) pr = (uint32_t)pcm_from_float(window_sum<P>(A1, B1, dw)) & 0xffffu;
+        B1[P] = b;
+    } else {
+        pr = pl;  // mono: both output channels carry channel 0 (frame.go:671-678)
+    }
+    if (!WARMUP && (f & 1) && (FAST || sigma < n_slots)) pcm32[sigma * 32 + lane] = pl | (pr << 16);
+}
+
+// 15 consecutive rows starting at `rb` (circular positions 0..14).
+template <bool FAST, bool WARMUP>
+__device__ __forceinline__ void synth_window_block(const float *U0, const float *U1, const uint8_t *flags, int rb, const SynLane &L,
+                                                   const float (&dw)[16], float (&A0)[15], float (&B0)[15], float (&A1)[15], float (&B1)[15],
+                                                   uint32_t *pcm32, long long sb, long long n_slots, int lane) {
+#define MP3_SLOT(Pp) synth_window_slot<Pp, FAST, WARMUP>(U0, U1, flags, rb + Pp, L, dw, A0, B0, A1, B1, pcm32, sb + Pp, n_slots, lane);
+    MP3_SLOT(0) MP3_SLOT(1) MP3_SLOT(2) MP3_SLOT(3) MP3_SLOT(4) MP3_SLOT(5) MP3_SLOT(6) MP3_SLOT(7)
+    MP3_SLOT(8) MP3_SLOT(9) MP3_SLOT(10) MP3_SLOT(11) MP3_SLOT(12) MP3_SLOT(13) MP3_SLOT(14)
+#undef MP3_SLOT
+}
+
+__global__ void __launch_bounds__(kSynThreads, 2)
 k_synth(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_granules, WaveBufs B,
         int16_t *__restrict__ pcm /* wave-local: [n_granules][576][2] */) {
-    __shared__ __align__(16) float s_v[kK4Threads * kVStride];
+    extern __shared__ __align__(16) float s_u[];  // U[2][256][36], then flags[256]
+    float *U0 = s_u, *U1 = s_u + kSynThreads * kURow;
+    uint8_t *flags = reinterpret_cast<uint8_t *>(s_u + 2 * kSynThreads * kURow);
     const int tid = threadIdx.x;
-    const long long t = (long long)blockIdx.x * kK4Slots - kK4Halo + tid;  // wave-local slot index
     const long long n_slots = (long long)n_granules * 18;
-    const bool in_range = t >= -18 && t < n_slots && (first_granule * 18 + t) >= 0;
-    const bool is_out = tid >= kK4Halo && t < n_slots;
-    long long g = 0;
-    uint32_t w2a = 0, w2b = 0;
-    int slot_in_gr = 0;
-    if (in_range) {
-        g = t >= 0 ? t / 18 : -1;
-        slot_in_gr = (int)(t - g * 18);
-        const mp3gpu_unit *ug = units + (first_granule + g) * 2;
-        w2a = ug[0].w2;
-        w2b = ug[1].w2;
-    }
-    // History available to this slot: a zero-state granule has nothing before its first slot.
-    const int hist = (in_range && u_zero(w2a)) ? slot_in_gr : 15;
-    uint32_t packed[32];  // per sample: L | R<<16
-#pragma unroll
-    for (int i = 0; i < 32; i++) packed[i] = 0;
+    const long long cta_first = (long long)blockIdx.x * kSynOut - kSynHalo;  // wave-local slot of row 0
 
+    // ---------------- phase A: matrixing, thread = slot ---------------------------------------------
+    {
+        const long long sigma = cta_first + tid;
+        const bool in_range = sigma >= -18 && sigma < n_slots && (first_granule * 18 + sigma) >= 0;
+        int f = 0;
+        if (in_range) {
+            const long long g = sigma >= 0 ? sigma / 18 : -1;
+            const int t = (int)(sigma - g * 18);
+            const mp3gpu_unit *ug = units + (first_granule + g) * 2;
+            const uint32_t w2a = __ldg(&ug[0].w2), w2b = __ldg(&ug[1].w2);
+            if (u_valid(w2a)) {
+                f = 1 | (u_valid(w2b) ? 2 : 0) | ((u_zero(w2a) && t == 0) ? 4 : 0);
 #pragma unroll 1
-    for (int ch = 0; ch < 2; ch++) {
-        const bool valid = in_range && u_valid(ch ? w2b : w2a);
-        float *vrow = s_v + tid * kVStride;
-        if (valid) {
-            float s[32];
-            const float4 *src = reinterpret_cast<const float4 *>(B.hyb[ch] + t * 32);
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                float4 v = __ldg(src + q);
-                s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
-            }
-            // Matrixing: V[i] = sum_j N[i][j] * s[j], j ascending (frame.go:644-650)
-#pragma unroll
-            for (int i4 = 0; i4 < 16; i4++) {
-                float v4[4];
-#pragma unroll
-                for (int ii = 0; ii < 4; ii++) {
-                    const int i = i4 * 4 + ii;
-                    float sum = 0.0f;
-#pragma unroll
-                    for (int j = 0; j < 32; j++) sum = mac(c_synth_n[i * 32 + j], s[j], sum);
-                    v4[ii] = sum;
-                }
-                *reinterpret_cast<float4 *>(vrow + i4 * 4) = make_float4(v4[0], v4[1], v4[2], v4[3]);
-            }
-        } else {
-#pragma unroll
-            for (int i4 = 0; i4 < 16; i4++) *reinterpret_cast<float4 *>(vrow + i4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncthreads();
-        if (is_out && valid) {
-            // out[i] = sum over k of V[t-2k][i]*D[64k+i] then V[t-2k-1][32+i]*D[64k+32+i]
-            // (U construction frame.go:651-661), taps ascending.
-#pragma unroll
-            for (int i4 = 0; i4 < 8; i4++) {
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int d = 0; d < 16; d++) {
-                    // d even: row t-d, columns i ; d odd: row t-d, columns 32+i
-                    const int col = (d & 1) ? 32 + i4 * 4 : i4 * 4;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (d <= hist) v = *reinterpret_cast<const float4 *>(s_v + (tid - d) * kVStride + col);
-                    const int dbase = (d >> 1) * 64 + ((d & 1) ? 32 : 0) + i4 * 4;
-                    acc[0] = mac(v.x, c_synth_d[dbase + 0], acc[0]);
-                    acc[1] = mac(v.y, c_synth_d[dbase + 1], acc[1]);
-                    acc[2] = mac(v.z, c_synth_d[dbase + 2], acc[2]);
-                    acc[3] = mac(v.w, c_synth_d[dbase + 3], acc[3]);
-                }
-#pragma unroll
-                for (int ii = 0; ii < 4; ii++) {
-                    uint32_t s16 = (uint32_t)pcm_from_float(acc[ii]) & 0xffffu;
-                    packed[i4 * 4 + ii] |= ch ? (s16 << 16) : s16;
-                }
+                for (int ch = 0; ch < 2; ch++)  // not unrolled: the 1,056 immediate FFMAs exist once in the code
+                    if (f & (1 << ch)) matrix_slot(B.hyb + ((g * 2 + ch) * 18 + t) * 32, (ch ? U1 : U0) + tid * kURow);
             }
         }
-        __syncthreads();
+        flags[tid] = (uint8_t)f;
     }
-    if (is_out && in_range && u_valid(w2a)) {
-        if (!u_valid(w2b)) {  // mono: duplicate (frame.go:671-678)
+    __syncthreads();
+
+    // ---------------- phase B: window + int16 store, warp = 30 slots, lane = output index -----------
+    const int lane = tid & 31, warp = tid >> 5;
+    SynLane L;
+    L.ai = lane <= 16 ? lane : 32 - lane;                      // V[i]    = i <= 16 ? U[i] : -U[32-i]
+    L.sa = lane <= 16 ? 0u : 0x80000000u;
+    L.bi = lane == 0 ? 0 : (lane <= 16 ? 16 + lane : 48 - lane);  // V[32+i] = i == 0 ? -U[0] : i <= 16 ? U[16+i] : U[48-i]
+    L.sb = lane == 0 ? 0x80000000u : 0u;
+    float dw[16];
 #pragma unroll
-            for (int i = 0; i < 32; i++) packed[i] |= packed[i] << 16;
+    for (int d = 0; d < 16; d++) dw[d] = __ldg(B.synth_d + 32 * d + lane);
+    float A0[15], B0[15], A1[15], B1[15];
+#pragma unroll
+    for (int i = 0; i < 15; i++) { A0[i] = B0[i] = A1[i] = B1[i] = 0.f; }
+    const int r0 = kSynHalo + warp * 30;  // first output row of this warp
+    uint32_t *pcm32 = reinterpret_cast<uint32_t *>(pcm);
+    // Blocks of 15 rows: warm-up (the 15 slots in front; slot -15+p sits at circular position p), then two output
+    // blocks.  A block whose rows are all plain stereo slots takes the branch-free FAST path.
+#pragma unroll 1
+    for (int blk = -1; blk < 2; blk++) {
+        const int rb = r0 + blk * 15;
+        const bool plain = __all_sync(0xffffffffu, lane >= 15 || flags[rb + lane] == 3);
+        const long long sb = cta_first + rb;
+        if (blk < 0) {
+            if (plain) synth_window_block<true, true>(U0, U1, flags, rb, L, dw, A0, B0, A1, B1, pcm32, sb, n_slots, lane);
+            else synth_window_block<false, true>(U0, U1, flags, rb, L, dw, A0, B0, A1, B1, pcm32, sb, n_slots, lane);
+        } else {
+            if (plain) synth_window_block<true, false>(U0, U1, flags, rb, L, dw, A0, B0, A1, B1, pcm32, sb, n_slots, lane);
+            else synth_window_block<false, false>(U0, U1, flags, rb, L, dw, A0, B0, A1, B1, pcm32, sb, n_slots, lane);
         }
-        uint4 *dst = reinterpret_cast<uint4 *>(pcm + t * 64);
-#pragma unroll
-        for (int q = 0; q < 8; q++) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
     }
 }
 

@@ -44,8 +44,12 @@ struct mp3gpu_ctx {
     int16_t *d_is16 = nullptr;
     uint32_t *d_meta = nullptr;
     uint32_t *d_sfpack = nullptr;
-    float *d_xr_t = nullptr;   // (wave+1) granules
-    float *d_hyb[2] = {nullptr, nullptr};  // (wave+1) granules each
+    float *d_hyb = nullptr;          // (wave+1) granules x [2][18][32] subband samples, look-back granule in front
+    float *d_tap_xr = nullptr;       // debug tap (opts.keep_intermediates)
+    float *d_synth = nullptr;        // synth_d[512]
+    unsigned int *d_counter = nullptr;
+    int sm_count = 0;
+    int seg_len = 32;
     // staging for host-buffer calls
     uint8_t *d_main = nullptr;
     size_t d_main_cap = 0;
@@ -54,9 +58,12 @@ struct mp3gpu_ctx {
     int16_t *d_pcm_ring[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_in[3]{}, ev_k[3]{}, ev_out[3]{};
     // timing
-    cudaEvent_t ev_t[kTimingSlots][5]{};
+    cudaEvent_t ev_t[kTimingSlots][4]{};
     cudaEvent_t ev_copy[4]{};
+    cudaEvent_t ev_user[8]{};
     mp3gpu_timings last{};
+    int last_slots = 0;          // timing slots recorded by the last call
+    bool last_collected = true;  // per-kernel times of the last call already read back
     // taps
     size_t last_wave_granules = 0;
     long long last_wave_first = 0;
@@ -70,11 +77,22 @@ static int upload_tables(mp3gpu_ctx *ctx) {
         ctx->err = std::string("table build failed: ") + e.what();
         return MP3GPU_E_INVALID;
     }
-    CK(cudaMemcpyToSymbol(c_cos36, h.cos36, sizeof h.cos36));
-    CK(cudaMemcpyToSymbol(c_cos12, h.cos12, sizeof h.cos12));
+    // The compile-time IMDCT tables (const_tables.inc) must be the ones this host computes.
+    if (memcmp(kCos36_host, h.cos36, sizeof h.cos36) != 0 || memcmp(kCos12_host, h.cos12, sizeof h.cos12) != 0 ||
+        memcmp(kWin_host, h.imdct_win, sizeof h.imdct_win) != 0 || memcmp(kSynthN_host, h.synth_n, sizeof h.synth_n) != 0) {
+        ctx->err = "const_tables.inc does not match the host-built IMDCT tables (rebuild the library on this libm)";
+        return MP3GPU_E_INVALID;
+    }
     CK(cudaMemcpyToSymbol(c_win, h.imdct_win, sizeof h.imdct_win));
-    CK(cudaMemcpyToSymbol(c_synth_n, h.synth_n, sizeof h.synth_n));
-    CK(cudaMemcpyToSymbol(c_synth_d, h.synth_d, sizeof h.synth_d));
+    // the symmetric matrixing of k_synth relies on these identities holding bitwise in the float32 table
+    for (int j = 0; j < 32; j++) {
+        for (int i = 0; i <= 15; i++)
+            if (h.synth_n[(32 - i) * 32 + j] != -h.synth_n[i * 32 + j]) { ctx->err = "synthNWin mirror-16 symmetry does not hold"; return MP3GPU_E_INVALID; }
+        for (int k = 1; k <= 15; k++)
+            if (h.synth_n[(48 + k) * 32 + j] != h.synth_n[(48 - k) * 32 + j]) { ctx->err = "synthNWin mirror-48 symmetry does not hold"; return MP3GPU_E_INVALID; }
+    }
+    CK(cudaMalloc(&ctx->d_synth, 512 * sizeof(float)));
+    CK(cudaMemcpy(ctx->d_synth, h.synth_d, sizeof h.synth_d, cudaMemcpyHostToDevice));
     // maindata.go:39-42
     static const uint8_t slen[16][2] = {{0, 0}, {0, 1}, {0, 2}, {0, 3}, {3, 0}, {1, 1}, {1, 2}, {1, 3},
                                         {2, 1}, {2, 2}, {2, 3}, {3, 1}, {3, 2}, {3, 3}, {4, 2}, {4, 3}};
@@ -154,24 +172,33 @@ extern "C" int mp3gpu_create(int device, const mp3gpu_opts *opts, mp3gpu_ctx **o
         int rc = upload_tables(ctx);
         if (rc) return rc;
         const size_t W = ctx->wave;
-        CK(cudaMalloc(&ctx->d_is16, W * 2 * 576 * sizeof(int16_t)));
-        CK(cudaMalloc(&ctx->d_meta, W * 2 * sizeof(uint32_t)));
-        CK(cudaMalloc(&ctx->d_sfpack, W * 2 * 8 * sizeof(uint32_t)));
-        CK(cudaMalloc(&ctx->d_xr_t, (W + 1) * 2 * 576 * sizeof(float)));
-        CK(cudaMemset(ctx->d_xr_t, 0, 2 * 576 * sizeof(float)));
-        for (int c = 0; c < 2; c++) {
-            CK(cudaMalloc(&ctx->d_hyb[c], (W + 1) * 576 * sizeof(float)));
-            CK(cudaMemset(ctx->d_hyb[c], 0, 576 * sizeof(float)));
-        }
+        // K1 outputs, with two look-back granules (halo of the fused kernel) in front
+        CK(cudaMalloc(&ctx->d_is16, (W + 2) * 2 * 576 * sizeof(int16_t)));
+        CK(cudaMalloc(&ctx->d_meta, (W + 2) * 2 * sizeof(uint32_t)));
+        CK(cudaMalloc(&ctx->d_sfpack, (W + 2) * 2 * 8 * sizeof(uint32_t)));
+        CK(cudaMemset(ctx->d_is16, 0, 2 * 2 * 576 * sizeof(int16_t)));
+        CK(cudaMemset(ctx->d_meta, 0, 2 * 2 * sizeof(uint32_t)));
+        CK(cudaMemset(ctx->d_sfpack, 0, 2 * 2 * 8 * sizeof(uint32_t)));
+        CK(cudaMalloc(&ctx->d_hyb, (W + 1) * 2 * 576 * sizeof(float)));
+        CK(cudaMemset(ctx->d_hyb, 0, 2 * 576 * sizeof(float)));
+        if (ctx->opts.keep_intermediates) CK(cudaMalloc(&ctx->d_tap_xr, W * 2 * 576 * sizeof(float)));
+        CK(cudaMalloc(&ctx->d_counter, sizeof(unsigned int)));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        ctx->sm_count = prop.multiProcessorCount;
         for (int i = 0; i < 3; i++) {
             CK(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
         }
         for (int i = 0; i < kTimingSlots; i++)
-            for (int j = 0; j < 5; j++) CK(cudaEventCreate(&ctx->ev_t[i][j]));
+            for (int j = 0; j < 4; j++) CK(cudaEventCreate(&ctx->ev_t[i][j]));
         for (int i = 0; i < 4; i++) CK(cudaEventCreate(&ctx->ev_copy[i]));
+        for (int i = 0; i < 8; i++) CK(cudaEventCreate(&ctx->ev_user[i]));
         CK(cudaFuncSetAttribute(k_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->lut_bytes));
+        CK(cudaFuncSetAttribute(k_hybrid<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHybSmemBytes));
+        CK(cudaFuncSetAttribute(k_hybrid<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHybSmemBytes));
+        CK(cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, kSynSmemBytes));
         return MP3GPU_OK;
     };
     int rc = init();
@@ -188,9 +215,10 @@ extern "C" void mp3gpu_destroy(mp3gpu_ctx *ctx) {
     cudaFree(ctx->d_is16);
     cudaFree(ctx->d_meta);
     cudaFree(ctx->d_sfpack);
-    cudaFree(ctx->d_xr_t);
-    cudaFree(ctx->d_hyb[0]);
-    cudaFree(ctx->d_hyb[1]);
+    cudaFree(ctx->d_hyb);
+    cudaFree(ctx->d_tap_xr);
+    cudaFree(ctx->d_synth);
+    cudaFree(ctx->d_counter);
     cudaFree(ctx->d_main);
     cudaFree(ctx->d_units);
     for (int i = 0; i < 3; i++) {
@@ -200,10 +228,12 @@ extern "C" void mp3gpu_destroy(mp3gpu_ctx *ctx) {
         if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
     }
     for (int i = 0; i < kTimingSlots; i++)
-        for (int j = 0; j < 5; j++)
+        for (int j = 0; j < 4; j++)
             if (ctx->ev_t[i][j]) cudaEventDestroy(ctx->ev_t[i][j]);
     for (int i = 0; i < 4; i++)
         if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
+    for (int i = 0; i < 8; i++)
+        if (ctx->ev_user[i]) cudaEventDestroy(ctx->ev_user[i]);
     if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
@@ -217,12 +247,13 @@ extern "C" const char *mp3gpu_last_error(const mp3gpu_ctx *ctx) { return ctx ? c
 static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, const mp3gpu_unit *d_units, long long first, int n,
                        int16_t *d_pcm_wave, int slot) {
     WaveBufs B;
-    B.is16 = ctx->d_is16;
-    B.meta = ctx->d_meta;
-    B.sfpack = ctx->d_sfpack;
-    B.xr_t = ctx->d_xr_t + 2 * 576;       // slot -1 lives in front
-    B.hyb[0] = ctx->d_hyb[0] + 576;
-    B.hyb[1] = ctx->d_hyb[1] + 576;
+    B.is16 = ctx->d_is16 + 2 * 2 * 576;  // granules -2, -1 live in front
+    B.meta = ctx->d_meta + 2 * 2;
+    B.sfpack = ctx->d_sfpack + 2 * 2 * 8;
+    B.hyb = ctx->d_hyb + 2 * 576;        // granule -1 lives in front
+    B.tap_xr = ctx->d_tap_xr;
+    B.synth_d = ctx->d_synth;
+    B.work_counter = ctx->d_counter;
     cudaStream_t s = ctx->s_compute;
     if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][0], s));
     {
@@ -230,57 +261,69 @@ static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, const mp3gpu_unit
         k_huffman<<<(nu + 127) / 128, 128, ctx->lut_bytes, s>>>(d_main, d_units, first * 2, nu, ctx->T, B);
     }
     if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][1], s));
-    k_requant<<<(n + kK2Warps - 1) / kK2Warps, kK2Warps * 32, 0, s>>>(d_units, first, n, ctx->T, B);
+    {
+        CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), s));
+        const int n_segs = (n + ctx->seg_len - 1) / ctx->seg_len;
+        const int grid = std::min((n_segs + kHybWarps - 1) / kHybWarps, ctx->sm_count * 5);
+        if (ctx->d_tap_xr) {
+            CK(cudaMemsetAsync(ctx->d_tap_xr, 0, (size_t)n * 2 * 576 * sizeof(float), s));
+            CK(cudaMemsetAsync(B.hyb, 0, (size_t)n * 2 * 576 * sizeof(float), s));  // taps of absent channels read as 0
+            k_hybrid<true><<<grid, kHybWarps * 32, kHybSmemBytes, s>>>(d_units, first, n, ctx->seg_len, n_segs, ctx->T, B);
+        } else {
+            k_hybrid<false><<<grid, kHybWarps * 32, kHybSmemBytes, s>>>(d_units, first, n, ctx->seg_len, n_segs, ctx->T, B);
+        }
+    }
     if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][2], s));
     {
-        int runs = (n + kRun - 1) / kRun;
-        int items = runs * 2;
-        k_imdct<<<(items + kK3Warps - 1) / kK3Warps, kK3Warps * 32, 0, s>>>(d_units, first, n, B);
+        const long long slots = (long long)n * 18;
+        const int grid = (int)((slots + kSynOut - 1) / kSynOut);
+        k_synth<<<grid, kSynThreads, kSynSmemBytes, s>>>(d_units, first, n, B, d_pcm_wave);
     }
     if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][3], s));
-    {
-        long long slots = (long long)n * 18;
-        int grid = (int)((slots + kK4Slots - 1) / kK4Slots);
-        k_synth<<<grid, kK4Threads, 0, s>>>(d_units, first, n, B, d_pcm_wave);
+    // Carry the last granule's subband samples into the look-back slot for the next wave's k_synth halo.
+    CK(cudaMemcpyAsync(ctx->d_hyb, B.hyb + (size_t)(n - 1) * 2 * 576, 2 * 576 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    // Carry K1's outputs of the last two granules into the look-back slots for the next wave.  In order k = 0, 1
+    // so that a one-granule wave shifts slot -1 to slot -2 before overwriting it.
+    for (int k = 0; k < 2; k++) {
+        const long long src = (long long)n - 2 + k;  // wave-local granule index; negative = an old look-back slot
+        CK(cudaMemcpyAsync(B.is16 + (k - 2) * 2 * 576, B.is16 + src * 2 * 576, 2 * 576 * sizeof(int16_t), cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(B.meta + (k - 2) * 2, B.meta + src * 2, 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(B.sfpack + (k - 2) * 2 * 8, B.sfpack + src * 2 * 8, 2 * 8 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
     }
-    if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][4], s));
-    // Carry the look-back slots for the next wave: last granule's xr_t and hybrid rows -> slot -1.
-    CK(cudaMemcpyAsync(ctx->d_xr_t, B.xr_t + (size_t)(n - 1) * 2 * 576, 2 * 576 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    for (int c = 0; c < 2; c++)
-        CK(cudaMemcpyAsync(ctx->d_hyb[c], B.hyb[c] + (size_t)(n - 1) * 576, 576 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     CK(cudaGetLastError());
-    ctx->last.launches += 4;
+    ctx->last.launches += 3;
     ctx->last_wave_first = first;
     ctx->last_wave_granules = (size_t)n;
     return MP3GPU_OK;
 }
 
 static int collect_timings(mp3gpu_ctx *ctx, int nslots) {
-    float k[4] = {0, 0, 0, 0};
+    float k[3] = {0, 0, 0};
     for (int i = 0; i < nslots; i++)
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < 3; j++) {
             float ms = 0;
             CK(cudaEventElapsedTime(&ms, ctx->ev_t[i][j], ctx->ev_t[i][j + 1]));
             k[j] += ms;
         }
     ctx->last.k1_huffman_ms = k[0];
-    ctx->last.k2_requant_ms = k[1];
-    ctx->last.k3_imdct_ms = k[2];
-    ctx->last.k4_synth_ms = k[3];
+    ctx->last.k_hybrid_ms = k[1];
+    ctx->last.k_synth_ms = k[2];
     if (nslots > 0) {
         float ms = 0;
-        CK(cudaEventElapsedTime(&ms, ctx->ev_t[0][0], ctx->ev_t[nslots - 1][4]));
+        CK(cudaEventElapsedTime(&ms, ctx->ev_t[0][0], ctx->ev_t[nslots - 1][3]));
         ctx->last.total_ms = ms;
     }
     return MP3GPU_OK;
 }
 
-extern "C" int mp3gpu_decode_device(mp3gpu_ctx *ctx, const uint8_t *d_main_data, size_t main_data_len,
-                                    const mp3gpu_unit *d_units, size_t n_granules, int16_t *d_pcm_out) {
+extern "C" int mp3gpu_decode_device_async(mp3gpu_ctx *ctx, const uint8_t *d_main_data, size_t main_data_len,
+                                          const mp3gpu_unit *d_units, size_t n_granules, int16_t *d_pcm_out) {
     if (!ctx) return MP3GPU_E_INVALID;
     (void)main_data_len;
     CK(cudaSetDevice(ctx->device));
     ctx->last = mp3gpu_timings{};
+    ctx->last_slots = 0;
+    ctx->last_collected = true;
     if (n_granules == 0) return MP3GPU_OK;
     int slot = 0;
     for (size_t first = 0; first < n_granules; first += ctx->wave) {
@@ -291,8 +334,32 @@ extern "C" int mp3gpu_decode_device(mp3gpu_ctx *ctx, const uint8_t *d_main_data,
         if (slot < kTimingSlots) slot++;
         ctx->last.waves++;
     }
+    ctx->last_slots = slot;
+    ctx->last_collected = false;
+    return MP3GPU_OK;
+}
+
+extern "C" int mp3gpu_decode_device(mp3gpu_ctx *ctx, const uint8_t *d_main_data, size_t main_data_len,
+                                    const mp3gpu_unit *d_units, size_t n_granules, int16_t *d_pcm_out) {
+    int rc = mp3gpu_decode_device_async(ctx, d_main_data, main_data_len, d_units, n_granules, d_pcm_out);
+    if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->s_compute));
-    return collect_timings(ctx, slot);
+    return MP3GPU_OK;
+}
+
+extern "C" int mp3gpu_event_record(mp3gpu_ctx *ctx, int which) {
+    if (!ctx || which < 0 || which >= 8) return MP3GPU_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev_user[which], ctx->s_compute));
+    return MP3GPU_OK;
+}
+
+extern "C" int mp3gpu_event_elapsed_ms(mp3gpu_ctx *ctx, int from, int to, float *ms) {
+    if (!ctx || !ms || from < 0 || from >= 8 || to < 0 || to >= 8) return MP3GPU_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->ev_user[to]));
+    CK(cudaEventElapsedTime(ms, ctx->ev_user[from], ctx->ev_user[to]));
+    return MP3GPU_OK;
 }
 
 template <typename T>
@@ -312,6 +379,8 @@ extern "C" int mp3gpu_decode(mp3gpu_ctx *ctx, const uint8_t *main_data, size_t m
     if (!ctx) return MP3GPU_E_INVALID;
     CK(cudaSetDevice(ctx->device));
     ctx->last = mp3gpu_timings{};
+    ctx->last_slots = 0;
+    ctx->last_collected = true;
     if (n_granules == 0) return MP3GPU_OK;
     if (!main_data || !units || !pcm_out) {
         ctx->err = "null pointer";
@@ -380,8 +449,8 @@ extern "C" int mp3gpu_decode(mp3gpu_ctx *ctx, const uint8_t *main_data, size_t m
     CK(cudaStreamSynchronize(ctx->s_in));
     CK(cudaStreamSynchronize(ctx->s_compute));
     CK(cudaStreamSynchronize(ctx->s_out));
-    rc = collect_timings(ctx, slot);
-    if (rc) return rc;
+    ctx->last_slots = slot;
+    ctx->last_collected = false;
     CK(cudaEventElapsedTime(&ctx->last.h2d_ms, ctx->ev_copy[0], ctx->ev_copy[1]));
     CK(cudaEventElapsedTime(&ctx->last.d2h_ms, ctx->ev_copy[2], ctx->ev_copy[3]));
     return MP3GPU_OK;
@@ -435,8 +504,15 @@ extern "C" int mp3gpu_synchronize(mp3gpu_ctx *ctx) {
     return MP3GPU_OK;
 }
 
-extern "C" int mp3gpu_last_timings(const mp3gpu_ctx *ctx, mp3gpu_timings *out) {
+extern "C" int mp3gpu_last_timings(mp3gpu_ctx *ctx, mp3gpu_timings *out) {
     if (!ctx || !out) return MP3GPU_E_INVALID;
+    if (!ctx->last_collected) {
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaStreamSynchronize(ctx->s_compute));
+        int rc = collect_timings(ctx, ctx->last_slots);
+        if (rc) return rc;
+        ctx->last_collected = true;
+    }
     *out = ctx->last;
     return MP3GPU_OK;
 }
@@ -450,11 +526,14 @@ extern "C" int mp3gpu_debug_read(mp3gpu_ctx *ctx, int tap, size_t first, size_t 
     CK(cudaSetDevice(ctx->device));
     CK(cudaDeviceSynchronize());
     std::vector<uint32_t> meta(n * 2);
-    CK(cudaMemcpy(meta.data(), ctx->d_meta + first * 2, n * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    const int16_t *d_is = ctx->d_is16 + 2 * 2 * 576;
+    const uint32_t *d_meta = ctx->d_meta + 2 * 2;
+    const uint32_t *d_sf = ctx->d_sfpack + 2 * 2 * 8;
+    CK(cudaMemcpy(meta.data(), d_meta + first * 2, n * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     switch (tap) {
     case MP3GPU_TAP_IS: {
         int16_t *o = (int16_t *)host_out;
-        CK(cudaMemcpy(o, ctx->d_is16 + first * 2 * 576, n * 2 * 576 * sizeof(int16_t), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(o, d_is + first * 2 * 576, n * 2 * 576 * sizeof(int16_t), cudaMemcpyDeviceToHost));
         for (size_t u = 0; u < n * 2; u++) {
             size_t c1 = meta[u] & 0x3ff;
             for (size_t i = c1; i < 576; i++) o[u * 576 + i] = 0;  // rzero region (huffman.go:130-134)
@@ -468,7 +547,7 @@ extern "C" int mp3gpu_debug_read(mp3gpu_ctx *ctx, int tap, size_t first, size_t 
     }
     case MP3GPU_TAP_SCALEFAC: {
         std::vector<uint32_t> pk(n * 2 * 8);
-        CK(cudaMemcpy(pk.data(), ctx->d_sfpack + first * 2 * 8, pk.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(pk.data(), d_sf + first * 2 * 8, pk.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
         uint8_t *o = (uint8_t *)host_out;
         for (size_t u = 0; u < n * 2; u++) {
             for (int k = 0; k < 64; k++) o[u * 64 + k] = (uint8_t)((pk[u * 8 + (k >> 3)] >> (4 * (k & 7))) & 0xf);
@@ -477,23 +556,24 @@ extern "C" int mp3gpu_debug_read(mp3gpu_ctx *ctx, int tap, size_t first, size_t 
         return MP3GPU_OK;
     }
     case MP3GPU_TAP_XR: {
-        std::vector<float> t(n * 2 * 576);
-        CK(cudaMemcpy(t.data(), ctx->d_xr_t + (first + 1) * 2 * 576, t.size() * sizeof(float), cudaMemcpyDeviceToHost));
-        float *o = (float *)host_out;
-        for (size_t u = 0; u < n * 2; u++)
-            for (int m = 0; m < 18; m++)
-                for (int sb = 0; sb < 32; sb++) o[u * 576 + sb * 18 + m] = t[u * 576 + m * 32 + sb];
+        if (!ctx->d_tap_xr) {
+            ctx->err = "debug_read: create the context with opts.keep_intermediates = 1";
+            return MP3GPU_E_INVALID;
+        }
+        CK(cudaMemcpy(host_out, ctx->d_tap_xr + first * 2 * 576, n * 2 * 576 * sizeof(float), cudaMemcpyDeviceToHost));
         return MP3GPU_OK;
     }
     case MP3GPU_TAP_HYBRID: {
-        float *o = (float *)host_out;
-        std::vector<float> t(n * 576);
-        for (int c = 0; c < 2; c++) {
-            CK(cudaMemcpy(t.data(), ctx->d_hyb[c] + (first + 1) * 576, t.size() * sizeof(float), cudaMemcpyDeviceToHost));
-            for (size_t g = 0; g < n; g++)
-                for (int i = 0; i < 18; i++)
-                    for (int sb = 0; sb < 32; sb++) o[(g * 2 + c) * 576 + sb * 18 + i] = t[g * 576 + i * 32 + sb];
+        if (!ctx->d_tap_xr) {
+            ctx->err = "debug_read: create the context with opts.keep_intermediates = 1";
+            return MP3GPU_E_INVALID;
         }
+        std::vector<float> t(n * 2 * 576);
+        CK(cudaMemcpy(t.data(), ctx->d_hyb + (first + 1) * 2 * 576, t.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        float *o = (float *)host_out;
+        for (size_t u = 0; u < n * 2; u++)
+            for (int i = 0; i < 18; i++)
+                for (int sb = 0; sb < 32; sb++) o[u * 576 + sb * 18 + i] = t[u * 576 + i * 32 + sb];
         return MP3GPU_OK;
     }
     }

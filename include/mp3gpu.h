@@ -116,10 +116,10 @@ typedef struct mp3gpu_opts {
 
 /* Per-kernel device time of the last decode call, from CUDA events on the launch stream. */
 typedef struct mp3gpu_timings {
-    float k1_huffman_ms;   /* scalefactors + Huffman          */
-    float k2_requant_ms;   /* requantise/reorder/stereo/alias */
-    float k3_imdct_ms;     /* IMDCT + window + overlap        */
-    float k4_synth_ms;     /* polyphase synthesis + int16     */
+    float k1_huffman_ms;   /* k_huffman : scalefactors + Huffman                                   */
+    float k_hybrid_ms;     /* k_hybrid  : requantise/reorder/stereo/alias + IMDCT/window/overlap   */
+    float k_synth_ms;      /* k_synth   : polyphase synthesis + int16 clamp/interleave             */
+    float reserved_ms;
     float total_ms;        /* first kernel start -> last kernel end (includes copies overlapped in between) */
     float h2d_ms, d2h_ms;  /* copy time on the copy streams (host-buffer calls only) */
     uint32_t waves;
@@ -144,6 +144,15 @@ int mp3gpu_decode(mp3gpu_ctx *ctx, const uint8_t *main_data, size_t main_data_le
 int mp3gpu_decode_device(mp3gpu_ctx *ctx, const uint8_t *d_main_data, size_t main_data_len,
                          const mp3gpu_unit *d_units, size_t n_granules, int16_t *d_pcm_out);
 
+/* Same, but returns as soon as the kernels are queued on the context's compute stream (no synchronise).
+ * Together with the two event calls below this lets a caller time K back-to-back passes on the device. */
+int mp3gpu_decode_device_async(mp3gpu_ctx *ctx, const uint8_t *d_main_data, size_t main_data_len,
+                               const mp3gpu_unit *d_units, size_t n_granules, int16_t *d_pcm_out);
+/* Record user event `which` (0..7) on the compute stream; elapsed time between two recorded events
+ * (synchronises on `to`). */
+int mp3gpu_event_record(mp3gpu_ctx *ctx, int which);
+int mp3gpu_event_elapsed_ms(mp3gpu_ctx *ctx, int from, int to, float *ms);
+
 /* Pinned host memory (page-locked) for main_data / units / pcm buffers. */
 void *mp3gpu_host_alloc(size_t bytes);
 void mp3gpu_host_free(void *p);
@@ -155,7 +164,7 @@ int mp3gpu_copy_to_device(mp3gpu_ctx *ctx, void *dst_device, const void *src_hos
 int mp3gpu_copy_to_host(mp3gpu_ctx *ctx, void *dst_host, const void *src_device, size_t bytes);
 int mp3gpu_synchronize(mp3gpu_ctx *ctx);
 
-int mp3gpu_last_timings(const mp3gpu_ctx *ctx, mp3gpu_timings *out);
+int mp3gpu_last_timings(mp3gpu_ctx *ctx, mp3gpu_timings *out);
 
 /* Debug taps (opts.keep_intermediates = 1): per-stage outputs of the LAST wave of the last call,
  * for parity tests against the oracle.  `first_granule`/`n_granules` index within that wave. */
