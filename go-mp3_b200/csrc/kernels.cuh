@@ -112,6 +112,10 @@ constexpr int kXrFloats = 32 * kXrStride;  // 608
 
 __device__ __forceinline__ int xr_pad(int i) { return i + i / 18; }
 
+// Value of a sum whose every term is the exact negation of the terms of `sum`, accumulated in the same order
+// from +0: -sum, except that a zero sum stays +0 (accumulators start at +0, and +0 + -0 = +0).
+__device__ __forceinline__ float mirror_neg(float sum) { return __fsub_rn(0.0f, sum); }
+
 // sum_{m=0..17} in[m] * cos36[m][P], m ascending from 0 (imdct.go:101-107); three outputs at a time for ILP
 template <int P0, int P1, int P2>
 __device__ __forceinline__ void dot36x3(const float (&in)[18], float &r0, float &r1, float &r2) {
@@ -160,7 +164,7 @@ __device__ __forceinline__ void imdct36_emit(const float (&in)[18], const Hybrid
 #pragma unroll
         for (int p = 0; p < 9; p++) {
             k.first(p, __fmul_rn(u[p], w[p]));
-            k.first(17 - p, __fmul_rn(-u[p], w[17 - p]));  // cos36[m][17-p] == -cos36[m][p] bitwise
+            k.first(17 - p, __fmul_rn(mirror_neg(u[p]), w[17 - p]));  // cos36[m][17-p] == -cos36[m][p] bitwise
         }
     }
     // the second half overwrites the overlap that first() has just consumed
@@ -191,7 +195,7 @@ __device__ __forceinline__ void imdct12_emit(const float (&in)[18], const Hybrid
         const float b0 = i == 0 ? dot12<0, 6>(in) : i == 1 ? dot12<1, 6>(in) : dot12<2, 6>(in);
         const float b1 = i == 0 ? dot12<0, 7>(in) : i == 1 ? dot12<1, 7>(in) : dot12<2, 7>(in);
         const float b2 = i == 0 ? dot12<0, 8>(in) : i == 1 ? dot12<1, 8>(in) : dot12<2, 8>(in);
-        s[0] = a0; s[1] = a1; s[2] = a2; s[3] = -a2; s[4] = -a1; s[5] = -a0;
+        s[0] = a0; s[1] = a1; s[2] = a2; s[3] = mirror_neg(a2); s[4] = mirror_neg(a1); s[5] = mirror_neg(a0);
         s[6] = b0; s[7] = b1; s[8] = b2; s[9] = b2; s[10] = b1; s[11] = b0;
 #pragma unroll
         for (int p = 0; p < 12; p++) raw[6 * i + p + 6] = mac(s[p], kWin[2][p], raw[6 * i + p + 6]);
@@ -215,7 +219,7 @@ __device__ __forceinline__ void hybrid_channel(const float (&in)[18], const Hybr
 }
 
 constexpr int kHybWarps = 4;
-constexpr int kHybSmemWords = 2 * kXrFloats + 2 * 18 * 32 + 16;  // per warp: staging, overlap, scalefactors
+constexpr int kHybSmemWords = 2 * kXrFloats + 2 * 18 * 32 + 16 + 2 * 64 * 2;  // per warp: staging, overlap, scalefactors, scale tables
 constexpr int kHybSmemBytes = kHybWarps * kHybSmemWords * 4;
 
 template <bool TAPS>
@@ -228,6 +232,7 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
     float(*s_x)[kXrFloats] = reinterpret_cast<float(*)[kXrFloats]>(s_base);                 // spectrum staging
     float(*s_ov)[18 * 32] = reinterpret_cast<float(*)[18 * 32]>(s_base + 2 * kXrFloats);   // IMDCT overlap (Frame.store)
     uint32_t(*s_pk)[8] = reinterpret_cast<uint32_t(*)[8]>(s_base + 2 * kXrFloats + 2 * 18 * 32);
+    double(*s_scale)[64] = reinterpret_cast<double(*)[64]>(s_base + 2 * kXrFloats + 2 * 18 * 32 + 16);  // 2^(k/4) per band
 
     for (;;) {
         int seg = 0;
@@ -256,21 +261,40 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
             __syncwarp();
 
             // ---------------- K2: requantise + reorder (frame.go:140-302) -------------------------------
+            // Per-band scale table first, then the lines two at a time (unit_logic.h, "scale-table form").
             const int cfg = u_lsf(w2a) * 3 + u_sfreq(w2a);
             if (lane < 16) s_pk[lane >> 3][lane & 7] = __ldg(B.sfpack + ((long long)g * 2 + (lane >> 3)) * 8 + (lane & 7));
-            GranuleChan c[2];
-            c[0] = make_chan(w0a, w1a, w2a, __ldg(B.meta + (long long)g * 2));
-            c[1] = make_chan(w0b, w1b, w2b, valid_b ? __ldg(B.meta + (long long)g * 2 + 1) : 0u);
+            GranuleChan c0 = make_chan(w0a, w1a, w2a, __ldg(B.meta + (long long)g * 2));
+            GranuleChan c1 = make_chan(w0b, w1b, w2b, valid_b ? __ldg(B.meta + (long long)g * 2 + 1) : 0u);
             __syncwarp();
 #pragma unroll 1
             for (int ch = 0; ch < 2; ch++) {
                 if (ch == 1 && !valid_b) break;
-                const int16_t *is = B.is16 + ((long long)g * 2 + ch) * 576;
+                const GranuleChan &c = ch ? c1 : c0;
+                s_scale[ch][lane] = scale_entry(T, c, s_pk[ch], lane);
+                s_scale[ch][lane + 32] = scale_entry(T, c, s_pk[ch], lane + 32);
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ch++) {
+                if (ch == 1 && !valid_b) break;
+                const GranuleChan &c = ch ? c1 : c0;
+                const uint32_t *is2 = reinterpret_cast<const uint32_t *>(B.is16 + ((long long)g * 2 + ch) * 576);
+                const int npair = c.cnt1 >> 1;  // count1 is even: big_values pairs + count1 quadruples
+                float *xs = s_x[ch];
 #pragma unroll 3
-                for (int i = lane; i < 576; i += 32) {
-                    int dst;
-                    float r = requant_line(T, cfg, c[ch], s_pk[ch], i, i < c[ch].cnt1 ? (int)__ldg(is + i) : 0, &dst);
-                    s_x[ch][xr_pad(dst)] = r;
+                for (int p = lane; p < 288; p += 32) {
+                    int d0, d1;
+                    const int e = pair_lookup(T, cfg, c, p, &d0, &d1);
+                    float x0 = 0.0f, x1 = 0.0f;  // lines at or above count1 stay +0 (maindata/huffman.go:130-134)
+                    if (p < npair) {
+                        const uint32_t w = __ldg(is2 + p);
+                        const double sc = s_scale[ch][e];
+                        x0 = requant_value(T, sc, (int)(int16_t)(w & 0xffffu));
+                        x1 = requant_value(T, sc, (int)(int16_t)(w >> 16));
+                    }
+                    xs[xr_pad(d0)] = x0;
+                    xs[xr_pad(d1)] = x1;
                 }
             }
             __syncwarp();
@@ -278,7 +302,7 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
             if (valid_b && u_mode(w2a) == 1) {
                 const int mode_ext = u_modeext(w2a);
                 if (mode_ext & 2) {
-                    const int max_pos = c[0].cnt1 > c[1].cnt1 ? c[0].cnt1 : c[1].cnt1;
+                    const int max_pos = c0.cnt1 > c1.cnt1 ? c0.cnt1 : c1.cnt1;
                     const float inv_sqrt2 = 0.70710678118654752440f;
                     for (int i = lane; i < max_pos; i += 32) {
                         const int p = xr_pad(i);
@@ -289,12 +313,23 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
                     __syncwarp();
                 }
                 if (mode_ext & 1) {
-                    for (int i = lane; i < 576; i += 32) {
-                        int is_pos = intensity_pos(T, cfg, c[0], s_pk[0], c[1].cnt1, i);
+                    // per-band intensity positions (channel 0's block type and scalefactors), then per line pair
+                    uint8_t *s_isp = reinterpret_cast<uint8_t *>(s_scale[1]);  // channel 1's scale table is no longer needed
+                    __syncwarp();
+                    s_isp[lane] = (uint8_t)intensity_entry(T, cfg, c0, s_pk[0], c1.cnt1, lane);
+                    s_isp[lane + 32] = (uint8_t)intensity_entry(T, cfg, c0, s_pk[0], c1.cnt1, lane + 32);
+                    __syncwarp();
+                    for (int p = lane; p < 288; p += 32) {
+                        int d0, d1;
+                        // the window is looked up at the PRE-reorder index although the data is reordered (frame.go:341-357)
+                        const int is_pos = s_isp[pair_lookup(T, cfg, c0, p, &d0, &d1)];
                         if (is_pos < 7) {
-                            const int p = xr_pad(i);
-                            s_x[0][p] = f_mul(s_x[0][p], T.is_ratio_l[is_pos]);
-                            s_x[1][p] = f_mul(s_x[1][p], T.is_ratio_r[is_pos]);
+                            const float rl = T.is_ratio_l[is_pos], rr = T.is_ratio_r[is_pos];
+                            const int q0 = xr_pad(2 * p), q1 = xr_pad(2 * p + 1);
+                            s_x[0][q0] = f_mul(s_x[0][q0], rl);
+                            s_x[1][q0] = f_mul(s_x[1][q0], rr);
+                            s_x[0][q1] = f_mul(s_x[0][q1], rl);
+                            s_x[1][q1] = f_mul(s_x[1][q1], rr);
                         }
                     }
                     __syncwarp();
@@ -304,7 +339,7 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
 #pragma unroll 1
             for (int ch = 0; ch < 2; ch++) {
                 if (ch == 1 && !valid_b) break;
-                const int nb = alias_butterflies(c[ch]);
+                const int nb = alias_butterflies(ch ? c1 : c0);
                 for (int b = lane; b < nb; b += 32) {
                     const int sb = (b >> 3) + 1, i = b & 7;
                     const int li = 18 * sb - 1 - i + (sb - 1), ui = 18 * sb + i + sb;  // padded positions
@@ -415,7 +450,7 @@ __device__ __forceinline__ float window_sum(const float (&A)[15], const float (&
 
 struct SynLane {  // where lane i finds V[i] and V[32+i] in a U row, and with which sign
     int ai, bi;
-    uint32_t sa, sb;  // sign-bit masks
+    float sa, sb;  // +1 or -1; applied as fma(u, s, +0) so that a mirrored zero stays +0 like the direct sum
 };
 
 // One slot of phase B at circular position P.  FAST: the caller has checked that this and the other 14 rows of the
@@ -431,15 +466,15 @@ __device__ __forceinline__ void synth_window_slot(const float *U0, const float *
     }
     uint32_t pl = 0, pr = 0;
     if (f & 1) {
-        const float a = __uint_as_float(__float_as_uint(U0[row * kURow + L.ai]) ^ L.sa);
-        const float b = __uint_as_float(__float_as_uint(U0[row * kURow + L.bi]) ^ L.sb);
+        const float a = __fmaf_rn(U0[row * kURow + L.ai], L.sa, 0.0f);
+        const float b = __fmaf_rn(U0[row * kURow + L.bi], L.sb, 0.0f);
         A0[P] = a;
         if (!WARMUP) pl = (uint32_t)pcm_from_float(window_sum<P>(A0, B0, dw)) & 0xffffu;
         B0[P] = b;
     }
     if (f & 2) {
-        const float a = __uint_as_float(__float_as_uint(U1[row * kURow + L.ai]) ^ L.sa);
-        const float b = __uint_as_float(__float_as_uint(U1[row * kURow + L.bi]) ^ L.sb);
+        const float a = __fmaf_rn(U1[row * kURow + L.ai], L.sa, 0.0f);
+        const float b = __fmaf_rn(U1[row * kURow + L.bi], L.sb, 0.0f);
         A1[P] = a;
         if (!WARMUP) pr = (uint32_t)pcm_from_float(window_sum<P>(A1, B1, dw)) & 0xffffu;
         B1[P] = b;
@@ -495,9 +530,9 @@ k_synth(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_gr
     const int lane = tid & 31, warp = tid >> 5;
     SynLane L;
     L.ai = lane <= 16 ? lane : 32 - lane;                      // V[i]    = i <= 16 ? U[i] : -U[32-i]
-    L.sa = lane <= 16 ? 0u : 0x80000000u;
+    L.sa = lane <= 16 ? 1.0f : -1.0f;
     L.bi = lane == 0 ? 0 : (lane <= 16 ? 16 + lane : 48 - lane);  // V[32+i] = i == 0 ? -U[0] : i <= 16 ? U[16+i] : U[48-i]
-    L.sb = lane == 0 ? 0x80000000u : 0u;
+    L.sb = lane == 0 ? -1.0f : 1.0f;
     float dw[16];
 #pragma unroll
     for (int d = 0; d < 16; d++) dw[d] = __ldg(B.synth_d + 32 * d + lane);

@@ -111,6 +111,9 @@ static int upload_tables(mp3gpu_ctx *ctx) {
     size_t o_lss = put(h.line_sfb_short, sizeof h.line_sfb_short);
     size_t o_lws = put(h.line_win_short, sizeof h.line_win_short);
     size_t o_rd = put(h.reorder_dst, sizeof h.reorder_dst);
+    size_t o_pl = put(h.pair_long, sizeof h.pair_long);
+    size_t o_ps = put(h.pair_short, sizeof h.pair_short);
+    size_t o_pd = put(h.pair_dst, sizeof h.pair_dst);
     size_t o_sl = put(h.sfb_long, sizeof h.sfb_long);
     size_t o_ss = put(h.sfb_short, sizeof h.sfb_short);
     size_t o_ns = put(h.nslen2, sizeof h.nslen2);
@@ -132,6 +135,9 @@ static int upload_tables(mp3gpu_ctx *ctx) {
     ctx->T.line_sfb_short = b + o_lss;
     ctx->T.line_win_short = b + o_lws;
     ctx->T.reorder_dst = (const uint16_t *)(b + o_rd);
+    ctx->T.pair_long = b + o_pl;
+    ctx->T.pair_short = b + o_ps;
+    ctx->T.pair_dst = (const uint16_t *)(b + o_pd);
     ctx->T.sfb_long = (const uint16_t *)(b + o_sl);
     ctx->T.sfb_short = (const uint16_t *)(b + o_ss);
     ctx->T.nslen2 = (const uint16_t *)(b + o_ns);

@@ -176,6 +176,18 @@ void build_host_tables(HostTables &t) {
                     }
             }
         }
+    // pair tables: lines 2p and 2p+1 always share their band (every band boundary is even)
+    for (int cfg = 0; cfg < kNumCfg; cfg++)
+        for (int p = 0; p < 288; p++) {
+            if (t.line_sfb_long[cfg][2 * p] != t.line_sfb_long[cfg][2 * p + 1] ||
+                t.line_sfb_short[cfg][2 * p] != t.line_sfb_short[cfg][2 * p + 1] ||
+                t.line_win_short[cfg][2 * p] != t.line_win_short[cfg][2 * p + 1] ||
+                t.reorder_dst[cfg][2 * p + 1] != t.reorder_dst[cfg][2 * p] + 3)
+                throw std::runtime_error("scalefactor band boundary is not even");
+            t.pair_long[cfg][p] = t.line_sfb_long[cfg][2 * p];
+            t.pair_short[cfg][p] = (uint8_t)(t.line_sfb_short[cfg][2 * p] * 3 + t.line_win_short[cfg][2 * p]);
+            t.pair_dst[cfg][p] = t.reorder_dst[cfg][2 * p];
+        }
     // maindata.go:54-81
     memset(t.nslen2, 0, sizeof t.nslen2);
     for (int i = 0; i < 4; i++)

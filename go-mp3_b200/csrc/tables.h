@@ -43,6 +43,9 @@ struct HostTables {
     uint8_t line_sfb_short[kNumCfg][576];  // for window-major index i within short sfbs
     uint8_t line_win_short[kNumCfg][576];
     uint16_t reorder_dst[kNumCfg][576];
+    uint8_t pair_long[kNumCfg][288];
+    uint8_t pair_short[kNumCfg][288];
+    uint16_t pair_dst[kNumCfg][288];
     uint16_t nslen2[512];
     uint8_t sfsize_mpeg2[3][6][4];
     std::vector<uint16_t> huff_lut;

@@ -31,6 +31,9 @@ struct DeviceTables {
     const uint8_t *line_sfb_short;  // [6][576]
     const uint8_t *line_win_short;  // [6][576]
     const uint16_t *reorder_dst;    // [6][576]
+    const uint8_t *pair_long;       // [6][288]  sfb of lines 2p, 2p+1 (all sfb boundaries are even)
+    const uint8_t *pair_short;      // [6][288]  sfb*3 + win of lines 2p, 2p+1 in the window-major short layout
+    const uint16_t *pair_dst;       // [6][288]  reorder destination of line 2p (line 2p+1 goes to +3)
     const uint16_t *sfb_long;       // [6][24]
     const uint16_t *sfb_short;      // [6][16]
     const uint16_t *nslen2;         // [512]
@@ -377,6 +380,64 @@ MP3_HD float requant_line(const DeviceTables &T, int cfg, const GranuleChan &c, 
     }
     double a = T.powtab34[v < 0 ? -v : v];
     return d_mul_to_f(T.pow2q[k4 + T.pow2_off], v < 0 ? -a : a);
+}
+
+
+// ---- K2, scale-table form ------------------------------------------------------------------------
+// The requantisation exponent is constant per scalefactor band (long) or per band x window (short), so K2
+// first tabulates 2^(k/4) per band (64 doubles: [0..21] long sfb, [24..62] short sfb*3+win) and then handles
+// the lines two at a time: every band boundary is even, so lines 2p and 2p+1 share their table entry.
+constexpr int kScaleShortBase = 24;
+
+// Table entry e of one channel (frame.go:146-148 long, :161-166 short); 0 where the entry is not used.
+MP3_HD double scale_entry(const DeviceTables &T, const GranuleChan &c, const uint32_t *pk, int e) {
+    const int mult = u_sfscale(c.w2) ? 4 : 2;  // 4 * sfMult
+    const int gg = u_ggain(c.w0) - 210;
+    int k4;
+    if (e < 22) {
+        if (c.is_short && !c.mixed) return 0.0;
+        k4 = gg - mult * (sf_nib(pk, e) + c.preflag * (int)T.pretab[e]);
+    } else if (e >= kScaleShortBase && e < kScaleShortBase + 39) {
+        if (!c.is_short) return 0.0;
+        const int code = e - kScaleShortBase, win = code % 3;
+        k4 = gg - 8 * u_sbg(c.w2, win) - mult * sf_nib(pk, 22 + code);
+    } else {
+        return 0.0;
+    }
+    return T.pow2q[k4 + T.pow2_off];
+}
+
+// Table index and reorder destinations of the pair of lines (2p, 2p+1) (frame.go:257-302).
+MP3_HD int pair_lookup(const DeviceTables &T, int cfg, const GranuleChan &c, int p, int *dst0, int *dst1) {
+    if (c.is_short && (!c.mixed || p >= 18)) {
+        *dst0 = T.pair_dst[cfg * 288 + p];
+        *dst1 = *dst0 + 3;
+        return kScaleShortBase + T.pair_short[cfg * 288 + p];
+    }
+    *dst0 = 2 * p;
+    *dst1 = 2 * p + 1;
+    return T.pair_long[cfg * 288 + p];
+}
+
+// One requantised line: sign(is) * |is|^(4/3) * scale, in double, rounded once (frame.go:146-155).
+MP3_HD float requant_value(const DeviceTables &T, double scale, int v) {
+    double a = T.powtab34[v < 0 ? -v : v];
+    return d_mul_to_f(scale, v < 0 ? -a : a);
+}
+
+// Intensity-stereo table entry e (same indexing as the scale table, channel 0's block type and scalefactors,
+// frame.go:312,340,385-419): is_pos if the band is intensity coded, else 7.
+MP3_HD int intensity_entry(const DeviceTables &T, int cfg, const GranuleChan &c0, const uint32_t *pk0, int cnt1_r, int e) {
+    if (e < 22) {
+        if (c0.is_short && !c0.mixed) return 7;
+        if (e < (c0.mixed ? 8 : 21) && (int)T.sfb_long[cfg * 24 + e] >= cnt1_r) return sf_nib(pk0, e);
+        return 7;
+    }
+    if (e >= kScaleShortBase && e < kScaleShortBase + 39 && c0.is_short) {
+        const int code = e - kScaleShortBase, sfb = code / 3;
+        if (sfb < 12 && (int)T.sfb_short[cfg * 16 + sfb] * 3 >= cnt1_r) return sf_nib(pk0, 22 + code);
+    }
+    return 7;
 }
 
 // Intensity-stereo position of line i, or 7 if the line is not intensity coded.

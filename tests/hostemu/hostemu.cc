@@ -27,6 +27,9 @@ void ensure() {
     g_T.line_sfb_short = &h.line_sfb_short[0][0];
     g_T.line_win_short = &h.line_win_short[0][0];
     g_T.reorder_dst = &h.reorder_dst[0][0];
+    g_T.pair_long = &h.pair_long[0][0];
+    g_T.pair_short = &h.pair_short[0][0];
+    g_T.pair_dst = &h.pair_dst[0][0];
     g_T.sfb_long = &h.sfb_long[0][0];
     g_T.sfb_short = &h.sfb_short[0][0];
     g_T.nslen2 = h.nslen2;
@@ -87,13 +90,22 @@ void emu_requant(const mp3gpu_unit *units, long long n_granules, const int16_t *
         c[0] = make_chan(ug[0].w0, ug[0].w1, ug[0].w2, meta[g * 2]);
         c[1] = make_chan(ug[1].w0, ug[1].w1, ug[1].w2, valid_b ? meta[g * 2 + 1] : 0u);
         float *x[2] = {x0, x1};
+        double scale[2][64];
         for (int ch = 0; ch < 2; ch++) {
             if (ch == 1 && !valid_b) break;
+            for (int e = 0; e < 64; e++) scale[ch][e] = scale_entry(g_T, c[ch], pk[ch], e);
             const int16_t *is = is16 + (g * 2 + ch) * 576;
-            for (int i = 0; i < 576; i++) {
-                int dst;
-                float r = requant_line(g_T, cfg, c[ch], pk[ch], i, i < c[ch].cnt1 ? (int)is[i] : 0, &dst);
-                x[ch][dst] = r;
+            const int npair = c[ch].cnt1 >> 1;
+            for (int p = 0; p < 288; p++) {
+                int d0, d1;
+                const int e = pair_lookup(g_T, cfg, c[ch], p, &d0, &d1);
+                float v0 = 0.0f, v1 = 0.0f;
+                if (p < npair) {
+                    v0 = requant_value(g_T, scale[ch][e], is[2 * p]);
+                    v1 = requant_value(g_T, scale[ch][e], is[2 * p + 1]);
+                }
+                x[ch][d0] = v0;
+                x[ch][d1] = v1;
             }
         }
         if (valid_b && u_mode(c[0].w2) == 1) {
@@ -108,11 +120,16 @@ void emu_requant(const mp3gpu_unit *units, long long n_granules, const int16_t *
                 }
             }
             if (mode_ext & 1) {
-                for (int i = 0; i < 576; i++) {
-                    int is_pos = intensity_pos(g_T, cfg, c[0], pk[0], c[1].cnt1, i);
+                int isp[64];
+                for (int e = 0; e < 64; e++) isp[e] = intensity_entry(g_T, cfg, c[0], pk[0], c[1].cnt1, e);
+                for (int p = 0; p < 288; p++) {
+                    int d0, d1;
+                    const int is_pos = isp[pair_lookup(g_T, cfg, c[0], p, &d0, &d1)];
                     if (is_pos < 7) {
-                        x0[i] = f_mul(x0[i], g_T.is_ratio_l[is_pos]);
-                        x1[i] = f_mul(x1[i], g_T.is_ratio_r[is_pos]);
+                        for (int i = 2 * p; i < 2 * p + 2; i++) {
+                            x0[i] = f_mul(x0[i], g_T.is_ratio_l[is_pos]);
+                            x1[i] = f_mul(x1[i], g_T.is_ratio_r[is_pos]);
+                        }
                     }
                 }
             }
