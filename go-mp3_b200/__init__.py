@@ -211,6 +211,14 @@ def gpu_lib(exact: bool = False) -> C.CDLL:
     return L
 
 
+def shard_streams(n_streams: int, world: int, rank: int) -> Tuple[int, int]:
+    """Half-open range [first, last) of the streams rank `rank` of `world` decodes.  Streams are independent
+    (SURVEY.md 8e), so multi-GPU decoding shards the stream set; there is no data-path collective."""
+    base, extra = divmod(n_streams, world)
+    first = rank * base + min(rank, extra)
+    return first, first + base + (1 if rank < extra else 0)
+
+
 def error_string(code: int) -> str:
     return host_lib().mp3_error_string(code).decode()
 

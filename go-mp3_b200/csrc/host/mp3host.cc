@@ -550,7 +550,14 @@ extern "C" long mp3_decoder_read(mp3_decoder *d, uint8_t *out, size_t n, int *er
             return 0;
         }
     }
+    // d.buf of the reference never holds more than the rest of ONE frame (decode.go:65,76-77), so a Read returns
+    // at most that; the decode-ahead buffer is cut at the same frame boundary.
     size_t live = d->buf.size() - d->buf_off;
+    for (const auto &m : d->marks)
+        if (m.pcm_end > d->buf_off) {
+            live = m.pcm_end - d->buf_off;
+            break;
+        }
     size_t c = std::min(n, live);
     memcpy(out, d->buf.data() + d->buf_off, c);
     d->buf_off += c;
