@@ -19,6 +19,7 @@
 #define MP3_HD __host__ __device__ __forceinline__
 #else
 #define MP3_HD inline
+struct alignas(16) uint4 { uint32_t x, y, z, w; };  // host-emulation build only (tests/hostemu)
 #endif
 
 namespace mp3gpu {
@@ -92,76 +93,77 @@ MP3_HD uint32_t load_be32(const uint32_t *p) { return __builtin_bswap32(*p); }
 #endif
 
 // ---- bit cursor with bits.go semantics ----------------------------------------------------------
+// Window = two consecutive big-endian 32-bit words [w0:w1] of main_data and a bit offset into w0; peek32() is one
+// funnel shift.  Bits at/after the frame's logical buffer end read as 0 (bits.go:46-49,65-68).
+#if defined(__CUDA_ARCH__)
+MP3_HD uint32_t funnel_l(uint32_t hi, uint32_t lo, int s) { return __funnelshift_l(lo, hi, s); }  // (hi:lo << s) >> 32, s in 0..31
+#else
+MP3_HD uint32_t funnel_l(uint32_t hi, uint32_t lo, int s) { return s ? (hi << s) | (lo >> (32 - s)) : hi; }
+#endif
+
 struct BitCursor {
-    const uint32_t *words;  // main_data viewed as aligned 32-bit words
-    uint64_t buf;           // MSB-first window; bits past `avail` (and past the buffer end) are 0
-    int avail;              // valid bits in buf
-    long long next_bit;     // absolute bit index of the next word to load
-    long long end_abs;      // absolute bit index one past the frame's logical buffer
+    const uint32_t *wp;     // next 32-bit word of main_data to load
+    uint32_t w0, w1;        // current window
+    int off;                // bit offset of the cursor inside w0 (0..31)
+    int rem;                // bits from the MSB of *wp to the end of the frame's logical buffer (<= 0: past the end)
     int pos;                // logical position relative to bit_start (BitPos() rebased to part2Start)
     int lim;                // max(buf_end_rel, 0): pos never advances past it (bits.go:46-49)
 
     MP3_HD void init(const uint8_t *main_data, uint64_t bit_start, int buf_end_rel) {
-        words = reinterpret_cast<const uint32_t *>(main_data);
-        end_abs = (long long)bit_start + buf_end_rel;
+        wp = reinterpret_cast<const uint32_t *>(main_data) + (bit_start >> 5);
+        off = (int)(bit_start & 31);
+        rem = off + buf_end_rel;
         lim = buf_end_rel > 0 ? buf_end_rel : 0;
         pos = 0;
-        next_bit = (long long)(bit_start & ~31ull);
-        int o = (int)(bit_start & 31);
-        uint32_t w = load_word();
-        buf = ((uint64_t)w << 32) << o;
-        avail = 32 - o;
+        w0 = load_word();
+        w1 = load_word();
     }
-    // Next aligned word in big-endian bit order, bits at/after end_abs forced to zero.
+    // Next aligned word in big-endian bit order, bits at/after the buffer end forced to zero.
     MP3_HD uint32_t load_word() {
-        long long rem = end_abs - next_bit;
         uint32_t w = 0;
         if (rem > 0) {
-            w = load_be32(words + (next_bit >> 5));
-            if (rem < 32) w &= ~(0xffffffffu >> (int)rem);
+            w = load_be32(wp);
+            if (rem < 32) w &= ~(0xffffffffu >> rem);
         }
-        next_bit += 32;
+        wp++;
+        rem -= 32;
         return w;
     }
-    MP3_HD void refill() {
-        if (avail <= 32) {
-            uint32_t w = load_word();
-            buf |= (uint64_t)w << (32 - avail);
-            avail += 32;
-        }
-    }
-    MP3_HD uint32_t peek(int n) const { return (uint32_t)(buf >> (64 - n)); }
-    // Bit()-style consumption (tree bits, sign bits): the cursor clamps at the buffer end.
+    MP3_HD uint32_t peek32() const { return funnel_l(w0, w1, off); }  // next 32 bits, MSB first
+    // Bit()-style consumption of n <= 32 bits (tree bits, sign bits): the logical cursor clamps at the buffer end.
     MP3_HD void skip(int n) {
-        buf <<= n;
-        avail -= n;
+        off += n;
         pos = imin(pos + n, lim);
+        if (off >= 32) {
+            off -= 32;
+            w0 = w1;
+            w1 = load_word();
+        }
     }
     // Bits(n), bits.go:58-77: returns 0 WITHOUT advancing when the read would cross the end.
     MP3_HD int bits(int n) {
         if (n == 0) return 0;
         if (pos + n > lim) return 0;
-        refill();
-        int v = (int)peek(n);
+        int v = (int)(peek32() >> (32 - n));
         skip(n);
         return v;
     }
     MP3_HD int bit() {
-        refill();
-        int v = (int)(buf >> 63);
+        int v = (int)(peek32() >> 31);
         skip(1);
         return v;
     }
 };
 
-MP3_HD uint32_t huff_lookup(const uint16_t *lut, uint32_t desc, const BitCursor &bc) {
+// Leaf entry of the code word at the head of w (MSB first); *len receives the tree bits.
+MP3_HD uint32_t huff_lookup(const uint16_t *lut, uint32_t desc, uint32_t w) {
     uint32_t base = desc & 0xffff;
     int rb = (int)((desc >> 16) & 0xf);
-    uint32_t e = lut[base + bc.peek(rb)];
+    uint32_t e = lut[base + (w >> (32 - rb))];
     int used = rb;
     while (e & 0x8000u) {  // rare: code longer than the root index
         int sb = (int)((e >> 12) & 7) + 1;
-        uint32_t idx = (e & 0xfff) + (uint32_t)((bc.buf << used) >> (64 - sb));
+        uint32_t idx = (e & 0xfff) + ((w << used) >> (32 - sb));
         e = lut[base + idx];
         used += sb;
     }
@@ -170,48 +172,66 @@ MP3_HD uint32_t huff_lookup(const uint16_t *lut, uint32_t desc, const BitCursor 
 
 // One big_values pair (huffman.go:404-416).  Returns x | y<<16 (int16 halves).
 MP3_HD uint32_t huff_pair(const uint16_t *lut, uint32_t desc, BitCursor &bc) {
-    bc.refill();
-    uint32_t e = huff_lookup(lut, desc, bc);
+    const uint32_t w = bc.peek32();
+    uint32_t e = huff_lookup(lut, desc, w);
     int len = (int)((e >> 8) & 0x1f);
     int x = (int)((e >> 4) & 0xf), y = (int)(e & 0xf);
     int linbits = (int)((desc >> 20) & 0xf);
-    bc.skip(len);
     if (linbits != 0 && (x == 15 || y == 15)) {
+        bc.skip(len);
         if (x == 15) x += bc.bits(linbits);
         if (x != 0 && bc.bit()) x = -x;
         if (y == 15) y += bc.bits(linbits);
         if (y != 0 && bc.bit()) y = -y;
     } else {
         int nx = x != 0, ny = y != 0;
-        uint32_t two = bc.peek(2);  // >= 13 valid bits remain after the tree bits
+        uint32_t two = (w << len) >> 30;  // len <= 19: the two bits after the tree bits are inside w
         int sx = nx ? (int)(two >> 1) : 0;
         int sy = ny ? (int)((nx ? two : (two >> 1)) & 1) : 0;
-        bc.skip(nx + ny);
+        bc.skip(len + nx + ny);
         x = sx ? -x : x;
         y = sy ? -y : y;
     }
     return ((uint32_t)x & 0xffffu) | ((uint32_t)y << 16);
 }
 
-// One count1 quadruple (huffman.go:387-403): v, w, x, y each in {-1, 0, 1}.
-MP3_HD void huff_quad(const uint16_t *lut, uint32_t desc, BitCursor &bc, int &v, int &w, int &x, int &y) {
-    bc.refill();
-    uint32_t e = huff_lookup(lut, desc, bc);
-    int len = (int)((e >> 8) & 0x1f);
+// One count1 quadruple (huffman.go:387-403): v, w, x, y each in {-1, 0, 1}; returns (v | w<<16), (x | y<<16).
+MP3_HD void huff_quad(const uint16_t *lut, uint32_t desc, BitCursor &bc, uint32_t &vw, uint32_t &xy) {
+    const uint32_t wd = bc.peek32();
+    uint32_t e = huff_lookup(lut, desc, wd);
+    int len = (int)((e >> 8) & 0x1f);  // <= 6 tree bits, then up to 4 sign bits
     int q = (int)(e & 0xf);
-    bc.skip(len);  // <= 6 tree bits + 4 sign bits < 33 buffered bits: no refill needed below
-    v = (q >> 3) & 1;
-    w = (q >> 2) & 1;
-    x = (q >> 1) & 1;
-    y = q & 1;
-    uint32_t four = bc.peek(4);
+    int v = (q >> 3) & 1, w = (q >> 2) & 1, x = (q >> 1) & 1, y = q & 1;
+    uint32_t four = (wd << len) >> 28;
     int used = 0;
     if (v) { if ((four >> (3 - used)) & 1) v = -1; used++; }
     if (w) { if ((four >> (3 - used)) & 1) w = -1; used++; }
     if (x) { if ((four >> (3 - used)) & 1) x = -1; used++; }
     if (y) { if ((four >> (3 - used)) & 1) y = -1; used++; }
-    bc.skip(used);
+    bc.skip(len + used);
+    vw = ((uint32_t)v & 0xffffu) | ((uint32_t)w << 16);
+    xy = ((uint32_t)x & 0xffffu) | ((uint32_t)y << 16);
 }
+
+// Collects decoded line pairs and writes them 16 bytes at a time: units sit 1,152 bytes apart, so every lane of a
+// store instruction hits its own sector and the instruction count is what costs.
+struct PairSink {
+    uint4 *dst;
+    uint32_t a0, a1, a2, a3;
+    int n;
+    MP3_HD void init(uint32_t *out) { dst = reinterpret_cast<uint4 *>(out); a0 = a1 = a2 = a3 = 0; n = 0; }
+    MP3_HD void put(uint32_t w) {
+        a0 = a1; a1 = a2; a2 = a3; a3 = w;
+        n++;
+        if ((n & 3) == 0) {
+            uint4 v; v.x = a0; v.y = a1; v.z = a2; v.w = a3;
+            dst[(n >> 2) - 1] = v;
+        }
+    }
+    MP3_HD void flush() {  // pad with zero pairs up to the next multiple of four (they lie above count1)
+        while (n & 3) put(0);
+    }
+};
 
 MP3_HD void sf_put(uint32_t *pk, int n, int v) { pk[n >> 3] |= (uint32_t)v << (4 * (n & 7)); }
 MP3_HD int sf_nib(const uint32_t *pk, int n) { return (int)((pk[n >> 3] >> (4 * (n & 7))) & 0xf); }
@@ -224,14 +244,14 @@ MP3_HD void sf_mpeg1_read_all(const DeviceTables &T, BitCursor &bc, uint32_t w0,
     if (u_winsw(w0) == 1 && u_btype(w0) == 2) {
         int sfb0 = 0;
         if (u_mixed(w2)) {
+#pragma unroll 1
             for (int sfb = 0; sfb < 8; sfb++) sf_put(pk, sfb, bc.bits(slen1));
             sfb0 = 3;
         }
-        for (int sfb = sfb0; sfb < 12; sfb++) {
-            int nb = sfb < 6 ? slen1 : slen2;
-            for (int win = 0; win < 3; win++) sf_put(pk, 22 + sfb * 3 + win, bc.bits(nb));
-        }
+#pragma unroll 1
+        for (int n = sfb0 * 3; n < 36; n++) sf_put(pk, 22 + n, bc.bits(n < 18 ? slen1 : slen2));
     } else {
+#pragma unroll 1
         for (int sfb = 0; sfb < 21; sfb++) sf_put(pk, sfb, bc.bits(sfb < 11 ? slen1 : slen2));
     }
 }
@@ -262,10 +282,12 @@ MP3_HD uint32_t huffman_unit(const DeviceTables &T, const uint16_t *lut, const u
         }
         int d = (slen >> 12) & 7;
         int idx = 0;
+#pragma unroll 1
         for (int i = 0; i < 4; i++) {
             int num = slen & 7;
             slen >>= 3;
             int cnt = T.sfsize_mpeg2[(n * 6 + d) * 4 + i];
+#pragma unroll 1
             for (int k = 0; k < cnt; k++) {
                 int v = num > 0 ? bc.bits(num) : 0;
                 // long blocks fill scalefac_l[idx]; short fill scalefac_s[idx/3][idx%3] (maindata.go:169-179)
@@ -289,6 +311,7 @@ MP3_HD uint32_t huffman_unit(const DeviceTables &T, const uint16_t *lut, const u
         int sfc = u_sfcomp(w1) & 15;
         int slen1 = T.slen_mpeg1[sfc * 2], slen2 = T.slen_mpeg1[sfc * 2 + 1];
         int scfsi = u_scfsi(w2);
+#pragma unroll 1
         for (int sfb = 0; sfb < 21; sfb++) {
             int band = sfb < 6 ? 0 : (sfb < 11 ? 1 : (sfb < 16 ? 2 : 3));
             int v;
@@ -317,28 +340,27 @@ MP3_HD uint32_t huffman_unit(const DeviceTables &T, const uint16_t *lut, const u
     }
     int nbig = u_bigval(w0);
     if (nbig > 288) nbig = 288;  // the host rejects such frames (huffman.go:68-70); never reached
-    int k = 0;
+    PairSink sink;
+    sink.init(is_out);
     {
-        uint32_t d0 = huff_desc[u_tsel(w1, 0)];
-        int e0 = imin(nbig, r1h);
-        for (; k < e0; k++) is_out[k] = huff_pair(lut, d0, bc);
-        uint32_t d1 = huff_desc[u_tsel(w1, 1)];
-        int e1 = imin(nbig, r2h);
-        for (; k < e1; k++) is_out[k] = huff_pair(lut, d1, bc);
-        uint32_t d2 = huff_desc[u_tsel(w1, 2)];
-        for (; k < nbig; k++) is_out[k] = huff_pair(lut, d2, bc);
+        const uint32_t d0 = huff_desc[u_tsel(w1, 0)], d1 = huff_desc[u_tsel(w1, 1)], d2 = huff_desc[u_tsel(w1, 2)];
+        for (int k = 0; k < nbig; k++) {
+            const uint32_t d = k < r1h ? d0 : (k < r2h ? d1 : d2);
+            sink.put(huff_pair(lut, d, bc));
+        }
     }
     int is_pos = nbig * 2;
     {
         uint32_t dq = huff_desc[32 + u_c1tsel(w2)];
         while (is_pos <= 572 && bc.pos <= bit_pos_end) {
-            int v, w, x, y;
-            huff_quad(lut, dq, bc, v, w, x, y);
-            is_out[is_pos >> 1] = ((uint32_t)v & 0xffffu) | ((uint32_t)w << 16);
-            is_out[(is_pos >> 1) + 1] = ((uint32_t)x & 0xffffu) | ((uint32_t)y << 16);
+            uint32_t vw, xy;
+            huff_quad(lut, dq, bc, vw, xy);
+            sink.put(vw);
+            sink.put(xy);
             is_pos += 4;
         }
     }
+    sink.flush();
     if (bc.pos > bit_pos_end + 1) is_pos -= 4;  // overshoot: drop the last quadruple (huffman.go:119-122)
     if (is_pos < 0) is_pos = 0;
     return (uint32_t)is_pos | ((uint32_t)preflag << 10);

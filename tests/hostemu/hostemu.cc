@@ -59,7 +59,7 @@ void emu_huffman(const uint8_t *main_data, const mp3gpu_unit *units, long long n
         meta[u] = 0;
         if (!u_valid(units[u].w2)) continue;
         uint32_t pk[8];
-        uint32_t out[288 + 2];
+        alignas(16) uint32_t out[288 + 4];
         memset(out, 0, sizeof out);
         uint32_t m = huffman_unit(g_T, g_T.huff_lut, g_T.huff_desc, main_data, units, u, pk, out);
         meta[u] = m;
@@ -177,9 +177,10 @@ int emu_huff_one(int table, const uint8_t *buf, int len_bytes, int *out4) {
         out4[1] = (int16_t)(r >> 16);
         out4[2] = out4[3] = 0;
     } else {
-        int v, w, x, y;
-        huff_quad(g_T.huff_lut, g_T.huff_desc[table], bc, v, w, x, y);
-        out4[0] = x; out4[1] = y; out4[2] = v; out4[3] = w;
+        uint32_t vw, xy;
+        huff_quad(g_T.huff_lut, g_T.huff_desc[table], bc, vw, xy);
+        out4[0] = (int16_t)(xy & 0xffff); out4[1] = (int16_t)(xy >> 16);
+        out4[2] = (int16_t)(vw & 0xffff); out4[3] = (int16_t)(vw >> 16);
     }
     return bc.pos;
 }
