@@ -222,17 +222,52 @@ constexpr int kHybWarps = 4;
 constexpr int kHybSmemWords = 2 * kXrFloats + 2 * 18 * 32 + 16 + 2 * 64 * 2;  // per warp: staging, overlap, scalefactors, scale tables
 constexpr int kHybSmemBytes = kHybWarps * kHybSmemWords * 4;
 
+// frame.go:422-425 (6-digit literals); checked against the host tables at mp3gpu_create
+__device__ constexpr float kCs[8] = {0.857493f, 0.881742f, 0.949629f, 0.983315f, 0.995518f, 0.999161f, 0.999899f, 0.999993f};
+__device__ constexpr float kCa[8] = {-0.514496f, -0.471732f, -0.313377f, -0.181913f, -0.094574f, -0.040966f, -0.014199f, -0.003700f};
+
+// What k_hybrid loads one granule ahead: descriptors, K1's count1/preflag words and — for the long-block fast path,
+// where lane = subband — the lane's own 18 lines (9 int16 pairs) of both channels.
+struct GranulePre {
+    uint32_t w0a, w1a, w2a, w0b, w1b, w2b, meta0, meta1;
+    uint32_t isw[2][9];
+};
+__device__ __forceinline__ void prefetch_granule(GranulePre &P, const mp3gpu_unit *__restrict__ units, long long first_granule, int g,
+                                                 const WaveBufs &B, int lane) {
+    const long long G = first_granule + g;
+    if (G < 0) {  // in front of the submission: nothing there
+        P.w2a = 0;
+        return;
+    }
+    const mp3gpu_unit *ug = units + G * 2;
+    P.w0a = __ldg(&ug[0].w0); P.w1a = __ldg(&ug[0].w1); P.w2a = __ldg(&ug[0].w2);
+    P.w0b = __ldg(&ug[1].w0); P.w1b = __ldg(&ug[1].w1); P.w2b = __ldg(&ug[1].w2);
+    P.meta0 = __ldg(B.meta + (long long)g * 2);
+    P.meta1 = __ldg(B.meta + (long long)g * 2 + 1);
+    const uint32_t *is2 = reinterpret_cast<const uint32_t *>(B.is16 + (long long)g * 2 * 576) + lane * 9;
+#pragma unroll
+    for (int q = 0; q < 9; q++) {
+        P.isw[0][q] = __ldg(is2 + q);
+        P.isw[1][q] = __ldg(is2 + 288 + q);  // channel 1's slot exists even when the channel does not
+    }
+}
+
 template <bool TAPS>
-__global__ void __launch_bounds__(kHybWarps * 32)
+__global__ void __launch_bounds__(kHybWarps * 32, 4)
 k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_granules, int seg_len, int n_segs,
          DeviceTables T, WaveBufs B) {
     extern __shared__ __align__(16) float s_dyn[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *const s_base = s_dyn + warp * kHybSmemWords;
-    float(*s_x)[kXrFloats] = reinterpret_cast<float(*)[kXrFloats]>(s_base);                 // spectrum staging
+    float(*s_x)[kXrFloats] = reinterpret_cast<float(*)[kXrFloats]>(s_base);                 // spectrum staging (short-block path)
     float(*s_ov)[18 * 32] = reinterpret_cast<float(*)[18 * 32]>(s_base + 2 * kXrFloats);   // IMDCT overlap (Frame.store)
     uint32_t(*s_pk)[8] = reinterpret_cast<uint32_t(*)[8]>(s_base + 2 * kXrFloats + 2 * 18 * 32);
     double(*s_scale)[64] = reinterpret_cast<double(*)[64]>(s_base + 2 * kXrFloats + 2 * 18 * 32 + 16);  // 2^(k/4) per band
+
+    int sfb_cfg = -1;      // sampling-rate configuration the lane's band codes below belong to
+    uint32_t sfb_q[9];     // long-block scalefactor band of the lane's pairs 9*lane .. 9*lane+8 (fast path)
+#pragma unroll
+    for (int q = 0; q < 9; q++) sfb_q[q] = 0;
 
     for (;;) {
         int seg = 0;
@@ -245,13 +280,13 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
 #pragma unroll
         for (int i = 0; i < 18; i++) { s_ov[0][i * 32 + lane] = 0.f; s_ov[1][i * 32 + lane] = 0.f; }
 
+        GranulePre P;
+        prefetch_granule(P, units, first_granule, g0 - 1, B, lane);
         for (int g = g0 - 1; g < g1; g++) {
-            const long long G = first_granule + g;
-            if (G < 0) continue;
-            const mp3gpu_unit *ug = units + G * 2;
-            const uint32_t w0a = __ldg(&ug[0].w0), w1a = __ldg(&ug[0].w1), w2a = __ldg(&ug[0].w2);
-            const uint32_t w0b = __ldg(&ug[1].w0), w1b = __ldg(&ug[1].w1), w2b = __ldg(&ug[1].w2);
-            if (!u_valid(w2a)) continue;  // a granule always has channel 0
+            const GranulePre C = P;                                                      // this granule
+            if (g + 1 < g1) prefetch_granule(P, units, first_granule, g + 1, B, lane);   // next one, in flight during this one
+            const uint32_t w0a = C.w0a, w1a = C.w1a, w2a = C.w2a, w0b = C.w0b, w1b = C.w1b, w2b = C.w2b;
+            if (first_granule + g < 0 || !u_valid(w2a)) continue;  // a granule always has channel 0
             const bool valid_b = u_valid(w2b);
             const bool need_first = g >= g0;  // the halo granule only contributes its overlap
             if (u_zero(w2a)) {  // start of a stream / of a Seek: Frame.store is zero (frame.go:48)
@@ -260,103 +295,189 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
             }
             __syncwarp();
 
-            // ---------------- K2: requantise + reorder (frame.go:140-302) -------------------------------
-            // Per-band scale table first, then the lines two at a time (unit_logic.h, "scale-table form").
             const int cfg = u_lsf(w2a) * 3 + u_sfreq(w2a);
             if (lane < 16) s_pk[lane >> 3][lane & 7] = __ldg(B.sfpack + ((long long)g * 2 + (lane >> 3)) * 8 + (lane & 7));
-            GranuleChan c0 = make_chan(w0a, w1a, w2a, __ldg(B.meta + (long long)g * 2));
-            GranuleChan c1 = make_chan(w0b, w1b, w2b, valid_b ? __ldg(B.meta + (long long)g * 2 + 1) : 0u);
+            const GranuleChan c0 = make_chan(w0a, w1a, w2a, C.meta0);
+            const GranuleChan c1 = make_chan(w0b, w1b, w2b, valid_b ? C.meta1 : 0u);
             __syncwarp();
-#pragma unroll 1
-            for (int ch = 0; ch < 2; ch++) {
-                if (ch == 1 && !valid_b) break;
-                const GranuleChan &c = ch ? c1 : c0;
-                s_scale[ch][lane] = scale_entry(T, c, s_pk[ch], lane);
-                s_scale[ch][lane + 32] = scale_entry(T, c, s_pk[ch], lane + 32);
-            }
-            __syncwarp();
-#pragma unroll 1
-            for (int ch = 0; ch < 2; ch++) {
-                if (ch == 1 && !valid_b) break;
-                const GranuleChan &c = ch ? c1 : c0;
-                const uint32_t *is2 = reinterpret_cast<const uint32_t *>(B.is16 + ((long long)g * 2 + ch) * 576);
-                const int npair = c.cnt1 >> 1;  // count1 is even: big_values pairs + count1 quadruples
-                float *xs = s_x[ch];
-#pragma unroll 3
-                for (int p = lane; p < 288; p += 32) {
-                    int d0, d1;
-                    const int e = pair_lookup(T, cfg, c, p, &d0, &d1);
-                    float x0 = 0.0f, x1 = 0.0f;  // lines at or above count1 stay +0 (maindata/huffman.go:130-134)
-                    if (p < npair) {
-                        const uint32_t w = __ldg(is2 + p);
-                        const double sc = s_scale[ch][e];
-                        x0 = requant_value(T, sc, (int)(int16_t)(w & 0xffffu));
-                        x1 = requant_value(T, sc, (int)(int16_t)(w >> 16));
-                    }
-                    xs[xr_pad(d0)] = x0;
-                    xs[xr_pad(d1)] = x1;
+            const bool fast = !c0.is_short && !(valid_b && c1.is_short);
+            float x0[18], x1[18];  // fast path: the lane's subband, both channels
+            if (fast) {
+                // ---------------- K2, long blocks: lane = subband, everything in registers ---------------
+                if (cfg != sfb_cfg) {
+                    sfb_cfg = cfg;
+#pragma unroll
+                    for (int q = 0; q < 9; q++) sfb_q[q] = T.pair_long[cfg * 288 + lane * 9 + q];
                 }
-            }
-            __syncwarp();
-            // ---------------- stereo (frame.go:362-420) -------------------------------------------------
-            if (valid_b && u_mode(w2a) == 1) {
-                const int mode_ext = u_modeext(w2a);
-                if (mode_ext & 2) {
-                    const int max_pos = c0.cnt1 > c1.cnt1 ? c0.cnt1 : c1.cnt1;
-                    const float inv_sqrt2 = 0.70710678118654752440f;
-                    for (int i = lane; i < max_pos; i += 32) {
-                        const int p = xr_pad(i);
-                        float a = s_x[0][p], b = s_x[1][p];
-                        s_x[0][p] = f_mul(f_add(a, b), inv_sqrt2);
-                        s_x[1][p] = f_mul(f_sub(a, b), inv_sqrt2);
-                    }
-                    __syncwarp();
+                if (lane < 22) {
+                    s_scale[0][lane] = scale_entry(T, c0, s_pk[0], lane);
+                    if (valid_b) s_scale[1][lane] = scale_entry(T, c1, s_pk[1], lane);
                 }
-                if (mode_ext & 1) {
-                    // per-band intensity positions (channel 0's block type and scalefactors), then per line pair
-                    uint8_t *s_isp = reinterpret_cast<uint8_t *>(s_scale[1]);  // channel 1's scale table is no longer needed
-                    __syncwarp();
-                    s_isp[lane] = (uint8_t)intensity_entry(T, cfg, c0, s_pk[0], c1.cnt1, lane);
-                    s_isp[lane + 32] = (uint8_t)intensity_entry(T, cfg, c0, s_pk[0], c1.cnt1, lane + 32);
-                    __syncwarp();
-                    for (int p = lane; p < 288; p += 32) {
-                        int d0, d1;
-                        // the window is looked up at the PRE-reorder index although the data is reordered (frame.go:341-357)
-                        const int is_pos = s_isp[pair_lookup(T, cfg, c0, p, &d0, &d1)];
-                        if (is_pos < 7) {
-                            const float rl = T.is_ratio_l[is_pos], rr = T.is_ratio_r[is_pos];
-                            const int q0 = xr_pad(2 * p), q1 = xr_pad(2 * p + 1);
-                            s_x[0][q0] = f_mul(s_x[0][q0], rl);
-                            s_x[1][q0] = f_mul(s_x[1][q0], rr);
-                            s_x[0][q1] = f_mul(s_x[0][q1], rl);
-                            s_x[1][q1] = f_mul(s_x[1][q1], rr);
+                __syncwarp();
+                {   // requantise (frame.go:140-158); lines at or above count1 stay +0
+                    const int np0 = c0.cnt1 >> 1, np1 = c1.cnt1 >> 1;
+#pragma unroll
+                    for (int q = 0; q < 9; q++) {
+                        const int p = lane * 9 + q;
+                        x0[2 * q] = x0[2 * q + 1] = x1[2 * q] = x1[2 * q + 1] = 0.0f;
+                        if (p < np0) {
+                            const double sc = s_scale[0][sfb_q[q]];
+                            x0[2 * q] = requant_value(T, sc, (int)(int16_t)(C.isw[0][q] & 0xffffu));
+                            x0[2 * q + 1] = requant_value(T, sc, (int)(int16_t)(C.isw[0][q] >> 16));
+                        }
+                        if (p < np1) {  // np1 == 0 without channel 1
+                            const double sc = s_scale[1][sfb_q[q]];
+                            x1[2 * q] = requant_value(T, sc, (int)(int16_t)(C.isw[1][q] & 0xffffu));
+                            x1[2 * q + 1] = requant_value(T, sc, (int)(int16_t)(C.isw[1][q] >> 16));
                         }
                     }
-                    __syncwarp();
                 }
-            }
-            // ---------------- alias reduction (frame.go:427-452) ----------------------------------------
-#pragma unroll 1
-            for (int ch = 0; ch < 2; ch++) {
-                if (ch == 1 && !valid_b) break;
-                const int nb = alias_butterflies(ch ? c1 : c0);
-                for (int b = lane; b < nb; b += 32) {
-                    const int sb = (b >> 3) + 1, i = b & 7;
-                    const int li = 18 * sb - 1 - i + (sb - 1), ui = 18 * sb + i + sb;  // padded positions
-                    const float xl = s_x[ch][li], xu = s_x[ch][ui];
-                    s_x[ch][li] = f_sub(f_mul(xl, T.cs[i]), f_mul(xu, T.ca[i]));
-                    s_x[ch][ui] = f_add(f_mul(xu, T.cs[i]), f_mul(xl, T.ca[i]));
+                if (valid_b && u_mode(w2a) == 1) {  // stereo (frame.go:362-420)
+                    const int mode_ext = u_modeext(w2a);
+                    if (mode_ext & 2) {
+                        const int max_pos = c0.cnt1 > c1.cnt1 ? c0.cnt1 : c1.cnt1;
+                        const float inv_sqrt2 = 0.70710678118654752440f;
+#pragma unroll
+                        for (int i = 0; i < 18; i++) {
+                            if (lane * 18 + i < max_pos) {
+                                const float a = x0[i], b = x1[i];
+                                x0[i] = f_mul(f_add(a, b), inv_sqrt2);
+                                x1[i] = f_mul(f_sub(a, b), inv_sqrt2);
+                            }
+                        }
+                    }
+                    if (mode_ext & 1) {
+                        uint8_t *s_isp = reinterpret_cast<uint8_t *>(s_scale[1]);  // channel 1's scale table is no longer needed
+                        __syncwarp();
+                        if (lane < 22) s_isp[lane] = (uint8_t)intensity_entry(T, cfg, c0, s_pk[0], c1.cnt1, lane);
+                        __syncwarp();
+#pragma unroll
+                        for (int q = 0; q < 9; q++) {
+                            const int is_pos = s_isp[sfb_q[q]];
+                            if (is_pos < 7) {
+                                const float rl = T.is_ratio_l[is_pos], rr = T.is_ratio_r[is_pos];
+                                x0[2 * q] = f_mul(x0[2 * q], rl); x1[2 * q] = f_mul(x1[2 * q], rr);
+                                x0[2 * q + 1] = f_mul(x0[2 * q + 1], rl); x1[2 * q + 1] = f_mul(x1[2 * q + 1], rr);
+                            }
+                        }
+                    }
                 }
+                // alias reduction (frame.go:427-452): butterfly i of the boundary below subband `lane` pairs this lane's
+                // line i with line 17-i of lane-1; all 31 x 8 butterflies touch disjoint lines, so order is free.
+#pragma unroll
+                for (int ch = 0; ch < 2; ch++) {
+                    float(&x)[18] = ch ? x1 : x0;
+                    if (ch == 1 && !valid_b) break;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const float lo_of_below = __shfl_up_sync(0xffffffffu, x[17 - i], 1);   // xr[18 sb - 1 - i] seen from sb
+                        const float up_of_above = __shfl_down_sync(0xffffffffu, x[i], 1);      // xr[18 (sb+1) + i] seen from sb
+                        const float nu = f_add(f_mul(x[i], kCs[i]), f_mul(lo_of_below, kCa[i]));
+                        const float nl = f_sub(f_mul(x[17 - i], kCs[i]), f_mul(up_of_above, kCa[i]));
+                        if (lane > 0) x[i] = nu;
+                        if (lane < 31) x[17 - i] = nl;
+                    }
+                }
+            } else {
+                // ---------------- K2: requantise + reorder (frame.go:140-302) -------------------------------
+                // Per-band scale table first, then the lines two at a time (unit_logic.h, "scale-table form").
+    #pragma unroll 1
+                for (int ch = 0; ch < 2; ch++) {
+                    if (ch == 1 && !valid_b) break;
+                    const GranuleChan &c = ch ? c1 : c0;
+                    s_scale[ch][lane] = scale_entry(T, c, s_pk[ch], lane);
+                    s_scale[ch][lane + 32] = scale_entry(T, c, s_pk[ch], lane + 32);
+                }
+                __syncwarp();
+    #pragma unroll 1
+                for (int ch = 0; ch < 2; ch++) {
+                    if (ch == 1 && !valid_b) break;
+                    const GranuleChan &c = ch ? c1 : c0;
+                    const uint32_t *is2 = reinterpret_cast<const uint32_t *>(B.is16 + ((long long)g * 2 + ch) * 576);
+                    const int npair = c.cnt1 >> 1;  // count1 is even: big_values pairs + count1 quadruples
+                    float *xs = s_x[ch];
+    #pragma unroll 3
+                    for (int p = lane; p < 288; p += 32) {
+                        int d0, d1;
+                        const int e = pair_lookup(T, cfg, c, p, &d0, &d1);
+                        float x0 = 0.0f, x1 = 0.0f;  // lines at or above count1 stay +0 (maindata/huffman.go:130-134)
+                        if (p < npair) {
+                            const uint32_t w = __ldg(is2 + p);
+                            const double sc = s_scale[ch][e];
+                            x0 = requant_value(T, sc, (int)(int16_t)(w & 0xffffu));
+                            x1 = requant_value(T, sc, (int)(int16_t)(w >> 16));
+                        }
+                        xs[xr_pad(d0)] = x0;
+                        xs[xr_pad(d1)] = x1;
+                    }
+                }
+                __syncwarp();
+                // ---------------- stereo (frame.go:362-420) -------------------------------------------------
+                if (valid_b && u_mode(w2a) == 1) {
+                    const int mode_ext = u_modeext(w2a);
+                    if (mode_ext & 2) {
+                        const int max_pos = c0.cnt1 > c1.cnt1 ? c0.cnt1 : c1.cnt1;
+                        const float inv_sqrt2 = 0.70710678118654752440f;
+                        for (int i = lane; i < max_pos; i += 32) {
+                            const int p = xr_pad(i);
+                            float a = s_x[0][p], b = s_x[1][p];
+                            s_x[0][p] = f_mul(f_add(a, b), inv_sqrt2);
+                            s_x[1][p] = f_mul(f_sub(a, b), inv_sqrt2);
+                        }
+                        __syncwarp();
+                    }
+                    if (mode_ext & 1) {
+                        // per-band intensity positions (channel 0's block type and scalefactors), then per line pair
+                        uint8_t *s_isp = reinterpret_cast<uint8_t *>(s_scale[1]);  // channel 1's scale table is no longer needed
+                        __syncwarp();
+                        s_isp[lane] = (uint8_t)intensity_entry(T, cfg, c0, s_pk[0], c1.cnt1, lane);
+                        s_isp[lane + 32] = (uint8_t)intensity_entry(T, cfg, c0, s_pk[0], c1.cnt1, lane + 32);
+                        __syncwarp();
+                        for (int p = lane; p < 288; p += 32) {
+                            int d0, d1;
+                            // the window is looked up at the PRE-reorder index although the data is reordered (frame.go:341-357)
+                            const int is_pos = s_isp[pair_lookup(T, cfg, c0, p, &d0, &d1)];
+                            if (is_pos < 7) {
+                                const float rl = T.is_ratio_l[is_pos], rr = T.is_ratio_r[is_pos];
+                                const int q0 = xr_pad(2 * p), q1 = xr_pad(2 * p + 1);
+                                s_x[0][q0] = f_mul(s_x[0][q0], rl);
+                                s_x[1][q0] = f_mul(s_x[1][q0], rr);
+                                s_x[0][q1] = f_mul(s_x[0][q1], rl);
+                                s_x[1][q1] = f_mul(s_x[1][q1], rr);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                // ---------------- alias reduction (frame.go:427-452) ----------------------------------------
+    #pragma unroll 1
+                for (int ch = 0; ch < 2; ch++) {
+                    if (ch == 1 && !valid_b) break;
+                    const int nb = alias_butterflies(ch ? c1 : c0);
+                    for (int b = lane; b < nb; b += 32) {
+                        const int sb = (b >> 3) + 1, i = b & 7;
+                        const int li = 18 * sb - 1 - i + (sb - 1), ui = 18 * sb + i + sb;  // padded positions
+                        const float xl = s_x[ch][li], xu = s_x[ch][ui];
+                        s_x[ch][li] = f_sub(f_mul(xl, T.cs[i]), f_mul(xu, T.ca[i]));
+                        s_x[ch][ui] = f_add(f_mul(xu, T.cs[i]), f_mul(xl, T.ca[i]));
+                    }
+                }
+                __syncwarp();
+
             }
-            __syncwarp();
 
             // ---------------- K3: IMDCT, lane = subband (frame.go:454-486) ------------------------------
 #pragma unroll 1
             for (int ch = 0; ch < 2; ch++) {
                 if (ch == 1 && !valid_b) break;
                 float in[18];
+                if (fast) {
 #pragma unroll
-                for (int m = 0; m < 18; m++) in[m] = s_x[ch][lane * kXrStride + m];
+                    for (int m = 0; m < 18; m++) in[m] = ch ? x1[m] : x0[m];
+                } else {
+#pragma unroll
+                    for (int m = 0; m < 18; m++) in[m] = s_x[ch][lane * kXrStride + m];
+                }
                 if (TAPS && need_first && B.tap_xr) {
                     float *o = B.tap_xr + ((long long)g * 2 + ch) * 576 + lane * 18;
 #pragma unroll

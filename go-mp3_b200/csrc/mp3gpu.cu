@@ -83,6 +83,15 @@ static int upload_tables(mp3gpu_ctx *ctx) {
         ctx->err = "const_tables.inc does not match the host-built IMDCT tables (rebuild the library on this libm)";
         return MP3GPU_E_INVALID;
     }
+    {
+        float cs[8], ca[8];
+        memcpy(cs, kCs, sizeof cs);
+        memcpy(ca, kCa, sizeof ca);
+        if (memcmp(cs, h.cs, sizeof cs) != 0 || memcmp(ca, h.ca, sizeof ca) != 0) {
+            ctx->err = "alias-reduction constants differ between kernels.cuh and tables.cc";
+            return MP3GPU_E_INVALID;
+        }
+    }
     CK(cudaMemcpyToSymbol(c_win, h.imdct_win, sizeof h.imdct_win));
     // the symmetric matrixing of k_synth relies on these identities holding bitwise in the float32 table
     for (int j = 0; j < 32; j++) {
