@@ -515,12 +515,14 @@ constexpr int kURow = 36;                        // floats per U row: 16-byte al
 constexpr int kSynSmemBytes = 2 * kSynThreads * kURow * 4 + kSynThreads;
 
 __device__ __forceinline__ int pcm_from_float(float sum) {
-    // frame.go:663-668: int(sum * 32767) truncates; Go on amd64 (CVTTSS2SQ) yields INT64_MIN for NaN / out of
-    // int64 range, which the clamp turns into -32767.
+    // frame.go:663-668: int(sum * 32767) truncates toward zero, then clamps to +-32767.  The clamp is done in float
+    // first (NaN -> -32767 like Go's INT64_MIN from CVTTSS2SQ; fmaxf returns the non-NaN operand).  The only inputs
+    // on which this differs from the reference are f >= 2^63 or +Inf (Go: INT64_MIN -> -32767, here +32767); they
+    // are unreachable: |xr| <= 8206^(4/3) * 2^(45/4) < 4.1e8, and 18 IMDCT terms x 32 x 16 synthesis terms x 32767
+    // bound |f| by 1.3e17 < 2^63.
     float f = __fmul_rn(sum, 32767.0f);
-    if (!(f < 9223372036854775808.0f && f >= -9223372036854775808.0f)) return -32767;
-    int s = __float2int_rz(f);  // saturates beyond int32, which the clamp absorbs
-    return max(-32767, min(32767, s));
+    f = fminf(fmaxf(f, -32767.0f), 32767.0f);
+    return __float2int_rz(f);
 }
 
 // NR consecutive rows of V for one slot: V[i] = sum_j N[i][j] * s[j], j ascending (frame.go:644-650)
@@ -569,9 +571,8 @@ __device__ __forceinline__ float window_sum(const float (&A)[15], const float (&
     return sum;
 }
 
-struct SynLane {  // where lane i finds V[i] and V[32+i] in a U row, and with which sign
+struct SynLane {  // where lane i finds V[i] and V[32+i] in a U row
     int ai, bi;
-    float sa, sb;  // +1 or -1; applied as fma(u, s, +0) so that a mirrored zero stays +0 like the direct sum
 };
 
 // One slot of phase B at circular position P.  FAST: the caller has checked that this and the other 14 rows of the
@@ -587,15 +588,15 @@ __device__ __forceinline__ void synth_window_slot(const float *U0, const float *
     }
     uint32_t pl = 0, pr = 0;
     if (f & 1) {
-        const float a = __fmaf_rn(U0[row * kURow + L.ai], L.sa, 0.0f);
-        const float b = __fmaf_rn(U0[row * kURow + L.bi], L.sb, 0.0f);
+        const float a = U0[row * kURow + L.ai];
+        const float b = U0[row * kURow + L.bi];
         A0[P] = a;
         if (!WARMUP) pl = (uint32_t)pcm_from_float(window_sum<P>(A0, B0, dw)) & 0xffffu;
         B0[P] = b;
     }
     if (f & 2) {
-        const float a = __fmaf_rn(U1[row * kURow + L.ai], L.sa, 0.0f);
-        const float b = __fmaf_rn(U1[row * kURow + L.bi], L.sb, 0.0f);
+        const float a = U1[row * kURow + L.ai];
+        const float b = U1[row * kURow + L.bi];
         A1[P] = a;
         if (!WARMUP) pr = (uint32_t)pcm_from_float(window_sum<P>(A1, B1, dw)) & 0xffffu;
         B1[P] = b;
@@ -649,14 +650,16 @@ k_synth(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_gr
 
     // ---------------- phase B: window + int16 store, warp = 30 slots, lane = output index -----------
     const int lane = tid & 31, warp = tid >> 5;
+    // V[i] = i <= 16 ? U[i] : -U[32-i];  V[32+i] = i == 0 ? -U[0] : i <= 16 ? U[16+i] : U[48-i].  A lane's sign is the
+    // same for all its even taps (V[i]) and for all its odd taps (V[32+i]), so it is folded into the window
+    // coefficients: fma(-u, D, acc) == fma(u, -D, acc) exactly, and a zero's sign never reaches a sum that starts at +0.
     SynLane L;
-    L.ai = lane <= 16 ? lane : 32 - lane;                      // V[i]    = i <= 16 ? U[i] : -U[32-i]
-    L.sa = lane <= 16 ? 1.0f : -1.0f;
-    L.bi = lane == 0 ? 0 : (lane <= 16 ? 16 + lane : 48 - lane);  // V[32+i] = i == 0 ? -U[0] : i <= 16 ? U[16+i] : U[48-i]
-    L.sb = lane == 0 ? -1.0f : 1.0f;
+    L.ai = lane <= 16 ? lane : 32 - lane;
+    L.bi = lane == 0 ? 0 : (lane <= 16 ? 16 + lane : 48 - lane);
+    const float sa = lane <= 16 ? 1.0f : -1.0f, sb = lane == 0 ? -1.0f : 1.0f;
     float dw[16];
 #pragma unroll
-    for (int d = 0; d < 16; d++) dw[d] = __ldg(B.synth_d + 32 * d + lane);
+    for (int d = 0; d < 16; d++) dw[d] = __ldg(B.synth_d + 32 * d + lane) * ((d & 1) ? sb : sa);
     float A0[15], B0[15], A1[15], B1[15];
 #pragma unroll
     for (int i = 0; i < 15; i++) { A0[i] = B0[i] = A1[i] = B1[i] = 0.f; }
