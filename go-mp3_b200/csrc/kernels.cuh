@@ -319,16 +319,17 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
 #pragma unroll
                     for (int q = 0; q < 9; q++) {
                         const int p = lane * 9 + q;
-                        x0[2 * q] = x0[2 * q + 1] = x1[2 * q] = x1[2 * q + 1] = 0.0f;
-                        if (p < np0) {
-                            const double sc = s_scale[0][sfb_q[q]];
-                            x0[2 * q] = requant_value(T, sc, (int)(int16_t)(C.isw[0][q] & 0xffffu));
-                            x0[2 * q + 1] = requant_value(T, sc, (int)(int16_t)(C.isw[0][q] >> 16));
-                        }
-                        if (p < np1) {  // np1 == 0 without channel 1
-                            const double sc = s_scale[1][sfb_q[q]];
-                            x1[2 * q] = requant_value(T, sc, (int)(int16_t)(C.isw[1][q] & 0xffffu));
-                            x1[2 * q + 1] = requant_value(T, sc, (int)(int16_t)(C.isw[1][q] >> 16));
+                        // a pair at or above count1 is read as (0, 0): powtab34[0] = 0 and scale * 0 = +0
+                        const uint32_t wa = p < np0 ? C.isw[0][q] : 0u;
+                        const double sa = s_scale[0][sfb_q[q]];
+                        x0[2 * q] = requant_value(T, sa, (int)(int16_t)(wa & 0xffffu));
+                        x0[2 * q + 1] = requant_value(T, sa, (int)(int16_t)(wa >> 16));
+                        x1[2 * q] = x1[2 * q + 1] = 0.0f;
+                        if (valid_b) {
+                            const uint32_t wb = p < np1 ? C.isw[1][q] : 0u;
+                            const double sb = s_scale[1][sfb_q[q]];
+                            x1[2 * q] = requant_value(T, sb, (int)(int16_t)(wb & 0xffffu));
+                            x1[2 * q + 1] = requant_value(T, sb, (int)(int16_t)(wb >> 16));
                         }
                     }
                 }

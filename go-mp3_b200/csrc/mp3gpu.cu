@@ -50,6 +50,7 @@ struct mp3gpu_ctx {
     unsigned int *d_counter = nullptr;
     int sm_count = 0;
     int seg_len = 32;
+    size_t ws_granules = 0;   // granules the wave workspace currently holds
     // staging for host-buffer calls
     uint8_t *d_main = nullptr;
     size_t d_main_cap = 0;
@@ -68,6 +69,30 @@ struct mp3gpu_ctx {
     size_t last_wave_granules = 0;
     long long last_wave_first = 0;
 };
+
+// Wave workspace, sized for min(wave, granules of the call) and grown on demand: a streaming Decoder that submits a
+// few hundred frames at a time should not pay for a million-granule batch workspace.
+static int ensure_workspace(mp3gpu_ctx *ctx, size_t granules) {
+    const size_t W = std::min<size_t>(ctx->wave, std::max<size_t>(granules, 1));
+    if (W <= ctx->ws_granules) return MP3GPU_OK;
+    CK(cudaStreamSynchronize(ctx->s_compute));
+    cudaFree(ctx->d_is16); cudaFree(ctx->d_meta); cudaFree(ctx->d_sfpack); cudaFree(ctx->d_hyb); cudaFree(ctx->d_tap_xr);
+    for (int i = 0; i < 3; i++) { cudaFree(ctx->d_pcm_ring[i]); ctx->d_pcm_ring[i] = nullptr; }
+    ctx->d_is16 = nullptr; ctx->d_meta = nullptr; ctx->d_sfpack = nullptr; ctx->d_hyb = nullptr; ctx->d_tap_xr = nullptr;
+    ctx->ws_granules = 0;
+    // K1 outputs, with two look-back granules (halo of k_hybrid) in front
+    CK(cudaMalloc(&ctx->d_is16, (W + 2) * 2 * 576 * sizeof(int16_t)));
+    CK(cudaMalloc(&ctx->d_meta, (W + 2) * 2 * sizeof(uint32_t)));
+    CK(cudaMalloc(&ctx->d_sfpack, (W + 2) * 2 * 8 * sizeof(uint32_t)));
+    CK(cudaMemset(ctx->d_is16, 0, 2 * 2 * 576 * sizeof(int16_t)));
+    CK(cudaMemset(ctx->d_meta, 0, 2 * 2 * sizeof(uint32_t)));
+    CK(cudaMemset(ctx->d_sfpack, 0, 2 * 2 * 8 * sizeof(uint32_t)));
+    CK(cudaMalloc(&ctx->d_hyb, (W + 1) * 2 * 576 * sizeof(float)));
+    CK(cudaMemset(ctx->d_hyb, 0, 2 * 576 * sizeof(float)));
+    if (ctx->opts.keep_intermediates) CK(cudaMalloc(&ctx->d_tap_xr, W * 2 * 576 * sizeof(float)));
+    ctx->ws_granules = W;
+    return MP3GPU_OK;
+}
 
 static int upload_tables(mp3gpu_ctx *ctx) {
     HostTables h;
@@ -173,7 +198,7 @@ extern "C" int mp3gpu_create(int device, const mp3gpu_opts *opts, mp3gpu_ctx **o
     mp3gpu_ctx *ctx = new mp3gpu_ctx();
     ctx->device = device;
     if (opts) ctx->opts = *opts;
-    ctx->wave = ctx->opts.wave_granules ? ctx->opts.wave_granules : 262144u;
+    ctx->wave = ctx->opts.wave_granules ? ctx->opts.wave_granules : 1048576u;
     auto fail = [&](int rc) {
         fprintf(stderr, "mp3gpu_create: %s\n", ctx->err.c_str());
         mp3gpu_destroy(ctx);
@@ -186,17 +211,6 @@ extern "C" int mp3gpu_create(int device, const mp3gpu_opts *opts, mp3gpu_ctx **o
         CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
         int rc = upload_tables(ctx);
         if (rc) return rc;
-        const size_t W = ctx->wave;
-        // K1 outputs, with two look-back granules (halo of the fused kernel) in front
-        CK(cudaMalloc(&ctx->d_is16, (W + 2) * 2 * 576 * sizeof(int16_t)));
-        CK(cudaMalloc(&ctx->d_meta, (W + 2) * 2 * sizeof(uint32_t)));
-        CK(cudaMalloc(&ctx->d_sfpack, (W + 2) * 2 * 8 * sizeof(uint32_t)));
-        CK(cudaMemset(ctx->d_is16, 0, 2 * 2 * 576 * sizeof(int16_t)));
-        CK(cudaMemset(ctx->d_meta, 0, 2 * 2 * sizeof(uint32_t)));
-        CK(cudaMemset(ctx->d_sfpack, 0, 2 * 2 * 8 * sizeof(uint32_t)));
-        CK(cudaMalloc(&ctx->d_hyb, (W + 1) * 2 * 576 * sizeof(float)));
-        CK(cudaMemset(ctx->d_hyb, 0, 2 * 576 * sizeof(float)));
-        if (ctx->opts.keep_intermediates) CK(cudaMalloc(&ctx->d_tap_xr, W * 2 * 576 * sizeof(float)));
         CK(cudaMalloc(&ctx->d_counter, sizeof(unsigned int)));
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, device));
@@ -340,9 +354,13 @@ extern "C" int mp3gpu_decode_device_async(mp3gpu_ctx *ctx, const uint8_t *d_main
     ctx->last_slots = 0;
     ctx->last_collected = true;
     if (n_granules == 0) return MP3GPU_OK;
+    {
+        int rc = ensure_workspace(ctx, n_granules);
+        if (rc) return rc;
+    }
     int slot = 0;
-    for (size_t first = 0; first < n_granules; first += ctx->wave) {
-        int n = (int)std::min<size_t>(ctx->wave, n_granules - first);
+    for (size_t first = 0; first < n_granules; first += ctx->ws_granules) {
+        int n = (int)std::min<size_t>(ctx->ws_granules, n_granules - first);
         int rc = launch_wave(ctx, d_main_data, d_units, (long long)first, n, d_pcm_out + first * 1152,
                              slot < kTimingSlots ? slot : -1);
         if (rc) return rc;
@@ -405,11 +423,12 @@ extern "C" int mp3gpu_decode(mp3gpu_ctx *ctx, const uint8_t *main_data, size_t m
     if (rc) return rc;
     rc = ensure_cap(ctx, (uint8_t **)&ctx->d_units, &ctx->d_units_cap, n_granules * 2 * sizeof(mp3gpu_unit));
     if (rc) return rc;
-    const size_t W = ctx->wave;
-    const size_t ring_bytes = std::min<size_t>(W, n_granules) * MP3GPU_PCM_BYTES_PER_GRANULE;
+    // host-buffer calls pipeline H2D / kernels / D2H wave by wave: use at least four waves per call so the copies overlap
+    rc = ensure_workspace(ctx, std::max<size_t>((n_granules + 3) / 4, std::min<size_t>(n_granules, 16384)));
+    if (rc) return rc;
+    const size_t W = std::min<size_t>(ctx->ws_granules, std::max<size_t>((n_granules + 3) / 4, std::min<size_t>(n_granules, 16384)));
     for (int i = 0; i < 3; i++)
-        if (!ctx->d_pcm_ring[i]) CK(cudaMalloc(&ctx->d_pcm_ring[i], W * MP3GPU_PCM_BYTES_PER_GRANULE));
-    (void)ring_bytes;
+        if (!ctx->d_pcm_ring[i]) CK(cudaMalloc(&ctx->d_pcm_ring[i], ctx->ws_granules * MP3GPU_PCM_BYTES_PER_GRANULE));
 
     // Wave w needs main_data up to the end of its last unit's frame buffer.  Units are in stream
     // order, so the byte ranges are monotonic; each wave uploads only the bytes not yet resident.

@@ -443,8 +443,9 @@ MP3_HD int pair_lookup(const DeviceTables &T, int cfg, const GranuleChan &c, int
 
 // One requantised line: sign(is) * |is|^(4/3) * scale, in double, rounded once (frame.go:146-155).
 MP3_HD float requant_value(const DeviceTables &T, double scale, int v) {
-    double a = T.powtab34[v < 0 ? -v : v];
-    return d_mul_to_f(scale, v < 0 ? -a : a);
+    // the sign is applied after the single rounding: round-to-nearest is symmetric, so float32(s * -a) == -float32(s * a)
+    const float r = d_mul_to_f(scale, T.powtab34[v < 0 ? -v : v]);
+    return v < 0 ? -r : r;
 }
 
 // Intensity-stereo table entry e (same indexing as the scale table, channel 0's block type and scalefactors,
