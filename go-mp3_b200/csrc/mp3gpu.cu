@@ -77,6 +77,7 @@ static int ensure_workspace(mp3gpu_ctx *ctx, size_t granules) {
     if (W <= ctx->ws_granules) return MP3GPU_OK;
     CK(cudaStreamSynchronize(ctx->s_compute));
     cudaFree(ctx->d_is16); cudaFree(ctx->d_meta); cudaFree(ctx->d_sfpack); cudaFree(ctx->d_hyb); cudaFree(ctx->d_tap_xr);
+
     for (int i = 0; i < 3; i++) { cudaFree(ctx->d_pcm_ring[i]); ctx->d_pcm_ring[i] = nullptr; }
     ctx->d_is16 = nullptr; ctx->d_meta = nullptr; ctx->d_sfpack = nullptr; ctx->d_hyb = nullptr; ctx->d_tap_xr = nullptr;
     ctx->ws_granules = 0;
@@ -286,8 +287,8 @@ static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, const mp3gpu_unit
     cudaStream_t s = ctx->s_compute;
     if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][0], s));
     {
-        int nu = 2 * n;
-        k_huffman<<<(nu + 127) / 128, 128, ctx->lut_bytes, s>>>(d_main, d_units, first * 2, nu, ctx->T, B);
+        const int nu = 2 * n;
+        k_huffman<<<(nu + kHuffThreads - 1) / kHuffThreads, kHuffThreads, ctx->lut_bytes, s>>>(d_main, d_units, first * 2, nu, ctx->T, B);
     }
     if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][1], s));
     {
