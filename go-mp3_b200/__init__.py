@@ -219,6 +219,37 @@ def shard_streams(n_streams: int, world: int, rank: int) -> Tuple[int, int]:
     return first, first + base + (1 if rank < extra else 0)
 
 
+def frame_range_job(pb: "ParsedBatch", stream: int, f0: int, f1: int):
+    """Self-contained decode job for frames [f0, f1) of one stream of a parsed batch (BASELINE.json configs[4]: one long
+    stream split at frame boundaries, e.g. one range per GPU, or a random-access read).
+
+    The job starts with a halo of whole frames covering the two granules in front of f0: PCM of a granule needs the
+    IMDCT overlap of the granule before it and 15 slots of V history, which in turn need the overlap of the one before
+    that.  The reservoir needs no halo: bit-slices were resolved on the host over the whole stream.
+    Returns (main_data_window, window_len, units, halo_granules); decode it and drop the first halo_granules * 2304 bytes.
+    """
+    st = pb.streams[stream]
+    frames = st["frames"]
+    if not (0 <= f0 <= f1 <= frames):
+        raise ValueError("frame range outside the stream")
+    gpf = (st["pcm_bytes"] // 2304) // frames if frames else 2   # granules per frame: 2 (MPEG-1) or 1 (LSF)
+    g_base = st["pcm_offset"] // 2304
+    halo_frames = min(f0, 2 // gpf if gpf else 1)
+    ga, gb = g_base + (f0 - halo_frames) * gpf, g_base + f1 * gpf
+    units = pb.units[2 * ga:2 * gb].copy()
+    if len(units) == 0:
+        return np.zeros(64, np.uint8), 0, units, 0
+    valid = (units["w2"] & W2_VALID) != 0
+    lo_bit = int(units["bit_start"][valid].min())
+    hi_bit = int((units["bit_start"][valid].astype(np.int64) + units["buf_end_rel"][valid]).max())
+    lo = (lo_bit // 8) & ~3
+    hi = min(pb.main_data_len, (max(hi_bit, lo_bit) + 7) // 8)
+    window = np.zeros(hi - lo + 64, np.uint8)
+    window[:hi - lo] = pb.main_data[lo:hi]
+    units["bit_start"] -= np.uint64(lo * 8)
+    return window, hi - lo, units, halo_frames * gpf
+
+
 def error_string(code: int) -> str:
     return host_lib().mp3_error_string(code).decode()
 
@@ -361,6 +392,13 @@ class GpuEngine:
 
     def host_free(self, p: int):
         self.lib.mp3gpu_host_free(p)
+
+    def decode_frames(self, pb: "ParsedBatch", stream: int, f0: int, f1: int) -> np.ndarray:
+        """PCM of frames [f0, f1) of one stream, decoded on their own (halo handled): int16 [samples, 2]."""
+        window, n, units, halo = frame_range_job(pb, stream, f0, f1)
+        if len(units) == 0:
+            return np.zeros((0, 2), np.int16)
+        return self.decode(window, n, units)[halo * 576:]
 
     def timings(self) -> dict:
         t = GpuTimings()
