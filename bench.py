@@ -244,23 +244,41 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- e2e: host buffers through the C ABI (pinned; H2D + kernels + D2H inside the timed region) ----------------
     e2e = None
-    h2d = pb.main_data_len + n_gr * 2 * 32
+    # Pinned host memory is bounded to ~48 GB over all ranks of the node: at N = 1 and 2 every rank runs its whole batch
+    # through the host API; beyond that a stream-ordered prefix of the batch (per-GPU e2e is PCIe-bound and does not depend
+    # on the batch size).  The prefix is a whole number of streams, so it is a self-contained submission.
+    e2e_streams = args.streams
+    per_stream_pcm = (n_gr * 2304) // max(args.streams, 1)
+    budget = int(48e9) // world
+    if per_stream_pcm * e2e_streams > budget:
+        e2e_streams = max(1, budget // max(per_stream_pcm, 1))
+    e2e_gr = sum(s["pcm_bytes"] for s in pb.streams[:e2e_streams]) // 2304
+    full_gr, full_main_len = n_gr, pb.main_data_len
+    if e2e_streams < args.streams:
+        u = pb.units[: e2e_gr * 2]
+        valid = (u["w2"] >> 25) & 1 == 1
+        main_end = int(((u["bit_start"][valid].astype(np.int64) + u["buf_end_rel"][valid]).max() + 7) // 8)
+        n_gr, main_len_e2e = e2e_gr, min(main_end, pb.main_data_len)
+    else:
+        main_len_e2e = pb.main_data_len
+    h2d = main_len_e2e + n_gr * 2 * 32
     d2h = n_gr * 2304
     del d_pcm
     torch.cuda.empty_cache()
     try:
-        p_main = eng.host_alloc(pb.main_data_len + 64)
+        p_main = eng.host_alloc(main_len_e2e + 64)
         p_units = eng.host_alloc(n_gr * 2 * 32)
         p_pcm = eng.host_alloc(d2h)
-        C.memmove(p_main, pb.main_data.ctypes.data, pb.main_data_len + 64)
+        C.memset(p_main, 0, main_len_e2e + 64)
+        C.memmove(p_main, pb.main_data.ctypes.data, main_len_e2e)
         C.memmove(p_units, pb.units.ctypes.data, n_gr * 2 * 32)
         e2e_steps = max(1, min(args.steps, 3))
-        eng.decode_host(p_main, pb.main_data_len, p_units, n_gr, p_pcm)  # warm-up (allocates the staging ring)
+        eng.decode_host(p_main, main_len_e2e, p_units, n_gr, p_pcm)  # warm-up (allocates the staging ring)
         if world > 1:
             dist.barrier()
         tw = time.perf_counter()
         for _ in range(e2e_steps):
-            eng.decode_host(p_main, pb.main_data_len, p_units, n_gr, p_pcm)
+            eng.decode_host(p_main, main_len_e2e, p_units, n_gr, p_pcm)
         e2e_s = (time.perf_counter() - tw) / e2e_steps
         e2e_t = eng.timings()
         if world > 1:
@@ -270,7 +288,7 @@ def run_ours(args, rank, world, local_rank):
         if rank == 0 and parity is not None:
             got = np.ctypeslib.as_array(C.cast(p_pcm, C.POINTER(C.c_int16)), shape=(ref.size,))
             parity["e2e_max_abs_diff_lsb"] = int(np.abs(got.astype(np.int32) - ref.astype(np.int32)).max())
-        e2e = {"value": samples_per_step * world / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+        e2e = {"value": n_gr * 576 * world / e2e_s / 1e6, "unit": UNIT, "streams_per_gpu": int(e2e_streams), "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                "api": "mp3gpu_decode (include/mp3gpu.h), pinned host buffers",
                "h2d_ms": e2e_t["h2d_ms"], "d2h_ms": e2e_t["d2h_ms"]}
@@ -278,6 +296,7 @@ def run_ours(args, rank, world, local_rank):
             eng.host_free(p)
     except MemoryError as ex:
         e2e = {"value": None, "unit": UNIT, "error": str(ex)}
+    n_gr = full_gr
 
     # ---- CPU baseline (rank 0, N = 1): oracle on all host cores over a bounded sample -----------------------------
     cpu_baseline = None

@@ -45,19 +45,37 @@ struct Rng {  // xoshiro256**
     bool chance(double p) { return uni() < p; }
 };
 
-struct BitWriter {
+struct BitWriter {  // sequential MSB-first writer starting at a byte boundary; whole bytes are overwritten
     std::vector<uint8_t> &buf;
-    size_t bit;  // absolute bit position in buf
-    BitWriter(std::vector<uint8_t> &b, size_t start_bit) : buf(b), bit(start_bit) {}
-    void put(uint32_t v, int n) {
-        for (int i = n - 1; i >= 0; i--) {
-            size_t byte = bit >> 3;
-            if (byte >= buf.size()) buf.resize(byte + 1, 0);
-            if ((v >> i) & 1) buf[byte] |= (uint8_t)(0x80u >> (bit & 7));
-            bit++;
+    size_t byte;    // next byte to write
+    uint64_t acc;   // pending bits (low nacc bits)
+    int nacc;
+    BitWriter(std::vector<uint8_t> &b, size_t start_bit) : buf(b), byte(start_bit >> 3), acc(0), nacc(0) {}
+    size_t bitpos() const { return byte * 8 + (size_t)nacc; }
+    void put(uint32_t v, int n) {  // n <= 32
+        if (n <= 0) return;
+        acc = (acc << n) | (uint64_t)(n == 32 ? v : (v & ((1u << n) - 1u)));
+        nacc += n;
+        if (byte + 8 > buf.size()) buf.resize(byte + 64, 0);
+        while (nacc >= 8) {
+            buf[byte++] = (uint8_t)(acc >> (nacc - 8));
+            nacc -= 8;
+        }
+    }
+    void flush() {  // write the pending partial byte (zero padded) without advancing
+        if (nacc > 0) {
+            if (byte + 1 > buf.size()) buf.resize(byte + 64, 0);
+            buf[byte] = (uint8_t)((acc << (8 - nacc)) & 0xff);
         }
     }
 };
+
+// -log(u) for u = (k + 0.5) / 1024: exponential variates by table instead of a log() per spectral value
+static double g_neglog[1024];
+static std::once_flag g_neglog_once;
+static inline double exp_variate(uint64_t r) {
+    return g_neglog[r >> 54];
+}
 
 // consts.go:68-97 (long-block sfb boundaries), [lsf][sfreq]
 const int kSfbLong[2][3][23] = {
@@ -97,6 +115,9 @@ struct EncTable {
 };
 EncTable g_enc[34];
 void ensure_enc() {
+    std::call_once(g_neglog_once, [] {
+        for (int k = 0; k < 1024; k++) g_neglog[k] = -std::log(((double)k + 0.5) / 1024.0);
+    });
     static std::once_flag once;
     std::call_once(once, [] {
         for (int t = 0; t < 34; t++) {
@@ -150,6 +171,14 @@ size_t synth_bound(const synth_cfg *c) {
 }  // extern "C"
 
 namespace {
+
+static inline void put_random(BitWriter &w, Rng &r, int nbits) {
+    while (nbits > 0) {
+        const int n = nbits > 32 ? 32 : nbits;
+        w.put((uint32_t)(r.next() >> 20) & (n == 32 ? 0xffffffffu : ((1u << n) - 1u)), n);
+        nbits -= n;
+    }
+}
 
 struct UnitSide {
     int p23 = 0, bigv = 0, ggain = 0, sfc = 0, ws = 0, bt = 0, mixed = 0, tsel[3] = {0, 0, 0}, sbg[3] = {0, 0, 0};
@@ -233,7 +262,7 @@ struct StreamGen {
         }
         if (budget > 4095) budget = 4095;
         if (c.wild && r.chance(0.03)) {  // Q1/Q6: zero-length unit; its scalefactor bits are still walked over
-            for (int i = 0; i < p2; i++) w.put((uint32_t)r.next() & 1, 1);
+            put_random(w, r, p2);
             u.p23 = 0;
             u.bigv = r.range(0, 288);
             for (int k = 0; k < 3; k++) u.tsel[k] = r.range(0, 31);
@@ -244,8 +273,8 @@ struct StreamGen {
             if (c.lsf) u.sfc = 0;
         }
         const int p2b = part2_bits(c, u, gr, scfsi);
-        const size_t start = w.bit;
-        for (int i = 0; i < p2b; i++) w.put((uint32_t)r.next() & 1, 1);
+        const size_t start = w.bitpos();
+        put_random(w, r, p2b);
         // region boundaries (maindata/huffman.go:41-64)
         int r1s, r2s;
         if (ws && bt == 2) { r1s = 36; r2s = 576; }
@@ -271,7 +300,9 @@ struct StreamGen {
         }
         int used = p2b;
         int nbig = 0;
-        for (; nbig < want_big; nbig++) {
+        const double decay = std::exp(-2.0 / tau);
+        double env = a0;  // a0 * exp(-pos / tau), updated per pair
+        for (; nbig < want_big; nbig++, env *= decay) {
             int pos = nbig * 2;
             int k = pos < r1s ? 0 : (pos < r2s ? 1 : 2);
             const EncTable &e = g_enc[u.tsel[k]];
@@ -279,11 +310,11 @@ struct StreamGen {
             uint32_t code = 0;
             int lin_x = 0, lin_y = 0;
             if (!e.empty) {
-                double a = a0 * std::exp(-(double)pos / tau);
+                const double a = env;
                 int cap = e.linbits ? 15 + (1 << e.linbits) - 1 : e.maxv;
                 cap = std::min(cap, region_max[k]);
                 auto draw = [&]() {
-                    double v = -std::log(1.0 - r.uni()) * a;  // exponential magnitude
+                    double v = exp_variate(r.next()) * a;  // exponential magnitude
                     int iv = (int)v;
                     return iv > cap ? cap : iv;
                 };
@@ -324,11 +355,11 @@ struct StreamGen {
         if (c.wild && r.chance(0.15)) {  // Q4: a few stuffing bits inside part2_3_length -> the count1 loop runs on / overshoots
             int extra = r.range(1, 9);
             if (used + extra <= budget) {
-                for (int i = 0; i < extra; i++) w.put((uint32_t)r.next() & 1, 1);
+                put_random(w, r, extra);
                 used += extra;
             }
         }
-        u.p23 = (int)(w.bit - start);
+        u.p23 = (int)(w.bitpos() - start);
         return u;
     }
 
@@ -422,16 +453,17 @@ struct StreamGen {
                         if (c.wild == 1 && bt != 2 && ws && r.chance(0.1)) mixed = 1;   // Q15: mixed flag on start/stop windows
                         if (c.wild == 1 && bt == 0 && r.chance(0.03)) ws = 1;           // Q15: window switching with block type 0
                     }
-                    long share = (budget - (long)(w.bit - write_pos * 8)) / (n_units - unit_i);
+                    long share = (budget - (long)(w.bitpos() - write_pos * 8)) / (n_units - unit_i);
                     if (share < 0) share = 0;
                     share = share * r.range(70, 130) / 100;
-                    long remaining = avail_bits - (long)(w.bit - write_pos * 8);
+                    long remaining = avail_bits - (long)(w.bitpos() - write_pos * 8);
                     if (share > remaining) share = remaining;
                     us[gr][ch] = gen_unit(w, gr, scfsi[ch], bt, ws, mixed, (int)share);
                     unit_i++;
                 }
             }
-            size_t end_byte = (w.bit + 7) >> 3;
+            w.flush();
+            size_t end_byte = (w.bitpos() + 7) >> 3;
             if (end_byte > slot_end) end_byte = slot_end;  // never triggers: budgets are bounded by avail_bits
             write_pos = end_byte;
             if (c.wild == 1 && f > 0 && r.chance(0.01)) mdb = r.range(mdb, mdb_max);  // Q8: reservoir underflow / misaligned start
@@ -500,6 +532,7 @@ struct StreamGen {
                         sw.put((uint32_t)u.c1t, 1);
                     }
             }
+            sw.flush();
             memcpy(&side[(size_t)f * (size_t)si_size], sib.data(), (size_t)si_size);
         }
         // ---- pass 3: byte stream -------------------------------------------------------------------
