@@ -1,0 +1,63 @@
+"""Size-independent properties at batch scale (the oracle is too slow to check every stream of a large batch):
+
+* position independence — a stream's PCM does not depend on where it sits in a batch, on its neighbours, or on how the
+  batch is cut into kernel waves (segment halos, CTA halos, wave look-back slots, K1 work-order sort);
+* determinism — two passes over the same batch are bit-identical;
+* spot checks against the oracle within the +-1 LSB tolerance of the north star, exact-match fraction reported.
+"""
+import numpy as np
+import pytest
+
+import common
+import oracle
+from tools.synth import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_batch_position_independence_and_oracle_spot_checks(pkg):
+    n = 160
+    cfgs = [(synth.cfg3(i, 300) if i % 2 == 0 else synth.cfg4(i, 300)) for i in range(n)]
+    buf, offs, lens = synth.batch(cfgs, 8)
+    sb = pkg.StreamBuffer(buf, offs, lens)
+    pb = pkg.parse_streams(sb, 8)
+    assert all(s["status"] == 0 and s["frames"] == 300 for s in pb.streams)
+    big = pkg.GpuEngine(0)                             # one wave
+    small = pkg.GpuEngine(0, wave_granules=7777)       # a dozen waves, cut at arbitrary granules
+    a = big.decode(pb.main_data, pb.main_data_len, pb.units)
+    b = small.decode(pb.main_data, pb.main_data_len, pb.units)
+    assert np.array_equal(a, b)
+    assert np.array_equal(a, big.decode(pb.main_data, pb.main_data_len, pb.units))   # determinism
+    worst, fracs = 0, []
+    for i in (0, 1, 37, 80, 121, 159):
+        st = pb.streams[i]
+        mine = a[st["pcm_offset"] // 4:(st["pcm_offset"] + st["pcm_bytes"]) // 4]
+        one = pkg.parse_streams([sb.stream(i)])
+        alone = big.decode(one.main_data, one.main_data_len, one.units)
+        assert np.array_equal(mine, alone), i                       # position independence
+        ref, err = oracle.OracleDecoder(sb.stream(i)).read_all()
+        mx, frac = common.pcm_stats(mine.reshape(-1), np.frombuffer(ref, np.int16))
+        worst = max(worst, mx)
+        fracs.append(frac)
+    print(f"max|diff| = {worst} LSB, exact-match fraction min {min(fracs):.6f}")
+    assert worst <= 1 and min(fracs) > 0.999   # tolerance: +-1 LSB of int16
+    big.close(); small.close()
+
+
+def test_host_and_device_apis_agree(pkg):
+    """mp3gpu_decode (host buffers, pipelined copies) and mp3gpu_decode_device (resident buffers) give the same PCM."""
+    import torch
+    cfgs = [synth.cfg4(i, 120) for i in range(48)]
+    buf, offs, lens = synth.batch(cfgs, 8)
+    pb = pkg.parse_streams(pkg.StreamBuffer(buf, offs, lens), 8)
+    g = pkg.GpuEngine(0, wave_granules=3000)
+    host = g.decode(pb.main_data, pb.main_data_len, pb.units)
+    dev = torch.device("cuda", 0)
+    d_main = torch.from_numpy(pb.main_data).to(dev)
+    d_units = torch.from_numpy(pb.units.view(np.uint8)).to(dev)
+    d_pcm = torch.zeros(pb.n_granules * 1152, dtype=torch.int16, device=dev)
+    g.decode_device(d_main.data_ptr(), pb.main_data_len, d_units.data_ptr(), pb.n_granules, d_pcm.data_ptr())
+    assert np.array_equal(host.reshape(-1), d_pcm.cpu().numpy())
+    t = g.timings()
+    assert t["launches"] == 3 * t["waves"] and t["waves"] >= 2
+    g.close()
