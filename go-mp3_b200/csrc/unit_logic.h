@@ -106,15 +106,15 @@ struct BitCursor {
     uint32_t w0, w1;        // current window
     int off;                // bit offset of the cursor inside w0 (0..31)
     int rem;                // bits from the MSB of *wp to the end of the frame's logical buffer (<= 0: past the end)
-    int pos;                // logical position relative to bit_start (BitPos() rebased to part2Start)
-    int lim;                // max(buf_end_rel, 0): pos never advances past it (bits.go:46-49)
+    int end_rel;            // buf_end_rel
+    int lim;                // max(buf_end_rel, 0): the logical position never advances past it (bits.go:46-49)
 
     MP3_HD void init(const uint8_t *main_data, uint64_t bit_start, int buf_end_rel) {
         wp = reinterpret_cast<const uint32_t *>(main_data) + (bit_start >> 5);
         off = (int)(bit_start & 31);
         rem = off + buf_end_rel;
+        end_rel = buf_end_rel;
         lim = buf_end_rel > 0 ? buf_end_rel : 0;
-        pos = 0;
         w0 = load_word();
         w1 = load_word();
     }
@@ -130,10 +130,13 @@ struct BitCursor {
         return w;
     }
     MP3_HD uint32_t peek32() const { return funnel_l(w0, w1, off); }  // next 32 bits, MSB first
-    // Bit()-style consumption of n <= 32 bits (tree bits, sign bits): the logical cursor clamps at the buffer end.
+    // Logical position relative to bit_start (BitPos() rebased to part2Start).  The window has consumed
+    // end_rel - 64 - rem + off bits since init (rem drops by 32 per loaded word); the reference's cursor is that,
+    // clamped at the buffer end: Bit() past the end returns 0 without advancing, and a refused Bits(n) moves neither.
+    MP3_HD int pos() const { return imin(end_rel - 64 - rem + off, lim); }
+    // Bit()-style consumption of n <= 32 bits (tree bits, sign bits).
     MP3_HD void skip(int n) {
         off += n;
-        pos = imin(pos + n, lim);
         if (off >= 32) {
             off -= 32;
             w0 = w1;
@@ -143,7 +146,7 @@ struct BitCursor {
     // Bits(n), bits.go:58-77: returns 0 WITHOUT advancing when the read would cross the end.
     MP3_HD int bits(int n) {
         if (n == 0) return 0;
-        if (pos + n > lim) return 0;
+        if (pos() + n > lim) return 0;
         int v = (int)(peek32() >> (32 - n));
         skip(n);
         return v;
@@ -219,7 +222,7 @@ struct PairSink {
     uint4 *dst;
     uint32_t a0, a1, a2, a3;
     int n;
-    MP3_HD void init(uint32_t *out) { dst = reinterpret_cast<uint4 *>(out); a0 = a1 = a2 = a3 = 0; n = 0; }
+    MP3_HD void init(uint32_t *out, int n0 = 0) { dst = reinterpret_cast<uint4 *>(out); a0 = a1 = a2 = a3 = 0; n = n0; }  // n0 % 4 == 0
     MP3_HD void put(uint32_t w) {
         a0 = a1; a1 = a2; a2 = a3; a3 = w;
         n++;
@@ -340,19 +343,26 @@ MP3_HD uint32_t huffman_unit(const DeviceTables &T, const uint16_t *lut, const u
     }
     int nbig = u_bigval(w0);
     if (nbig > 288) nbig = 288;  // the host rejects such frames (huffman.go:68-70); never reached
-    PairSink sink;
-    sink.init(is_out);
-    {
-        const uint32_t d0 = huff_desc[u_tsel(w1, 0)], d1 = huff_desc[u_tsel(w1, 1)], d2 = huff_desc[u_tsel(w1, 2)];
-        for (int k = 0; k < nbig; k++) {
-            const uint32_t d = k < r1h ? d0 : (k < r2h ? d1 : d2);
-            sink.put(huff_pair(lut, d, bc));
+    const uint32_t d0 = huff_desc[u_tsel(w1, 0)], d1 = huff_desc[u_tsel(w1, 1)], d2 = huff_desc[u_tsel(w1, 2)];
+    int k = 0;
+    {   // four pairs per 16-byte store
+        uint4 *dst4 = reinterpret_cast<uint4 *>(is_out);
+        for (; k + 4 <= nbig; k += 4) {
+            uint4 v;
+            v.x = huff_pair(lut, k < r1h ? d0 : (k < r2h ? d1 : d2), bc);
+            v.y = huff_pair(lut, k + 1 < r1h ? d0 : (k + 1 < r2h ? d1 : d2), bc);
+            v.z = huff_pair(lut, k + 2 < r1h ? d0 : (k + 2 < r2h ? d1 : d2), bc);
+            v.w = huff_pair(lut, k + 3 < r1h ? d0 : (k + 3 < r2h ? d1 : d2), bc);
+            dst4[k >> 2] = v;
         }
     }
+    PairSink sink;
+    sink.init(is_out, k);
+    for (; k < nbig; k++) sink.put(huff_pair(lut, k < r1h ? d0 : (k < r2h ? d1 : d2), bc));
     int is_pos = nbig * 2;
     {
         uint32_t dq = huff_desc[32 + u_c1tsel(w2)];
-        while (is_pos <= 572 && bc.pos <= bit_pos_end) {
+        while (is_pos <= 572 && bc.pos() <= bit_pos_end) {
             uint32_t vw, xy;
             huff_quad(lut, dq, bc, vw, xy);
             sink.put(vw);
@@ -361,7 +371,7 @@ MP3_HD uint32_t huffman_unit(const DeviceTables &T, const uint16_t *lut, const u
         }
     }
     sink.flush();
-    if (bc.pos > bit_pos_end + 1) is_pos -= 4;  // overshoot: drop the last quadruple (huffman.go:119-122)
+    if (bc.pos() > bit_pos_end + 1) is_pos -= 4;  // overshoot: drop the last quadruple (huffman.go:119-122)
     if (is_pos < 0) is_pos = 0;
     return (uint32_t)is_pos | ((uint32_t)preflag << 10);
     // Lines >= count1 are zero by definition; K2 masks them instead of K1 writing zeros.

@@ -182,6 +182,6 @@ int emu_huff_one(int table, const uint8_t *buf, int len_bytes, int *out4) {
         out4[0] = (int16_t)(xy & 0xffff); out4[1] = (int16_t)(xy >> 16);
         out4[2] = (int16_t)(vw & 0xffff); out4[3] = (int16_t)(vw >> 16);
     }
-    return bc.pos;
+    return bc.pos();
 }
 }
