@@ -424,10 +424,12 @@ extern "C" int mp3gpu_decode(mp3gpu_ctx *ctx, const uint8_t *main_data, size_t m
     if (rc) return rc;
     rc = ensure_cap(ctx, (uint8_t **)&ctx->d_units, &ctx->d_units_cap, n_granules * 2 * sizeof(mp3gpu_unit));
     if (rc) return rc;
-    // host-buffer calls pipeline H2D / kernels / D2H wave by wave: use at least four waves per call so the copies overlap
-    rc = ensure_workspace(ctx, std::max<size_t>((n_granules + 3) / 4, std::min<size_t>(n_granules, 16384)));
+    // Host-buffer calls pipeline H2D / kernels / D2H wave by wave.  Only the first wave's upload + kernels and the last
+    // wave's download are exposed, so a call is cut into 16 waves (of at least 16,384 granules to keep launches efficient).
+    const size_t want = std::max<size_t>((n_granules + 15) / 16, std::min<size_t>(n_granules, 16384));
+    rc = ensure_workspace(ctx, want);
     if (rc) return rc;
-    const size_t W = std::min<size_t>(ctx->ws_granules, std::max<size_t>((n_granules + 3) / 4, std::min<size_t>(n_granules, 16384)));
+    const size_t W = std::min<size_t>(ctx->ws_granules, want);
     for (int i = 0; i < 3; i++)
         if (!ctx->d_pcm_ring[i]) CK(cudaMalloc(&ctx->d_pcm_ring[i], ctx->ws_granules * MP3GPU_PCM_BYTES_PER_GRANULE));
 
