@@ -76,8 +76,8 @@ struct WaveBufs {
 constexpr int kHuffThreads = 256;
 
 __global__ void __launch_bounds__(kHuffThreads)
-k_huffman(const uint8_t *__restrict__ main_data, const mp3gpu_unit *__restrict__ units, long long first_unit,
-          int n_units, DeviceTables T, WaveBufs B) {
+k_huffman(const uint8_t *__restrict__ main_data, unsigned long long main_bits, const mp3gpu_unit *__restrict__ units,
+          long long first_unit, int n_units, DeviceTables T, WaveBufs B) {
     extern __shared__ uint16_t s_lut[];
     __shared__ uint32_t s_desc[34];
     __shared__ unsigned int s_bin[40];
@@ -114,7 +114,7 @@ k_huffman(const uint8_t *__restrict__ main_data, const mp3gpu_unit *__restrict__
     }
     uint32_t pk[8];
     uint32_t *out = reinterpret_cast<uint32_t *>(B.is16 + (size_t)ul * 576);
-    uint32_t meta = huffman_unit(T, s_lut, s_desc, main_data, units, first_unit + ul, pk, out);
+    uint32_t meta = huffman_unit(T, s_lut, s_desc, main_data, main_bits, units, first_unit + ul, pk, out);
     uint4 *dst = reinterpret_cast<uint4 *>(B.sfpack + (size_t)ul * 8);
     dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);

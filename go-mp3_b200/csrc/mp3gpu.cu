@@ -274,7 +274,7 @@ extern "C" const char *mp3gpu_last_error(const mp3gpu_ctx *ctx) { return ctx ? c
 
 // Launch the four kernels for granules [first, first+n) of the submission on s_compute.
 // d_pcm_wave points at the PCM of granule `first`.  `slot` selects the timing events (or -1).
-static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, const mp3gpu_unit *d_units, long long first, int n,
+static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, size_t main_len, const mp3gpu_unit *d_units, long long first, int n,
                        int16_t *d_pcm_wave, int slot) {
     WaveBufs B;
     B.is16 = ctx->d_is16 + 2 * 2 * 576;  // granules -2, -1 live in front
@@ -288,7 +288,7 @@ static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, const mp3gpu_unit
     if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][0], s));
     {
         const int nu = 2 * n;
-        k_huffman<<<(nu + kHuffThreads - 1) / kHuffThreads, kHuffThreads, ctx->lut_bytes, s>>>(d_main, d_units, first * 2, nu, ctx->T, B);
+        k_huffman<<<(nu + kHuffThreads - 1) / kHuffThreads, kHuffThreads, ctx->lut_bytes, s>>>(d_main, (unsigned long long)main_len * 8ull, d_units, first * 2, nu, ctx->T, B);
     }
     if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][1], s));
     {
@@ -349,7 +349,6 @@ static int collect_timings(mp3gpu_ctx *ctx, int nslots) {
 extern "C" int mp3gpu_decode_device_async(mp3gpu_ctx *ctx, const uint8_t *d_main_data, size_t main_data_len,
                                           const mp3gpu_unit *d_units, size_t n_granules, int16_t *d_pcm_out) {
     if (!ctx) return MP3GPU_E_INVALID;
-    (void)main_data_len;
     CK(cudaSetDevice(ctx->device));
     ctx->last = mp3gpu_timings{};
     ctx->last_slots = 0;
@@ -362,7 +361,7 @@ extern "C" int mp3gpu_decode_device_async(mp3gpu_ctx *ctx, const uint8_t *d_main
     int slot = 0;
     for (size_t first = 0; first < n_granules; first += ctx->ws_granules) {
         int n = (int)std::min<size_t>(ctx->ws_granules, n_granules - first);
-        int rc = launch_wave(ctx, d_main_data, d_units, (long long)first, n, d_pcm_out + first * 1152,
+        int rc = launch_wave(ctx, d_main_data, main_data_len, d_units, (long long)first, n, d_pcm_out + first * 1152,
                              slot < kTimingSlots ? slot : -1);
         if (rc) return rc;
         if (slot < kTimingSlots) slot++;
@@ -468,7 +467,7 @@ extern "C" int mp3gpu_decode(mp3gpu_ctx *ctx, const uint8_t *main_data, size_t m
         // -- kernels on s_compute (wait for inputs and for the ring slot to be drained)
         CK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_in[r], 0));
         if (widx >= 3) CK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_out[r], 0));
-        rc = launch_wave(ctx, ctx->d_main, ctx->d_units, (long long)first, n, ctx->d_pcm_ring[r],
+        rc = launch_wave(ctx, ctx->d_main, main_data_len, ctx->d_units, (long long)first, n, ctx->d_pcm_ring[r],
                          slot < kTimingSlots ? slot : -1);
         if (rc) return rc;
         if (slot < kTimingSlots) slot++;

@@ -51,6 +51,8 @@ struct DeviceTables {
     int pow2_off;
 };
 
+MP3_HD int imin(int a, int b) { return a < b ? a : b; }
+
 // ---- side-info field accessors ---------------------------------------------------------------
 MP3_HD int u_p23len(uint32_t w0) { return (int)(w0 & 0xfff); }
 MP3_HD int u_bigval(uint32_t w0) { return (int)((w0 >> 12) & 0x1ff); }
@@ -67,7 +69,7 @@ MP3_HD int u_sfscale(uint32_t w2) { return (int)((w2 >> 10) & 1); }
 MP3_HD int u_c1tsel(uint32_t w2) { return (int)((w2 >> 11) & 1); }
 MP3_HD int u_scfsi(uint32_t w2) { return (int)((w2 >> 12) & 0xf); }
 MP3_HD int u_lsf(uint32_t w2) { return (int)((w2 >> 16) & 1); }
-MP3_HD int u_sfreq(uint32_t w2) { return (int)((w2 >> 17) & 3); }
+MP3_HD int u_sfreq(uint32_t w2) { return imin((int)((w2 >> 17) & 3), 2); }  // 3 is reserved (frameheader.go:178); clamped so table indices stay in range
 MP3_HD int u_mode(uint32_t w2) { return (int)((w2 >> 19) & 3); }
 MP3_HD int u_modeext(uint32_t w2) { return (int)((w2 >> 21) & 3); }
 MP3_HD int u_gr(uint32_t w2) { return (int)((w2 >> 23) & 1); }
@@ -75,7 +77,6 @@ MP3_HD bool u_valid(uint32_t w2) { return (w2 & MP3GPU_W2_VALID) != 0; }
 MP3_HD bool u_zero(uint32_t w2) { return (w2 & MP3GPU_W2_ZERO_STATE) != 0; }
 MP3_HD int u_mixed(uint32_t w2) { return (int)((w2 >> 27) & 1); }
 
-MP3_HD int imin(int a, int b) { return a < b ? a : b; }
 
 // ---- rounding-exact float helpers (no contraction on either side) -----------------------------
 #if defined(__CUDA_ARCH__)
@@ -109,7 +110,12 @@ struct BitCursor {
     int end_rel;            // buf_end_rel
     int lim;                // max(buf_end_rel, 0): the logical position never advances past it (bits.go:46-49)
 
-    MP3_HD void init(const uint8_t *main_data, uint64_t bit_start, int buf_end_rel) {
+    // main_bits = 8 * main_data_len: a descriptor that points outside main_data (a caller's bug, never produced by the
+    // host stage) is clipped to it instead of reading out of bounds.
+    MP3_HD void init(const uint8_t *main_data, uint64_t main_bits, uint64_t bit_start, int buf_end_rel) {
+        if (bit_start > main_bits) bit_start = main_bits;
+        const uint64_t room = main_bits - bit_start;
+        if (buf_end_rel > 0 && (uint64_t)buf_end_rel > room) buf_end_rel = (int)room;
         wp = reinterpret_cast<const uint32_t *>(main_data) + (bit_start >> 5);
         off = (int)(bit_start & 31);
         rem = off + buf_end_rel;
@@ -264,12 +270,12 @@ MP3_HD void sf_mpeg1_read_all(const DeviceTables &T, BitCursor &bc, uint32_t w0,
 // Outputs: pk[8] scalefactor nibbles (n = sfb for scalefac_l, 22 + sfb*3 + win for scalefac_s),
 // is_out[0..count1/2) packed int16 pairs, return value meta = count1 | preflag << 10.
 MP3_HD uint32_t huffman_unit(const DeviceTables &T, const uint16_t *lut, const uint32_t *huff_desc,
-                             const uint8_t *main_data, const mp3gpu_unit *units, long long unit_index,
+                             const uint8_t *main_data, uint64_t main_bits, const mp3gpu_unit *units, long long unit_index,
                              uint32_t *pk, uint32_t *is_out) {
     const mp3gpu_unit u = units[unit_index];
     const uint32_t w0 = u.w0, w1 = u.w1, w2 = u.w2;
     BitCursor bc;
-    bc.init(main_data, u.bit_start, u.buf_end_rel);
+    bc.init(main_data, main_bits, u.bit_start, u.buf_end_rel);
     for (int i = 0; i < 8; i++) pk[i] = 0;
 
     // ---- part 2: scalefactors -------------------------------------------------------------
@@ -304,11 +310,11 @@ MP3_HD uint32_t huffman_unit(const DeviceTables &T, const uint16_t *lut, const u
     } else {
         // gr 1, long-type block, at least one scfsi band set: those bands copy ScalefacL[0][ch]
         // as gr 0's parse left it (zeros if gr 0 was short; sfb 0-7 only if gr 0 was mixed).
-        const mp3gpu_unit u0 = units[unit_index - 2];
         uint32_t pk0[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        {
+        if (unit_index >= 2) {  // a submission always starts on a frame boundary; guard against one that does not
+            const mp3gpu_unit u0 = units[unit_index - 2];
             BitCursor b0;
-            b0.init(main_data, u0.bit_start, u0.buf_end_rel);
+            b0.init(main_data, main_bits, u0.bit_start, u0.buf_end_rel);
             sf_mpeg1_read_all(T, b0, u0.w0, u0.w1, u0.w2, pk0);
         }
         int sfc = u_sfcomp(w1) & 15;

@@ -50,8 +50,8 @@ void ensure() {
 extern "C" {
 
 // K1 on the CPU: is16 [n][576] (zero-filled above count1), meta [n], scalefac [n][64] (as MP3GPU_TAP_SCALEFAC).
-void emu_huffman(const uint8_t *main_data, const mp3gpu_unit *units, long long n_units, int16_t *is16, uint32_t *meta,
-                 uint8_t *scalefac) {
+void emu_huffman(const uint8_t *main_data, unsigned long long main_bits, const mp3gpu_unit *units, long long n_units, int16_t *is16,
+                 uint32_t *meta, uint8_t *scalefac) {
     ensure();
     for (long long u = 0; u < n_units; u++) {
         memset(is16 + u * 576, 0, 576 * sizeof(int16_t));
@@ -61,7 +61,7 @@ void emu_huffman(const uint8_t *main_data, const mp3gpu_unit *units, long long n
         uint32_t pk[8];
         alignas(16) uint32_t out[288 + 4];
         memset(out, 0, sizeof out);
-        uint32_t m = huffman_unit(g_T, g_T.huff_lut, g_T.huff_desc, main_data, units, u, pk, out);
+        uint32_t m = huffman_unit(g_T, g_T.huff_lut, g_T.huff_desc, main_data, main_bits, units, u, pk, out);
         meta[u] = m;
         int c1 = (int)(m & 0x3ff);
         for (int i = 0; i < c1; i++) is16[u * 576 + i] = (int16_t)((out[i >> 1] >> (16 * (i & 1))) & 0xffff);
@@ -170,7 +170,7 @@ int emu_huff_one(int table, const uint8_t *buf, int len_bytes, int *out4) {
     std::vector<uint8_t> padded((size_t)((len_bytes + 3) & ~3) + 64, 0);
     memcpy(padded.data(), buf, (size_t)len_bytes);
     BitCursor bc;
-    bc.init(padded.data(), 0, len_bytes * 8);
+    bc.init(padded.data(), (uint64_t)len_bytes * 8, 0, len_bytes * 8);
     if (table < 32) {
         uint32_t r = huff_pair(g_T.huff_lut, g_T.huff_desc[table], bc);
         out4[0] = (int16_t)(r & 0xffff);

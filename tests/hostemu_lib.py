@@ -15,7 +15,7 @@ def lib():
         subprocess.check_call(["make", "-s", "-C", HERE])
         L = C.CDLL(os.path.join(HERE, "libhostemu.so"))
         vp = C.c_void_p
-        L.emu_huffman.argtypes = [vp, vp, C.c_longlong, vp, vp, vp]
+        L.emu_huffman.argtypes = [vp, C.c_ulonglong, vp, C.c_longlong, vp, vp, vp]
         L.emu_huffman.restype = None
         L.emu_requant.argtypes = [vp, C.c_longlong, vp, vp, vp, vp]
         L.emu_requant.restype = None
@@ -35,7 +35,7 @@ def huffman(main_data: np.ndarray, units: np.ndarray):
     sf = np.zeros((n, 64), np.uint8)
     main_data = np.ascontiguousarray(main_data)
     units = np.ascontiguousarray(units)
-    lib().emu_huffman(main_data.ctypes.data, units.ctypes.data, n, is16.ctypes.data, meta.ctypes.data, sf.ctypes.data)
+    lib().emu_huffman(main_data.ctypes.data, (len(main_data) - 64) * 8, units.ctypes.data, n, is16.ctypes.data, meta.ctypes.data, sf.ctypes.data)
     return is16, meta, sf
 
 

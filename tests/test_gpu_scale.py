@@ -61,3 +61,24 @@ def test_host_and_device_apis_agree(pkg):
     t = g.timings()
     assert t["launches"] == 3 * t["waves"] and t["waves"] >= 2
     g.close()
+
+
+def test_hostile_descriptors_do_not_fault(pkg, classic_lame):
+    """The C ABI is handed descriptors by a host layer; garbage ones (random fields, bit positions outside main_data) must
+    not fault the device.  Afterwards the same engine still decodes a good stream bit-identically."""
+    rng = np.random.default_rng(99)
+    pb = pkg.parse_streams([classic_lame])
+    g = pkg.GpuEngine(0, exact=True)
+    good = g.decode(pb.main_data, pb.main_data_len, pb.units)
+    n = 4096
+    bad = np.zeros(n * 2, dtype=pkg.UNIT_DTYPE)
+    bad["bit_start"] = rng.integers(0, 16 * pb.main_data_len, n * 2, dtype=np.uint64)
+    bad["bit_start"][::7] = np.uint64(2**63)
+    bad["buf_end_rel"] = rng.integers(-5000, 2**31 - 1, n * 2, dtype=np.int64).astype(np.int32)
+    for w in ("w0", "w1", "w2"):
+        bad[w] = rng.integers(0, 2**32, n * 2, dtype=np.uint64).astype(np.uint32)
+    bad["w2"] |= np.uint32(pkg.W2_VALID)
+    out = g.decode(pb.main_data, pb.main_data_len, bad)
+    assert out.shape == (n * 576, 2)
+    assert np.array_equal(g.decode(pb.main_data, pb.main_data_len, pb.units), good)
+    g.close()
