@@ -275,6 +275,7 @@ def run_ours(args, rank, world, local_rank):
     d2h = n_gr * 2304
     del d_pcm
     torch.cuda.empty_cache()
+    numa_node = eng.bind_host_to_gpu_numa_node() if world > 1 else None  # keep each rank's pinned buffers next to its GPU
     try:
         p_main = eng.host_alloc(main_len_e2e + 64)
         p_units = eng.host_alloc(n_gr * 2 * 32)
@@ -300,7 +301,7 @@ def run_ours(args, rank, world, local_rank):
             parity["e2e_max_abs_diff_lsb"] = int(np.abs(got.astype(np.int32) - ref.astype(np.int32)).max())
         e2e = {"value": n_gr * 576 * world / e2e_s / 1e6, "unit": UNIT, "streams_per_gpu": int(e2e_streams), "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-               "api": "mp3gpu_decode (include/mp3gpu.h), pinned host buffers",
+               "api": "mp3gpu_decode (include/mp3gpu.h), pinned host buffers", "numa_node": numa_node,
                "h2d_ms": e2e_t["h2d_ms"], "d2h_ms": e2e_t["d2h_ms"]}
         for p in (p_main, p_units, p_pcm):
             eng.host_free(p)

@@ -205,6 +205,8 @@ def gpu_lib(exact: bool = False) -> C.CDLL:
     L.mp3gpu_debug_read.restype = C.c_int
     L.mp3gpu_device_info.argtypes = [vp, C.c_char_p, sz, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.mp3gpu_device_info.restype = C.c_int
+    L.mp3gpu_device_pci_bus_id.argtypes = [vp, C.c_char_p, sz]
+    L.mp3gpu_device_pci_bus_id.restype = C.c_int
     L.mp3gpu_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.mp3gpu_measure_fp32_peak.restype = C.c_int
     _gpu[exact] = L
@@ -418,6 +420,30 @@ class GpuEngine:
         sm, maj, mnr = C.c_int(), C.c_int(), C.c_int()
         self._check(self.lib.mp3gpu_device_info(self.ctx, name, 256, C.byref(sm), C.byref(maj), C.byref(mnr)))
         return {"name": name.value.decode(), "sm_count": sm.value, "cc": f"{maj.value}.{mnr.value}"}
+
+    def bind_host_to_gpu_numa_node(self):
+        """Pin the calling process to the CPUs of the NUMA node this GPU hangs off, so that pinned buffers allocated
+        afterwards (first touch) and the copies' host side stay local.  Returns the node, or None if unknown."""
+        buf = C.create_string_buffer(64)
+        if self.lib.mp3gpu_device_pci_bus_id(self.ctx, buf, 64) != 0:
+            return None
+        bus = buf.value.decode().lower()
+        try:
+            with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+                node = int(f.read().strip())
+            if node < 0:
+                return None
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                cpus = set()
+                for part in f.read().strip().split(","):
+                    a, _, b = part.partition("-")
+                    cpus.update(range(int(a), int(b or a) + 1))
+            allowed = cpus & os.sched_getaffinity(0)
+            if allowed:
+                os.sched_setaffinity(0, allowed)
+            return node
+        except (OSError, ValueError):
+            return None
 
     def fp32_peak_tflops(self) -> float:
         v = C.c_double()

@@ -631,6 +631,12 @@ extern "C" int mp3gpu_device_info(mp3gpu_ctx *ctx, char *name, size_t name_len, 
     return MP3GPU_OK;
 }
 
+extern "C" int mp3gpu_device_pci_bus_id(mp3gpu_ctx *ctx, char *out, size_t out_len) {
+    if (!ctx || !out || out_len < 16) return MP3GPU_E_INVALID;
+    CK(cudaDeviceGetPCIBusId(out, (int)out_len, ctx->device));
+    return MP3GPU_OK;
+}
+
 extern "C" int mp3gpu_measure_fp32_peak(mp3gpu_ctx *ctx, double *tflops) {
     if (!ctx || !tflops) return MP3GPU_E_INVALID;
     CK(cudaSetDevice(ctx->device));

@@ -180,6 +180,10 @@ int mp3gpu_debug_read(mp3gpu_ctx *ctx, int tap, size_t first_granule, size_t n_g
 /* Device properties, for logs. */
 int mp3gpu_device_info(mp3gpu_ctx *ctx, char *name, size_t name_len, int *sm_count, int *cc_major, int *cc_minor);
 
+/* PCI bus id of the context's device ("0000:1b:00.0"), so a host can place its pinned buffers and threads on the
+ * GPU's NUMA node (/sys/bus/pci/devices/<id>/numa_node). */
+int mp3gpu_device_pci_bus_id(mp3gpu_ctx *ctx, char *out, size_t out_len);
+
 /* Measures the FP32 FMA issue peak of the device with a register-resident FFMA loop (TFLOP/s).
  * Used by bench.py as the fp32 roofline denominator (MEASURED_PEAKS.json has no fp32 entry). */
 int mp3gpu_measure_fp32_peak(mp3gpu_ctx *ctx, double *tflops);
