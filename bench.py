@@ -381,7 +381,7 @@ def run_ours(args, rank, world, local_rank):
                        "granules_per_gpu": int(n_gr), "granule_channels_per_gpu": n_units_valid,
                        "main_data_bytes_per_gpu": int(pb.main_data_len), "pcm_bytes_per_gpu": int(n_gr * 2304),
                        "l2": "inputs (main data + descriptors) and outputs per pass are >> 126 MB L2; no explicit flush",
-                       "parallelism": f"streams sharded over {world} GPU(s), no collective", "wave_granules": args.wave or 262144,
+                       "parallelism": f"streams sharded over {world} GPU(s), no collective", "wave_granules": args.wave or 2097152,
                        "device": info, "setup_s": {"synthesise": t1 - t0, "host_parse": t2 - t1}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches * args.steps), "roofline": roofline,
             "kernels": kernels, "pipeline": pipeline, "cpu_baseline": cpu_baseline, "parity": parity}

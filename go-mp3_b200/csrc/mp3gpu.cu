@@ -199,7 +199,7 @@ extern "C" int mp3gpu_create(int device, const mp3gpu_opts *opts, mp3gpu_ctx **o
     mp3gpu_ctx *ctx = new mp3gpu_ctx();
     ctx->device = device;
     if (opts) ctx->opts = *opts;
-    ctx->wave = ctx->opts.wave_granules ? ctx->opts.wave_granules : 1048576u;
+    ctx->wave = ctx->opts.wave_granules ? ctx->opts.wave_granules : 2097152u;
     auto fail = [&](int rc) {
         fprintf(stderr, "mp3gpu_create: %s\n", ctx->err.c_str());
         mp3gpu_destroy(ctx);
