@@ -1,12 +1,12 @@
 // kernels.cuh — sm_100a device kernels of the MP3 Layer III granule decode path.
 //
-//   K1 k_huffman : scalefactors + Huffman         maindata.go:119-288, maindata/huffman.go:27-138,
-//                                                 huffman.go:348-419, bits.go:45-86
-//   K2 k_requant : requantise, reorder, stereo,   frame.go:140-452
-//                  alias reduction
-//   K3 k_imdct   : IMDCT + window + overlap-add   frame.go:454-486, imdct.go:83-108
-//                  + frequency inversion
-//   K4 k_synth   : polyphase synthesis + int16    frame.go:630-688
+//   k_huffman (K1)    : scalefactors + Huffman            maindata.go:119-288, maindata/huffman.go:27-138,
+//                                                         huffman.go:348-419, bits.go:45-86
+//   k_hybrid  (K2+K3) : requantise, reorder, stereo,      frame.go:140-452
+//                       alias reduction;
+//                       IMDCT + window + overlap-add      frame.go:454-486, imdct.go:83-108
+//                       + frequency inversion
+//   k_synth   (K4)    : polyphase synthesis + int16 store frame.go:630-688
 //
 // Design notes (see DESIGN.md for the full derivation):
 //  * K1 is one THREAD per granule-channel: the code stream of a unit is serial, so the
@@ -49,7 +49,7 @@ __device__ __forceinline__ float mac(float a, float b, float sum) {
 // immediate operand: no constant-cache or shared-memory traffic for coefficients.
 // ------------------------------------------------------------------------------------------
 #include "const_tables.inc"
-__constant__ float c_win[4 * 36];  // per-lane window lookup, only for the rare mixed-flag + start/stop case (Q15)
+__constant__ float c_win[4 * 36];  // IMDCT window rows, indexed by the run-time block type (warp-uniform except quirk Q15)
 
 // Wave-local intermediate buffers.  Index j = local granule (g - wave_first).  k_hybrid looks one
 // granule back (halo) and k_synth 16 time slots, so K1's outputs and hyb have valid look-back slots in
