@@ -187,11 +187,18 @@ MP3_HD uint32_t huff_pair(const uint16_t *lut, uint32_t desc, BitCursor &bc) {
     int x = (int)((e >> 4) & 0xf), y = (int)(e & 0xf);
     int linbits = (int)((desc >> 20) & 0xf);
     if (linbits != 0 && (x == 15 || y == 15)) {
+        // Escape: x-linbits, x-sign, y-linbits, y-sign (huffman.go:405-416) are at most 2 * 13 + 2 = 28 bits, one window.
+        // The reference reads them with Bits(n) / Bit(), which refuse to read (return 0, do not advance) at the end of
+        // the frame's buffer (bits.go:45-77); p is that logical cursor.
         bc.skip(len);
-        if (x == 15) x += bc.bits(linbits);
-        if (x != 0 && bc.bit()) x = -x;
-        if (y == 15) y += bc.bits(linbits);
-        if (y != 0 && bc.bit()) y = -y;
+        const uint32_t v = bc.peek32();
+        const int p0 = bc.pos(), lim = bc.lim;
+        int p = p0;
+        if (x == 15 && p + linbits <= lim) { x += (int)((v << (p - p0)) >> (32 - linbits)); p += linbits; }
+        if (x != 0 && p < lim) { if ((v << (p - p0)) >> 31) x = -x; p++; }
+        if (y == 15 && p + linbits <= lim) { y += (int)((v << (p - p0)) >> (32 - linbits)); p += linbits; }
+        if (y != 0 && p < lim) { if ((v << (p - p0)) >> 31) y = -y; p++; }
+        bc.skip(p - p0);
     } else {
         int nx = x != 0, ny = y != 0;
         uint32_t two = (w << len) >> 30;  // len <= 19: the two bits after the tree bits are inside w
