@@ -379,18 +379,20 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
                         }
                     }
                     if (mode_ext & 1) {
-                        uint8_t *s_isp = reinterpret_cast<uint8_t *>(s_scale[1]);  // channel 1's scale table is no longer needed
+                        // per-band intensity ratios (channel 0's scalefactors); a band that is not intensity coded gets
+                        // (1, 1), and x * 1.0f is x exactly, so the lines need no test
+                        float2 *s_isr = reinterpret_cast<float2 *>(s_scale[1]);  // channel 1's scale table is no longer needed
                         __syncwarp();
-                        if (lane < 22) s_isp[lane] = (uint8_t)intensity_entry(T, cfg, c0, s_pk[0], c1.cnt1, lane);
+                        if (lane < 22) {
+                            const int is_pos = intensity_entry(T, cfg, c0, s_pk[0], c1.cnt1, lane);
+                            s_isr[lane] = is_pos < 7 ? make_float2(T.is_ratio_l[is_pos], T.is_ratio_r[is_pos]) : make_float2(1.0f, 1.0f);
+                        }
                         __syncwarp();
 #pragma unroll
                         for (int q = 0; q < 9; q++) {
-                            const int is_pos = s_isp[sfb_q[q]];
-                            if (is_pos < 7) {
-                                const float rl = T.is_ratio_l[is_pos], rr = T.is_ratio_r[is_pos];
-                                x0[2 * q] = f_mul(x0[2 * q], rl); x1[2 * q] = f_mul(x1[2 * q], rr);
-                                x0[2 * q + 1] = f_mul(x0[2 * q + 1], rl); x1[2 * q + 1] = f_mul(x1[2 * q + 1], rr);
-                            }
+                            const float2 r = s_isr[sfb_q[q]];
+                            x0[2 * q] = f_mul(x0[2 * q], r.x); x1[2 * q] = f_mul(x1[2 * q], r.y);
+                            x0[2 * q + 1] = f_mul(x0[2 * q + 1], r.x); x1[2 * q + 1] = f_mul(x1[2 * q + 1], r.y);
                         }
                     }
                 }
