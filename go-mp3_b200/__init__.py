@@ -519,17 +519,19 @@ class Decoder:
         self.close()
 
     def read(self, n: int) -> Tuple[bytes, int]:
-        """Decoder.Read: returns (bytes, err) with err MP3_OK, MP3_EOF or a fatal code."""
-        buf = C.create_string_buffer(n)
+        """Decoder.Read: returns (bytes, err) with err MP3_OK, MP3_EOF or a fatal code.  Like the reference it hands out at
+        most the rest of one frame per call."""
+        if getattr(self, "_rbuf", None) is None or len(self._rbuf) < n:
+            self._rbuf = C.create_string_buffer(max(n, 8192))
         err = C.c_int(0)
-        got = self.lib.mp3_decoder_read(self.h, buf, n, C.byref(err))
-        return buf.raw[:got], err.value
+        got = self.lib.mp3_decoder_read(self.h, self._rbuf, n, C.byref(err))
+        return C.string_at(self._rbuf, got), err.value
 
     def read_all(self) -> Tuple[bytes, int]:
         """io.ReadAll(d): (bytes, err) with err MP3_OK on clean EOF."""
         chunks = []
         while True:
-            b, err = self.read(1 << 20)
+            b, err = self.read(8192)
             if not b:
                 return b"".join(chunks), (MP3_OK if err == MP3_EOF else err)
             chunks.append(b)
