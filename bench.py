@@ -309,6 +309,22 @@ def run_ours(args, rank, world, local_rank):
         e2e = {"value": None, "unit": UNIT, "error": str(ex)}
     n_gr = full_gr
 
+    # ---- informational: DecodeBatch from raw .mp3 bytes (host parse + gather + device), rank 0 at N = 1 ------------
+    decode_batch = None
+    if rank == 0 and world == 1 and not args.no_decode_batch:
+        try:
+            heng = pkg.Engine(local_rank, host_threads=cores)
+            n_b = min(args.streams, 1024)  # bounded: the first 1,024 streams
+            sub = pkg.StreamBuffer(buf, offs[:n_b], lens[:n_b])
+            heng.decode_batch(sub)            # first call allocates the pinned arenas
+            res_b, pcm_b, tm = heng.decode_batch(sub)
+            decode_batch = {"streams": n_b, "value": tm["pcm_bytes"] / 4 / tm["total_s"] / 1e6, "unit": UNIT,
+                            "parse_s": tm["parse_s"], "gather_s": tm["gather_s"], "device_s": tm["device_s"],
+                            "host_threads": cores, "api": "mp3_decode_batch (include/mp3host.h): raw .mp3 bytes in, PCM out"}
+            heng.close()
+        except Exception as ex:  # informational only
+            decode_batch = {"error": str(ex)}
+
     # ---- CPU baseline (rank 0, N = 1): oracle on all host cores over a bounded sample -----------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -384,7 +400,8 @@ def run_ours(args, rank, world, local_rank):
                        "parallelism": f"streams sharded over {world} GPU(s), no collective", "wave_granules": args.wave or 2097152,
                        "device": info, "setup_s": {"synthesise": t1 - t0, "host_parse": t2 - t1}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches * args.steps), "roofline": roofline,
-            "kernels": kernels, "pipeline": pipeline, "cpu_baseline": cpu_baseline, "parity": parity}
+            "kernels": kernels, "pipeline": pipeline, "cpu_baseline": cpu_baseline, "parity": parity,
+            "decode_batch_from_mp3_bytes": decode_batch}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -401,6 +418,7 @@ def main():
     ap.add_argument("--frames", type=int, default=1149, help="frames per stream (1149 = 30 s at 44.1 kHz)")
     ap.add_argument("--wave", type=int, default=0, help="granules per kernel wave (0 = engine default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decode-batch", action="store_true")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
