@@ -84,13 +84,18 @@ MP3_HD float f_mul(float a, float b) { return __fmul_rn(a, b); }
 MP3_HD float f_add(float a, float b) { return __fadd_rn(a, b); }
 MP3_HD float f_sub(float a, float b) { return __fsub_rn(a, b); }
 MP3_HD float d_mul_to_f(double a, double b) { return __double2float_rn(__dmul_rn(a, b)); }
-MP3_HD uint32_t load_be32(const uint32_t *p) { return __byte_perm(__ldg(p), 0, 0x0123); }
+MP3_HD uint32_t load_raw32(const uint32_t *p) { return __ldg(p); }
+MP3_HD uint32_t be32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+// 0xffffffff >> min(n, 32) with n taken as unsigned: n >= 32 and negative n give 0
+MP3_HD uint32_t ones_shr_clamp(int n) { return __funnelshift_rc(0xffffffffu, 0u, (uint32_t)n); }
 #else
 MP3_HD float f_mul(float a, float b) { volatile float r = a * b; return r; }
 MP3_HD float f_add(float a, float b) { volatile float r = a + b; return r; }
 MP3_HD float f_sub(float a, float b) { volatile float r = a - b; return r; }
 MP3_HD float d_mul_to_f(double a, double b) { volatile double r = a * b; return (float)r; }
-MP3_HD uint32_t load_be32(const uint32_t *p) { return __builtin_bswap32(*p); }
+MP3_HD uint32_t load_raw32(const uint32_t *p) { return *p; }
+MP3_HD uint32_t be32(uint32_t v) { return __builtin_bswap32(v); }
+MP3_HD uint32_t ones_shr_clamp(int n) { return (uint32_t)n >= 32u ? 0u : 0xffffffffu >> n; }
 #endif
 
 // ---- bit cursor with bits.go semantics ----------------------------------------------------------
@@ -103,10 +108,11 @@ MP3_HD uint32_t funnel_l(uint32_t hi, uint32_t lo, int s) { return s ? (hi << s)
 #endif
 
 struct BitCursor {
-    const uint32_t *wp;     // next 32-bit word of main_data to load
-    uint32_t w0, w1;        // current window
+    const uint32_t *wp;     // next 32-bit word of main_data to prefetch
+    uint32_t w0, w1;        // current window (big-endian bit order, masked at the buffer end)
+    uint32_t nxt;           // the word after w1 as loaded (raw byte order, unmasked; 0 when at/after the buffer end)
     int off;                // bit offset of the cursor inside w0 (0..31)
-    int rem;                // bits from the MSB of *wp to the end of the frame's logical buffer (<= 0: past the end)
+    int rem;                // bits from the MSB of the nxt word to the end of the frame's logical buffer (<= 0: past the end)
     int end_rel;            // buf_end_rel
     int lim;                // max(buf_end_rel, 0): the logical position never advances past it (bits.go:46-49)
 
@@ -121,32 +127,38 @@ struct BitCursor {
         rem = off + buf_end_rel;
         end_rel = buf_end_rel;
         lim = buf_end_rel > 0 ? buf_end_rel : 0;
-        w0 = load_word();
-        w1 = load_word();
+        w1 = 0;
+        fetch();
+        shift_in();
+        shift_in();
     }
-    // Next aligned word in big-endian bit order, bits at/after the buffer end forced to zero.
-    MP3_HD uint32_t load_word() {
-        uint32_t w = 0;
-        if (rem > 0) {
-            w = load_be32(wp);
-            if (rem < 32) w &= ~(0xffffffffu >> rem);
-        }
+    // Prefetch: nxt <- the word at wp (raw), or 0 at/after the buffer end.  The load is not consumed before the next
+    // refill, a full word of code bits later, so its latency stays off the decode chain.
+    MP3_HD void fetch() {
+        nxt = 0;
+        if (rem > 0) nxt = load_raw32(wp);
         wp++;
+    }
+    // w0 <- w1, w1 <- nxt in big-endian bit order with the bits at/after the buffer end forced to zero, then prefetch.
+    MP3_HD void shift_in() {
+        w0 = w1;
+        w1 = be32(nxt) & ~ones_shr_clamp(rem);
         rem -= 32;
-        return w;
+        fetch();
     }
     MP3_HD uint32_t peek32() const { return funnel_l(w0, w1, off); }  // next 32 bits, MSB first
     // Logical position relative to bit_start (BitPos() rebased to part2Start).  The window has consumed
-    // end_rel - 64 - rem + off bits since init (rem drops by 32 per loaded word); the reference's cursor is that,
-    // clamped at the buffer end: Bit() past the end returns 0 without advancing, and a refused Bits(n) moves neither.
+    // end_rel - 64 - rem + off bits since init (rem drops by 32 per word shifted in, two of them in init); the
+    // reference's cursor is that, clamped at the buffer end: Bit() past the end returns 0 without advancing, and a
+    // refused Bits(n) moves neither.
     MP3_HD int pos() const { return imin(end_rel - 64 - rem + off, lim); }
-    // Bit()-style consumption of n <= 32 bits (tree bits, sign bits).
+    // Bit()-style consumption of n <= 32 bits (tree bits, sign bits).  Written without a branch: lanes of a warp refill
+    // at different code words, and a divergent refill branch cost more issue slots than the predicated form.
     MP3_HD void skip(int n) {
         off += n;
         if (off >= 32) {
             off -= 32;
-            w0 = w1;
-            w1 = load_word();
+            shift_in();
         }
     }
     // Bits(n), bits.go:58-77: returns 0 WITHOUT advancing when the read would cross the end.
