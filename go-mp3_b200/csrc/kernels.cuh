@@ -78,12 +78,14 @@ constexpr int kHuffThreads = 256;
 __global__ void __launch_bounds__(kHuffThreads)
 k_huffman(const uint8_t *__restrict__ main_data, unsigned long long main_bits, const mp3gpu_unit *__restrict__ units,
           long long first_unit, int n_units, DeviceTables T, WaveBufs B) {
-    extern __shared__ uint16_t s_lut[];
+    extern __shared__ uint32_t s_lut[];
+    __shared__ uint64_t s_quad[256];
     __shared__ uint32_t s_desc[34];
     __shared__ unsigned int s_bin[40];
     __shared__ uint16_t s_order[kHuffThreads];
     for (int i = threadIdx.x; i < T.huff_lut_n; i += blockDim.x) s_lut[i] = T.huff_lut[i];
     if (threadIdx.x < 34) s_desc[threadIdx.x] = T.huff_desc[threadIdx.x];
+    s_quad[threadIdx.x] = T.quad_signs[threadIdx.x];  // kHuffThreads == 256
     if (threadIdx.x < 40) s_bin[threadIdx.x] = 0;
     __syncthreads();
     // ---- work order inside the CTA ----------------------------------------------------------------
@@ -114,7 +116,7 @@ k_huffman(const uint8_t *__restrict__ main_data, unsigned long long main_bits, c
     }
     uint32_t pk[8];
     uint32_t *out = reinterpret_cast<uint32_t *>(B.is16 + (size_t)ul * 576);
-    uint32_t meta = huffman_unit(T, s_lut, s_desc, main_data, main_bits, units, first_unit + ul, pk, out);
+    uint32_t meta = huffman_unit(T, s_lut, s_desc, s_quad, main_data, main_bits, units, first_unit + ul, pk, out);
     uint4 *dst = reinterpret_cast<uint4 *>(B.sfpack + (size_t)ul * 8);
     dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);

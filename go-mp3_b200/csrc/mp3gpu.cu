@@ -152,7 +152,8 @@ static int upload_tables(mp3gpu_ctx *ctx) {
     size_t o_sl = put(h.sfb_long, sizeof h.sfb_long);
     size_t o_ss = put(h.sfb_short, sizeof h.sfb_short);
     size_t o_ns = put(h.nslen2, sizeof h.nslen2);
-    size_t o_lut = put(h.huff_lut.data(), h.huff_lut.size() * sizeof(uint16_t));
+    size_t o_lut = put(h.huff_lut.data(), h.huff_lut.size() * sizeof(uint32_t));
+    size_t o_qs = put(h.quad_signs, sizeof h.quad_signs);
     size_t o_rl = put(h.is_ratio_l, sizeof h.is_ratio_l);
     size_t o_rr = put(h.is_ratio_r, sizeof h.is_ratio_r);
     size_t o_pt = put(h.pretab, sizeof h.pretab);
@@ -176,7 +177,8 @@ static int upload_tables(mp3gpu_ctx *ctx) {
     ctx->T.sfb_long = (const uint16_t *)(b + o_sl);
     ctx->T.sfb_short = (const uint16_t *)(b + o_ss);
     ctx->T.nslen2 = (const uint16_t *)(b + o_ns);
-    ctx->T.huff_lut = (const uint16_t *)(b + o_lut);
+    ctx->T.huff_lut = (const uint32_t *)(b + o_lut);
+    ctx->T.quad_signs = (const uint64_t *)(b + o_qs);
     ctx->T.is_ratio_l = (const float *)(b + o_rl);
     ctx->T.is_ratio_r = (const float *)(b + o_rr);
     ctx->T.pretab = b + o_pt;
@@ -187,7 +189,7 @@ static int upload_tables(mp3gpu_ctx *ctx) {
     ctx->T.ca = (const float *)(b + o_ca);
     ctx->T.huff_lut_n = (int)h.huff_lut.size();
     ctx->T.pow2_off = kPow2Off;
-    ctx->lut_bytes = (int)(h.huff_lut.size() * sizeof(uint16_t));
+    ctx->lut_bytes = (int)(h.huff_lut.size() * sizeof(uint32_t));
     return MP3GPU_OK;
 }
 

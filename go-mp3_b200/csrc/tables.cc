@@ -42,12 +42,36 @@ const int kSfSizeMpeg2[3][6][4] = {
 const long double kPiL = 3.14159265358979323846264338327950288L;
 
 // ---- Huffman LUT construction ------------------------------------------------
+// Entry formats: tables.h.  `pairs` trees carry (x, y); the two count1 trees carry the 4-bit (v w x y) pattern in the
+// x field.  `esc` marks x == 15 or y == 15 in the two trees every linbits table shares.
 struct LutBuilder {
-    std::vector<uint16_t> &lut;
+    std::vector<uint32_t> &lut;
     size_t base;
     const huff_code_t *codes;
     int n;
-    explicit LutBuilder(std::vector<uint16_t> &l, const huff_code_t *c, int n_) : lut(l), base(l.size()), codes(c), n(n_) {}
+    bool quad, esc_tree;
+    LutBuilder(std::vector<uint32_t> &l, const huff_code_t *c, int n_, bool quad_, bool esc_tree_)
+        : lut(l), base(l.size()), codes(c), n(n_), quad(quad_), esc_tree(esc_tree_) {}
+
+    uint32_t leaf(const huff_code_t &c) const {
+        const int x = c.x, y = c.y, tlen = c.hlen;
+        int signs;
+        uint32_t e;
+        if (quad) {
+            const int q = y & 0xf;  // count1 tables are stored as (x = 0, y = v<<3 | w<<2 | x<<1 | y)
+            signs = ((q >> 3) & 1) + ((q >> 2) & 1) + ((q >> 1) & 1) + (q & 1);
+            e = (uint32_t)q;
+        } else {
+            signs = (x != 0) + (y != 0);
+            e = (uint32_t)x | ((uint32_t)y << 8);
+            if (esc_tree && (x == 15 || y == 15)) e |= 1u << 4;
+        }
+        const int total = tlen + signs;
+        e |= (uint32_t)tlen << 16;
+        e |= (uint32_t)((total - 1) & 31) << 21;
+        e |= (uint32_t)total << 26;
+        return e;
+    }
 
     // Fill a table of `bits` index bits for all codes whose first `plen` bits equal `prefix`.
     void fill(size_t off, int bits, uint32_t prefix, int plen, int sub_cap) {
@@ -61,7 +85,7 @@ struct LutBuilder {
                 if ((full >> (plen + bits - L)) == codes[i].hcod) { found = i; break; }
             }
             if (found >= 0) {
-                lut[base + off + idx] = (uint16_t)((codes[found].hlen << 8) | (codes[found].x << 4) | codes[found].y);
+                lut[base + off + idx] = leaf(codes[found]);
                 continue;
             }
             // Need a sub-table: longest remaining length among codes with this (plen+bits)-bit prefix.
@@ -75,9 +99,9 @@ struct LutBuilder {
             if (maxrem == 0) throw std::runtime_error("huffman tree not complete");
             int sb = std::min(maxrem, sub_cap);
             size_t sub_off = lut.size() - base;
-            if (sub_off > 0xfff) throw std::runtime_error("huffman LUT too large");
+            if (sub_off > 0xffff) throw std::runtime_error("huffman LUT too large");
             lut.resize(lut.size() + (1u << sb), 0);
-            lut[base + off + idx] = (uint16_t)(0x8000u | ((uint32_t)(sb - 1) << 12) | (uint32_t)sub_off);
+            lut[base + off + idx] = 0x80000000u | ((uint32_t)sb << 16) | (uint32_t)sub_off;
             fill(sub_off, sb, full, plen + bits, sub_cap);
         }
     }
@@ -200,12 +224,12 @@ void build_host_tables(HostTables &t) {
         for (int j = 0; j < 5; j++)
             for (int k = 0; k < 4; k++) t.nslen2[k + j * 4 + i * 20 + 400] = (uint16_t)(i | (j << 3) | (k << 6) | (1 << 12));
 
-    // Huffman LUTs: one per distinct tree; tables sharing a tree share the LUT.
+    // Huffman LUTs: one per distinct tree; tables sharing a tree share the LUT.  Every root table is indexed by the
+    // same kHuffRootBits bits, so the kernel's root lookup needs no per-table shift.
     t.huff_lut.clear();
-    // entry 0..1: the "empty table" LUT (root bits 1, two zero-length zero leaves)
-    t.huff_lut.push_back(0);
-    t.huff_lut.push_back(0);
-    const uint32_t empty_desc = 0u | (1u << 16);
+    // entries 0..2^root-1: the "empty table" LUT (zero-length zero leaves: total = 0, x = y = 0)
+    t.huff_lut.resize((size_t)1 << kHuffRootBits, (uint32_t)(31u << 21));
+    const uint32_t empty_desc = 0u;
     const huff_code_t *seen[34];
     uint32_t seen_desc[34];
     int nseen = 0;
@@ -220,20 +244,33 @@ void build_host_tables(HostTables &t) {
         for (int s = 0; s < nseen; s++)
             if (seen[s] == d.codes) { desc = seen_desc[s]; have = true; }
         if (!have) {
-            int maxlen = 0;
-            for (int i = 0; i < d.n; i++) maxlen = std::max(maxlen, (int)d.codes[i].hlen);
-            int root = std::min(maxlen, 8);
-            LutBuilder b(t.huff_lut, d.codes, d.n);
-            if (b.base > 0xffff) throw std::runtime_error("huffman LUT base overflow");
-            t.huff_lut.resize(t.huff_lut.size() + (1u << root), 0);
-            b.fill(0, root, 0, 0, 6);
-            desc = (uint32_t)b.base | ((uint32_t)root << 16);
+            LutBuilder b(t.huff_lut, d.codes, d.n, tab >= 32, d.linbits != 0);
+            if (b.base * 4 > 0xffffff) throw std::runtime_error("huffman LUT base overflow");
+            t.huff_lut.resize(t.huff_lut.size() + ((size_t)1 << kHuffRootBits), 0);
+            b.fill(0, kHuffRootBits, 0, 0, 6);
+            desc = (uint32_t)b.base * 4u;
             seen[nseen] = d.codes;
             seen_desc[nseen] = desc;
             nseen++;
         }
-        t.huff_desc[tab] = desc | ((uint32_t)d.linbits << 20);
+        t.huff_desc[tab] = desc | ((uint32_t)d.linbits << 24);
     }
+    // count1 sign expansion: index = pattern << 4 | the four bits after the tree bits; value = the two output words
+    // (v | w << 16) and (x | y << 16) << 32 with the sign bits dealt to the non-zero values in order (huffman.go:387-403)
+    for (int q = 0; q < 16; q++)
+        for (int four = 0; four < 16; four++) {
+            int val[4], used = 0;
+            for (int i = 0; i < 4; i++) {
+                val[i] = (q >> (3 - i)) & 1;
+                if (val[i]) {
+                    if ((four >> (3 - used)) & 1) val[i] = -1;
+                    used++;
+                }
+            }
+            const uint64_t vw = ((uint32_t)val[0] & 0xffffu) | ((uint32_t)val[1] << 16);
+            const uint64_t xy = ((uint32_t)val[2] & 0xffffu) | ((uint32_t)val[3] << 16);
+            t.quad_signs[q * 16 + four] = vw | (xy << 32);
+        }
 }
 
 }  // namespace mp3gpu

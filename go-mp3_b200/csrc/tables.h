@@ -19,13 +19,18 @@ constexpr int kPow2Off = 336;   // pow2q index = 4*idx + kPow2Off ; 4*idx in [-3
 constexpr int kPow2N = 400;
 constexpr int kNumCfg = 6;      // cfg = lsf*3 + sampling_frequency index
 
-// Huffman LUT entry (uint16):
-//   leaf : bit15 = 0, bits 8..12 = total code length (0..19), bits 4..7 = x, bits 0..3 = y
-//   link : bit15 = 1, bits 12..14 = (sub-table index bits - 1), bits 0..11 = sub-table offset
-//          relative to the tree's base
-// Table descriptor (uint32): bits 0..15 = LUT base offset, bits 16..19 = root index bits,
-// bits 20..23 = linbits.  Tables 0/4/14 (empty: huffman.go:354-356) map to a 2-entry
-// all-zero leaf table of length 0 so that they consume nothing.
+// Huffman LUT entry (uint32).  Every tree's root table is indexed by the first kHuffRootBits bits of the code stream.
+//   leaf : bit31 = 0
+//          bits 0..3   x (pairs) / the (v w x y) pattern (count1 trees)
+//          bit  4      escape: x == 15 or y == 15 in a tree used with linbits (tables 16..31)
+//          bits 8..11  y
+//          bits 16..20 tree bits of the code word
+//          bits 21..25 (total - 1) & 31      \  total = tree bits + sign bits that follow when no escape is taken;
+//          bits 26..30 total                 /  the first two fields are used as (mod 32) shift counts
+//   link : bit31 = 1, bits 16..20 = sub-table index bits, bits 0..15 = sub-table offset (entries) from the tree's base
+// Table descriptor (uint32): bits 0..23 = byte offset of the tree's root table in the LUT, bits 24..27 = linbits.
+// Tables 0/4/14 (empty: huffman.go:354-356) map to a root table of zero-length zero leaves: they consume nothing.
+constexpr int kHuffRootBits = 8;
 struct HostTables {
     float cos36[18 * 36];
     float cos12[6 * 12];
@@ -48,7 +53,8 @@ struct HostTables {
     uint16_t pair_dst[kNumCfg][288];
     uint16_t nslen2[512];
     uint8_t sfsize_mpeg2[3][6][4];
-    std::vector<uint16_t> huff_lut;
+    std::vector<uint32_t> huff_lut;
+    uint64_t quad_signs[256];       // count1 sign expansion, see tables.cc
     uint32_t huff_desc[34];
 };
 

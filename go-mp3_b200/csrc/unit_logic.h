@@ -38,8 +38,9 @@ struct DeviceTables {
     const uint16_t *sfb_long;       // [6][24]
     const uint16_t *sfb_short;      // [6][16]
     const uint16_t *nslen2;         // [512]
-    const uint16_t *huff_lut;       // LUT entries (see tables.h)
+    const uint32_t *huff_lut;       // LUT entries (see tables.h)
     const uint32_t *huff_desc;      // [34]
+    const uint64_t *quad_signs;     // [256] count1 sign expansion
     const float *is_ratio_l;        // [8]
     const float *is_ratio_r;        // [8]
     const uint8_t *pretab;          // [24]
@@ -104,7 +105,7 @@ MP3_HD uint32_t ones_shr_clamp(int n) { return (uint32_t)n >= 32u ? 0u : 0xfffff
 #if defined(__CUDA_ARCH__)
 MP3_HD uint32_t funnel_l(uint32_t hi, uint32_t lo, int s) { return __funnelshift_l(lo, hi, s); }  // (hi:lo << s) >> 32, s in 0..31
 #else
-MP3_HD uint32_t funnel_l(uint32_t hi, uint32_t lo, int s) { return s ? (hi << s) | (lo >> (32 - s)) : hi; }
+MP3_HD uint32_t funnel_l(uint32_t hi, uint32_t lo, int s) { s &= 31; return s ? (hi << s) | (lo >> (32 - s)) : hi; }
 #endif
 
 struct BitCursor {
@@ -176,33 +177,39 @@ struct BitCursor {
     }
 };
 
-// Leaf entry of the code word at the head of w (MSB first); *len receives the tree bits.
-MP3_HD uint32_t huff_lookup(const uint16_t *lut, uint32_t desc, uint32_t w) {
-    uint32_t base = desc & 0xffff;
-    int rb = (int)((desc >> 16) & 0xf);
-    uint32_t e = lut[base + (w >> (32 - rb))];
-    int used = rb;
-    while (e & 0x8000u) {  // rare: code longer than the root index
-        int sb = (int)((e >> 12) & 7) + 1;
-        uint32_t idx = (e & 0xfff) + ((w << used) >> (32 - sb));
-        e = lut[base + idx];
+// ---- Huffman code words (LUT entry layout: tables.h) -------------------------------------------------------------
+constexpr int kRootBits = 8;  // == tables.h kHuffRootBits
+MP3_HD uint32_t lut_at(const uint32_t *lut, uint32_t byte_off) {
+    return *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(lut) + byte_off);
+}
+// Leaf entry of the code word at the head of w (MSB first); d = byte offset of the tree's root table.
+MP3_HD uint32_t huff_lookup(const uint32_t *lut, uint32_t d, uint32_t w) {
+    uint32_t e = lut_at(lut, d + ((w >> (32 - kRootBits)) << 2));
+    int used = kRootBits;
+    while ((int32_t)e < 0) {  // rare: code longer than the root index
+        const int sb = (int)((e >> 16) & 0x1f);
+        const uint32_t idx = (e & 0xffff) + ((w << used) >> (32 - sb));
+        e = lut_at(lut, d + (idx << 2));
         used += sb;
     }
     return e;
 }
+// x << (n mod 32): the LUT's shift-count fields are used without masking their neighbours off
+MP3_HD uint32_t shl_mod32(uint32_t x, uint32_t n) { return funnel_l(x, 0u, (int)(n & 31)); }
 
-// One big_values pair (huffman.go:404-416).  Returns x | y<<16 (int16 halves).
-MP3_HD uint32_t huff_pair(const uint16_t *lut, uint32_t desc, BitCursor &bc) {
+// One big_values pair (huffman.go:404-416).  Returns x | y<<16 (int16 halves).  linbits() is only evaluated for an
+// escape (x or y == 15 in a table with linbits).
+template <class LinbitsFn>
+MP3_HD uint32_t huff_pair(const uint32_t *lut, uint32_t d, LinbitsFn linbits_of, BitCursor &bc) {
     const uint32_t w = bc.peek32();
-    uint32_t e = huff_lookup(lut, desc, w);
-    int len = (int)((e >> 8) & 0x1f);
-    int x = (int)((e >> 4) & 0xf), y = (int)(e & 0xf);
-    int linbits = (int)((desc >> 20) & 0xf);
-    if (linbits != 0 && (x == 15 || y == 15)) {
+    const uint32_t e = huff_lookup(lut, d, w);
+    int x = (int)(e & 0xf), y = (int)((e >> 8) & 0xf);
+    if (e & 0x10u) {
         // Escape: x-linbits, x-sign, y-linbits, y-sign (huffman.go:405-416) are at most 2 * 13 + 2 = 28 bits, one window.
         // The reference reads them with Bits(n) / Bit(), which refuse to read (return 0, do not advance) at the end of
         // the frame's buffer (bits.go:45-77); p is that logical cursor.
-        bc.skip(len);
+        const int linbits = linbits_of();
+        bc.skip((int)((e >> 16) & 0x1f));
         const uint32_t v = bc.peek32();
         const int p0 = bc.pos(), lim = bc.lim;
         int p = p0;
@@ -212,33 +219,27 @@ MP3_HD uint32_t huff_pair(const uint16_t *lut, uint32_t desc, BitCursor &bc) {
         if (y != 0 && p < lim) { if ((v << (p - p0)) >> 31) y = -y; p++; }
         bc.skip(p - p0);
     } else {
-        int nx = x != 0, ny = y != 0;
-        uint32_t two = (w << len) >> 30;  // len <= 19: the two bits after the tree bits are inside w
-        int sx = nx ? (int)(two >> 1) : 0;
-        int sy = ny ? (int)((nx ? two : (two >> 1)) & 1) : 0;
-        bc.skip(len + nx + ny);
-        x = sx ? -x : x;
-        y = sy ? -y : y;
+        // x's sign bit (if x != 0) follows the tree bits, y's (if y != 0) is the last of the `total` bits; the tree is
+        // at most 19 bits, so both lie inside w.  A zero value ignores the mask it gets: (0 ^ m) - m == 0.
+        const int mx = (int32_t)shl_mod32(w, e >> 16) >> 31;
+        const int my = (int32_t)shl_mod32(w, e >> 21) >> 31;
+        x = (x ^ mx) - mx;
+        y = (y ^ my) - my;
+        bc.skip((int)(e >> 26));
     }
     return ((uint32_t)x & 0xffffu) | ((uint32_t)y << 16);
 }
 
 // One count1 quadruple (huffman.go:387-403): v, w, x, y each in {-1, 0, 1}; returns (v | w<<16), (x | y<<16).
-MP3_HD void huff_quad(const uint16_t *lut, uint32_t desc, BitCursor &bc, uint32_t &vw, uint32_t &xy) {
+// quad_signs[pattern << 4 | next four bits] holds both words with the sign bits dealt out (tables.cc).
+MP3_HD void huff_quad(const uint32_t *lut, const uint64_t *quad_signs, uint32_t d, BitCursor &bc, uint32_t &vw, uint32_t &xy) {
     const uint32_t wd = bc.peek32();
-    uint32_t e = huff_lookup(lut, desc, wd);
-    int len = (int)((e >> 8) & 0x1f);  // <= 6 tree bits, then up to 4 sign bits
-    int q = (int)(e & 0xf);
-    int v = (q >> 3) & 1, w = (q >> 2) & 1, x = (q >> 1) & 1, y = q & 1;
-    uint32_t four = (wd << len) >> 28;
-    int used = 0;
-    if (v) { if ((four >> (3 - used)) & 1) v = -1; used++; }
-    if (w) { if ((four >> (3 - used)) & 1) w = -1; used++; }
-    if (x) { if ((four >> (3 - used)) & 1) x = -1; used++; }
-    if (y) { if ((four >> (3 - used)) & 1) y = -1; used++; }
-    bc.skip(len + used);
-    vw = ((uint32_t)v & 0xffffu) | ((uint32_t)w << 16);
-    xy = ((uint32_t)x & 0xffffu) | ((uint32_t)y << 16);
+    const uint32_t e = huff_lookup(lut, d, wd);                   // <= 6 tree bits, then up to 4 sign bits
+    const uint32_t four = shl_mod32(wd, e >> 16) >> 28;
+    const uint64_t r = quad_signs[((e & 0xf) << 4) | four];
+    bc.skip((int)(e >> 26));
+    vw = (uint32_t)r;
+    xy = (uint32_t)(r >> 32);
 }
 
 // Collects decoded line pairs and writes them 16 bytes at a time: units sit 1,152 bytes apart, so every lane of a
@@ -288,7 +289,7 @@ MP3_HD void sf_mpeg1_read_all(const DeviceTables &T, BitCursor &bc, uint32_t w0,
 // scfsi set re-reads gr 0's scalefactor bits (maindata.go:239-278, quirk Q14).
 // Outputs: pk[8] scalefactor nibbles (n = sfb for scalefac_l, 22 + sfb*3 + win for scalefac_s),
 // is_out[0..count1/2) packed int16 pairs, return value meta = count1 | preflag << 10.
-MP3_HD uint32_t huffman_unit(const DeviceTables &T, const uint16_t *lut, const uint32_t *huff_desc,
+MP3_HD uint32_t huffman_unit(const DeviceTables &T, const uint32_t *lut, const uint32_t *huff_desc, const uint64_t *quad_signs,
                              const uint8_t *main_data, uint64_t main_bits, const mp3gpu_unit *units, long long unit_index,
                              uint32_t *pk, uint32_t *is_out) {
     const mp3gpu_unit u = units[unit_index];
@@ -368,28 +369,33 @@ MP3_HD uint32_t huffman_unit(const DeviceTables &T, const uint16_t *lut, const u
     }
     int nbig = u_bigval(w0);
     if (nbig > 288) nbig = 288;  // the host rejects such frames (huffman.go:68-70); never reached
-    const uint32_t d0 = huff_desc[u_tsel(w1, 0)], d1 = huff_desc[u_tsel(w1, 1)], d2 = huff_desc[u_tsel(w1, 2)];
+    const uint32_t e0 = huff_desc[u_tsel(w1, 0)], e1 = huff_desc[u_tsel(w1, 1)], e2 = huff_desc[u_tsel(w1, 2)];
+    const uint32_t d0 = e0 & 0xffffffu, d1 = e1 & 0xffffffu, d2 = e2 & 0xffffffu;  // root table byte offsets per region
+    auto pair_at = [&](int kk) {
+        const bool in0 = kk < r1h, in1 = kk < r2h;
+        return huff_pair(lut, in0 ? d0 : (in1 ? d1 : d2), [&] { return (int)((in0 ? e0 : (in1 ? e1 : e2)) >> 24); }, bc);
+    };
     int k = 0;
     {   // four pairs per 16-byte store
         uint4 *dst4 = reinterpret_cast<uint4 *>(is_out);
         for (; k + 4 <= nbig; k += 4) {
             uint4 v;
-            v.x = huff_pair(lut, k < r1h ? d0 : (k < r2h ? d1 : d2), bc);
-            v.y = huff_pair(lut, k + 1 < r1h ? d0 : (k + 1 < r2h ? d1 : d2), bc);
-            v.z = huff_pair(lut, k + 2 < r1h ? d0 : (k + 2 < r2h ? d1 : d2), bc);
-            v.w = huff_pair(lut, k + 3 < r1h ? d0 : (k + 3 < r2h ? d1 : d2), bc);
+            v.x = pair_at(k);
+            v.y = pair_at(k + 1);
+            v.z = pair_at(k + 2);
+            v.w = pair_at(k + 3);
             dst4[k >> 2] = v;
         }
     }
     PairSink sink;
     sink.init(is_out, k);
-    for (; k < nbig; k++) sink.put(huff_pair(lut, k < r1h ? d0 : (k < r2h ? d1 : d2), bc));
+    for (; k < nbig; k++) sink.put(pair_at(k));
     int is_pos = nbig * 2;
     {
-        uint32_t dq = huff_desc[32 + u_c1tsel(w2)];
+        const uint32_t dq = huff_desc[32 + u_c1tsel(w2)] & 0xffffffu;
         while (is_pos <= 572 && bc.pos() <= bit_pos_end) {
             uint32_t vw, xy;
-            huff_quad(lut, dq, bc, vw, xy);
+            huff_quad(lut, quad_signs, dq, bc, vw, xy);
             sink.put(vw);
             sink.put(xy);
             is_pos += 4;

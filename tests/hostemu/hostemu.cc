@@ -35,6 +35,7 @@ void ensure() {
     g_T.nslen2 = h.nslen2;
     g_T.huff_lut = h.huff_lut.data();
     g_T.huff_desc = h.huff_desc;
+    g_T.quad_signs = h.quad_signs;
     g_T.is_ratio_l = h.is_ratio_l;
     g_T.is_ratio_r = h.is_ratio_r;
     g_T.pretab = h.pretab;
@@ -61,7 +62,7 @@ void emu_huffman(const uint8_t *main_data, unsigned long long main_bits, const m
         uint32_t pk[8];
         alignas(16) uint32_t out[288 + 4];
         memset(out, 0, sizeof out);
-        uint32_t m = huffman_unit(g_T, g_T.huff_lut, g_T.huff_desc, main_data, main_bits, units, u, pk, out);
+        uint32_t m = huffman_unit(g_T, g_T.huff_lut, g_T.huff_desc, g_T.quad_signs, main_data, main_bits, units, u, pk, out);
         meta[u] = m;
         int c1 = (int)(m & 0x3ff);
         for (int i = 0; i < c1; i++) is16[u * 576 + i] = (int16_t)((out[i >> 1] >> (16 * (i & 1))) & 0xffff);
@@ -172,13 +173,14 @@ int emu_huff_one(int table, const uint8_t *buf, int len_bytes, int *out4) {
     BitCursor bc;
     bc.init(padded.data(), (uint64_t)len_bytes * 8, 0, len_bytes * 8);
     if (table < 32) {
-        uint32_t r = huff_pair(g_T.huff_lut, g_T.huff_desc[table], bc);
+        const uint32_t desc = g_T.huff_desc[table];
+        uint32_t r = huff_pair(g_T.huff_lut, desc & 0xffffffu, [&] { return (int)(desc >> 24); }, bc);
         out4[0] = (int16_t)(r & 0xffff);
         out4[1] = (int16_t)(r >> 16);
         out4[2] = out4[3] = 0;
     } else {
         uint32_t vw, xy;
-        huff_quad(g_T.huff_lut, g_T.huff_desc[table], bc, vw, xy);
+        huff_quad(g_T.huff_lut, g_T.quad_signs, g_T.huff_desc[table] & 0xffffffu, bc, vw, xy);
         out4[0] = (int16_t)(xy & 0xffff); out4[1] = (int16_t)(xy >> 16);
         out4[2] = (int16_t)(vw & 0xffff); out4[3] = (int16_t)(vw >> 16);
     }
