@@ -580,6 +580,36 @@ __device__ __forceinline__ void matrix_rows(const float (&s)[32], float *urow, i
     }
 }
 
+#if !MP3GPU_EXACT
+// Fast build: the 64 x 32 matrixing is a 32-point DCT-II, V[i] = +-c[n] with c[n] = sum_j s[j] cos(n (2j+1) pi / 64),
+// computed by Lee's recursion (80 multiplies + 209 adds instead of 1,056 multiply-adds): split into the symmetric and
+// the antisymmetric half, the latter scaled by 1 / (2 cos), two half-size DCTs, odd outputs W[k] + W[k+1].  The result
+// differs from the reference's direct summation by float32 rounding only; the PCM stays within +-1 LSB with the same
+// exact-match fraction as fused multiply-add alone gives (tests/test_gpu_*.py state both).  The exact build keeps the
+// direct form below and is bit-identical to the reference.
+template <int N, int LVL>
+__device__ __forceinline__ void lee_dct(const float (&x)[N], float (&X)[N]) {
+    if constexpr (N == 1) {
+        X[0] = x[0];
+    } else {
+        constexpr int H = N / 2;
+        float u[H], v[H], E[H], W[H];
+#pragma unroll
+        for (int n = 0; n < H; n++) {
+            u[n] = x[n] + x[N - 1 - n];
+            v[n] = (x[n] - x[N - 1 - n]) * kLeeSec[LVL][n];
+        }
+        lee_dct<H, LVL + 1>(u, E);
+        lee_dct<H, LVL + 1>(v, W);
+#pragma unroll
+        for (int k = 0; k < H; k++) {
+            X[2 * k] = E[k];
+            X[2 * k + 1] = k < H - 1 ? W[k] + W[k + 1] : W[H - 1];
+        }
+    }
+}
+#endif
+
 __device__ __forceinline__ void matrix_slot(const float *__restrict__ src, float *urow) {
     float s[32];
 #pragma unroll
@@ -587,11 +617,29 @@ __device__ __forceinline__ void matrix_slot(const float *__restrict__ src, float
         const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + q);
         s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
     }
+#if MP3GPU_EXACT
     // rows 0..16 -> U[0..16]; rows 33..48 -> U[17..32]
     matrix_rows<0, 4>(s, urow, 0);   matrix_rows<4, 4>(s, urow, 4);   matrix_rows<8, 4>(s, urow, 8);
     matrix_rows<12, 4>(s, urow, 12); matrix_rows<16, 1>(s, urow, 16);
     matrix_rows<33, 3>(s, urow, 17); matrix_rows<36, 4>(s, urow, 20); matrix_rows<40, 4>(s, urow, 24);
     matrix_rows<44, 4>(s, urow, 28); matrix_rows<48, 1>(s, urow, 32);
+#else
+    // V[0..15] = c[16..31], V[16] = c[32] = 0 (the reference's row 16 is float32(cos(odd * pi/2)) ~ 1e-17 times the
+    // samples: below half an ulp of any sum it joins), V[33 + m] = -c[15 - m], V[48] = -c[0].  Stored without the
+    // signs: U[17..32] = c[15..0]; phase B folds the minus into its window coefficients.
+    float c[32];
+    lee_dct<32, 0>(s, c);
+    float4 *u4 = reinterpret_cast<float4 *>(urow);
+    u4[0] = make_float4(c[16], c[17], c[18], c[19]);
+    u4[1] = make_float4(c[20], c[21], c[22], c[23]);
+    u4[2] = make_float4(c[24], c[25], c[26], c[27]);
+    u4[3] = make_float4(c[28], c[29], c[30], c[31]);
+    u4[4] = make_float4(0.0f, c[15], c[14], c[13]);
+    u4[5] = make_float4(c[12], c[11], c[10], c[9]);
+    u4[6] = make_float4(c[8], c[7], c[6], c[5]);
+    u4[7] = make_float4(c[4], c[3], c[2], c[1]);
+    urow[32] = c[0];
+#endif
 }
 
 template <int P>
@@ -692,7 +740,11 @@ k_synth(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_gr
     SynLane L;
     L.ai = lane <= 16 ? lane : 32 - lane;
     L.bi = lane == 0 ? 0 : (lane <= 16 ? 16 + lane : 48 - lane);
+#if MP3GPU_EXACT
     const float sa = lane <= 16 ? 1.0f : -1.0f, sb = lane == 0 ? -1.0f : 1.0f;
+#else
+    const float sa = lane <= 16 ? 1.0f : -1.0f, sb = -1.0f;  // U[17..32] hold +c[15..0] (matrix_slot): V[32+i] = -U[bi] for every lane
+#endif
     float dw[16];
 #pragma unroll
     for (int d = 0; d < 16; d++) dw[d] = __ldg(B.synth_d + 32 * d + lane) * ((d & 1) ? sb : sa);

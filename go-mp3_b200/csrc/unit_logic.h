@@ -285,13 +285,52 @@ MP3_HD void sf_mpeg1_read_all(const DeviceTables &T, BitCursor &bc, uint32_t w0,
     }
 }
 
-// K1 body for one unit.  `units` is the whole submission (absolute indexing): a gr-1 unit with
-// scfsi set re-reads gr 0's scalefactor bits (maindata.go:239-278, quirk Q14).
-// Outputs: pk[8] scalefactor nibbles (n = sfb for scalefac_l, 22 + sfb*3 + win for scalefac_s),
-// is_out[0..count1/2) packed int16 pairs, return value meta = count1 | preflag << 10.
-MP3_HD uint32_t huffman_unit(const DeviceTables &T, const uint32_t *lut, const uint32_t *huff_desc, const uint64_t *quad_signs,
-                             const uint8_t *main_data, uint64_t main_bits, const mp3gpu_unit *units, long long unit_index,
-                             uint32_t *pk, uint32_t *is_out) {
+// K1 for one unit, in two stages so that a CTA can re-deal its units to threads in between (kernels.cuh):
+//   stage A  scalefactors + the big_values pairs in whole groups of four   (cost ~ big_values)
+//   stage B  the last big_values % 4 pairs + the count1 quadruples         (cost ~ bits left in part 3)
+// `units` is the whole submission (absolute indexing): a gr-1 unit with scfsi set re-reads gr 0's scalefactor
+// bits (maindata.go:239-278, quirk Q14).
+// Outputs: pk[8] scalefactor nibbles (n = sfb for scalefac_l, 22 + sfb*3 + win for scalefac_s), is_out[0..count1/2)
+// packed int16 pairs, meta = count1 | preflag << 10.  Lines >= count1 are zero by definition; K2 masks them
+// instead of K1 writing zeros.
+struct HuffRegions {  // region starts in PAIRS (all sfb boundaries are even) and the three trees
+    int r1h, r2h, nbig;
+    uint32_t e0, e1, e2;  // huff_desc of the three regions
+};
+MP3_HD HuffRegions huff_regions(const DeviceTables &T, const uint32_t *huff_desc, uint32_t w0, uint32_t w1, uint32_t w2) {
+    HuffRegions R;
+    if (u_winsw(w0) == 1 && u_btype(w0) == 2) {
+        R.r1h = 18;
+        R.r2h = 288;
+    } else {
+        const uint16_t *l = T.sfb_long + (u_lsf(w2) * 3 + u_sfreq(w2)) * 24;
+        int i = u_reg0(w1) + 1;  // <= 16 < 23
+        R.r1h = l[i] >> 1;
+        int j = u_reg0(w1) + u_reg1(w1) + 2;
+        R.r2h = j >= 23 ? 288 : (l[j] >> 1);
+    }
+    R.nbig = u_bigval(w0);
+    if (R.nbig > 288) R.nbig = 288;  // the host rejects such frames (huffman.go:68-70); never reached
+    R.e0 = huff_desc[u_tsel(w1, 0)];
+    R.e1 = huff_desc[u_tsel(w1, 1)];
+    R.e2 = huff_desc[u_tsel(w1, 2)];
+    return R;
+}
+MP3_HD uint32_t huff_pair_at(const uint32_t *lut, const HuffRegions &R, int k, BitCursor &bc) {
+    const bool in0 = k < R.r1h, in1 = k < R.r2h;
+    return huff_pair(lut, (in0 ? R.e0 : (in1 ? R.e1 : R.e2)) & 0xffffffu,
+                     [&] { return (int)((in0 ? R.e0 : (in1 ? R.e1 : R.e2)) >> 24); }, bc);
+}
+
+// State handed from stage A to stage B: bits 0..29 logical cursor position (relative to bit_start), bit 30 preflag,
+// bit 31 = nothing left to do (part2_3_length == 0, quirk Q1: nothing decoded, Count1 stays 0).
+constexpr uint32_t kHuffDone = 0x80000000u;
+MP3_HD int huff_state_pos(uint32_t st) { return (int)(st & 0x3fffffffu); }
+MP3_HD int huff_state_preflag(uint32_t st) { return (int)((st >> 30) & 1); }
+
+MP3_HD uint32_t huffman_stage_a(const DeviceTables &T, const uint32_t *lut, const uint32_t *huff_desc,
+                                const uint8_t *main_data, uint64_t main_bits, const mp3gpu_unit *units, long long unit_index,
+                                uint32_t *pk, uint32_t *is_out) {
     const mp3gpu_unit u = units[unit_index];
     const uint32_t w0 = u.w0, w1 = u.w1, w2 = u.w2;
     BitCursor bc;
@@ -352,45 +391,47 @@ MP3_HD uint32_t huffman_unit(const DeviceTables &T, const uint32_t *lut, const u
         }
     }
 
-    // ---- part 3: Huffman (maindata/huffman.go:27-138) ---------------------------------------
-    const int p23 = u_p23len(w0);
-    if (p23 == 0) return (uint32_t)preflag << 10;  // Q1: nothing decoded, Count1 stays 0
-    const int bit_pos_end = p23 - 1;               // part2Start is position 0 of this cursor
-    int r1h, r2h;                                  // region starts in PAIRS (all sfb boundaries are even)
-    if (u_winsw(w0) == 1 && u_btype(w0) == 2) {
-        r1h = 18;
-        r2h = 288;
-    } else {
-        const uint16_t *l = T.sfb_long + (u_lsf(w2) * 3 + u_sfreq(w2)) * 24;
-        int i = u_reg0(w1) + 1;  // <= 16 < 23
-        r1h = l[i] >> 1;
-        int j = u_reg0(w1) + u_reg1(w1) + 2;
-        r2h = j >= 23 ? 288 : (l[j] >> 1);
+    // ---- part 3: Huffman (maindata/huffman.go:27-138), whole groups of four pairs ---------------
+    if (u_p23len(w0) == 0) return kHuffDone | ((uint32_t)preflag << 30);
+    const HuffRegions R = huff_regions(T, huff_desc, w0, w1, w2);
+    uint4 *dst4 = reinterpret_cast<uint4 *>(is_out);
+    for (int k = 0; k + 4 <= R.nbig; k += 4) {  // four pairs per 16-byte store
+        uint4 v;
+        v.x = huff_pair_at(lut, R, k, bc);
+        v.y = huff_pair_at(lut, R, k + 1, bc);
+        v.z = huff_pair_at(lut, R, k + 2, bc);
+        v.w = huff_pair_at(lut, R, k + 3, bc);
+        dst4[k >> 2] = v;
     }
-    int nbig = u_bigval(w0);
-    if (nbig > 288) nbig = 288;  // the host rejects such frames (huffman.go:68-70); never reached
-    const uint32_t e0 = huff_desc[u_tsel(w1, 0)], e1 = huff_desc[u_tsel(w1, 1)], e2 = huff_desc[u_tsel(w1, 2)];
-    const uint32_t d0 = e0 & 0xffffffu, d1 = e1 & 0xffffffu, d2 = e2 & 0xffffffu;  // root table byte offsets per region
-    auto pair_at = [&](int kk) {
-        const bool in0 = kk < r1h, in1 = kk < r2h;
-        return huff_pair(lut, in0 ? d0 : (in1 ? d1 : d2), [&] { return (int)((in0 ? e0 : (in1 ? e1 : e2)) >> 24); }, bc);
-    };
-    int k = 0;
-    {   // four pairs per 16-byte store
-        uint4 *dst4 = reinterpret_cast<uint4 *>(is_out);
-        for (; k + 4 <= nbig; k += 4) {
-            uint4 v;
-            v.x = pair_at(k);
-            v.y = pair_at(k + 1);
-            v.z = pair_at(k + 2);
-            v.w = pair_at(k + 3);
-            dst4[k >> 2] = v;
-        }
-    }
+    return (uint32_t)bc.pos() | ((uint32_t)preflag << 30);
+}
+
+// Bits of part 3 left after stage A: what stage B's cost grows with.
+MP3_HD int huff_bits_left(uint32_t w0, uint32_t st) {
+    if (st & kHuffDone) return 0;
+    const int left = u_p23len(w0) - huff_state_pos(st);
+    return left > 0 ? left : 0;
+}
+
+MP3_HD uint32_t huffman_stage_b(const DeviceTables &T, const uint32_t *lut, const uint32_t *huff_desc, const uint64_t *quad_signs,
+                                const uint8_t *main_data, uint64_t main_bits, const mp3gpu_unit *units, long long unit_index,
+                                uint32_t st, uint32_t *is_out) {
+    const uint32_t preflag = (uint32_t)huff_state_preflag(st);
+    if (st & kHuffDone) return preflag << 10;
+    const mp3gpu_unit u = units[unit_index];
+    const uint32_t w0 = u.w0, w1 = u.w1, w2 = u.w2;
+    // Restart the cursor at the logical position stage A reached.  A cursor that had run past the buffer end reads
+    // zeros and reports the end position; so does one restarted exactly there.
+    const int pos0 = huff_state_pos(st);
+    BitCursor bc;
+    bc.init(main_data, main_bits, u.bit_start + (uint64_t)pos0, u.buf_end_rel - pos0);
+    const int bit_pos_end = u_p23len(w0) - 1 - pos0;  // part2Start is position -pos0 of this cursor
+    const HuffRegions R = huff_regions(T, huff_desc, w0, w1, w2);
+    int k = R.nbig & ~3;
     PairSink sink;
     sink.init(is_out, k);
-    for (; k < nbig; k++) sink.put(pair_at(k));
-    int is_pos = nbig * 2;
+    for (; k < R.nbig; k++) sink.put(huff_pair_at(lut, R, k, bc));
+    int is_pos = R.nbig * 2;
     {
         const uint32_t dq = huff_desc[32 + u_c1tsel(w2)] & 0xffffffu;
         while (is_pos <= 572 && bc.pos() <= bit_pos_end) {
@@ -404,8 +445,15 @@ MP3_HD uint32_t huffman_unit(const DeviceTables &T, const uint32_t *lut, const u
     sink.flush();
     if (bc.pos() > bit_pos_end + 1) is_pos -= 4;  // overshoot: drop the last quadruple (huffman.go:119-122)
     if (is_pos < 0) is_pos = 0;
-    return (uint32_t)is_pos | ((uint32_t)preflag << 10);
-    // Lines >= count1 are zero by definition; K2 masks them instead of K1 writing zeros.
+    return (uint32_t)is_pos | (preflag << 10);
+}
+
+// Both stages back to back (host emulation and tests).
+MP3_HD uint32_t huffman_unit(const DeviceTables &T, const uint32_t *lut, const uint32_t *huff_desc, const uint64_t *quad_signs,
+                             const uint8_t *main_data, uint64_t main_bits, const mp3gpu_unit *units, long long unit_index,
+                             uint32_t *pk, uint32_t *is_out) {
+    const uint32_t st = huffman_stage_a(T, lut, huff_desc, main_data, main_bits, units, unit_index, pk, is_out);
+    return huffman_stage_b(T, lut, huff_desc, quad_signs, main_data, main_bits, units, unit_index, st, is_out);
 }
 
 // ---- K2 per-line logic ---------------------------------------------------------------------------
