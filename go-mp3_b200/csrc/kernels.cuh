@@ -530,25 +530,28 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
 // ------------------------------------------------------------------------------------------
 // k_synth = K4: polyphase synthesis + int16 clamp/interleave (frame.go:630-688).
 //
-// CTA = 256 consecutive time slots of the wave (slot = granule*18 + t), the first 16 being the
-// V-history halo of the 240 output slots.
-//   Phase A (matrixing, frame.go:644-650): one THREAD per slot, both channels.  The 32 subband
-//     samples of the slot sit in registers and the cosine matrix is compile-time, so every
-//     multiply-add is an FFMA with an immediate coefficient.  Only the 33 rows that are unique
-//     are computed: synthNWin[32-i][j] == -synthNWin[i][j] (i = 1..16) and
-//     synthNWin[48+m][j] == synthNWin[48-m][j] (m = 1..15) hold BITWISE in the float32 table, and
-//     a sum of negated terms in the same order is the exact negation.  Row u of the slot goes to
-//     shared memory: U[0..16] = V[0..16], U[17..32] = V[33..48].
-//   Phase B (window, frame.go:651-678): one WARP per 30 consecutive output slots, lane = output
-//     index i, marching in time with the 15-slot V history in registers (circular, period 15) and
-//     D[32d + i] in registers; taps accumulate in the reference's order (d ascending).  Both
-//     channels are done together so the int16 pair is packed and stored as one coalesced word.
+// Every WARP owns a segment of kSynSegSlots consecutive time slots of the wave (slot = granule*18 + t) and walks it
+// in blocks of 30 slots, alternating two phases on a private shared-memory buffer; warps never synchronise with each
+// other, so one warp's loads overlap the other warps' arithmetic.
+//   Phase A (matrixing, frame.go:644-650): lane = slot of the block, both channels.  Exact build: the 32 subband
+//     samples of the slot sit in registers and the cosine matrix is compile-time, so every multiply-add is an FFMA
+//     with an immediate coefficient; only the 33 rows that are unique are computed: synthNWin[32-i][j] ==
+//     -synthNWin[i][j] (i = 1..16) and synthNWin[48+m][j] == synthNWin[48-m][j] (m = 1..15) hold BITWISE in the
+//     float32 table, and a sum of negated terms in the same order is the exact negation.  Fast build: a 32-point
+//     Lee DCT (below).  Row u of the slot goes to shared memory: U[0..16] = V[0..16], U[17..32] = V[33..48].
+//   Phase B (window, frame.go:651-678): lane = output index i, marching in time with the 15-slot V history in
+//     registers (circular, period 15) and D[32d + i] in registers; taps accumulate in the reference's order
+//     (d ascending).  Both channels are done together so the int16 pair is packed and stored as one coalesced word.
+// The history carries over from block to block; a segment starts by replaying the 15 slots in front of it
+// (phase A + history fill only), which recreates exactly the state a linear decode has there.
 // ------------------------------------------------------------------------------------------
-constexpr int kSynThreads = 256;
-constexpr int kSynHalo = 16;
-constexpr int kSynOut = kSynThreads - kSynHalo;  // 240 = 8 warps x 30 slots
+constexpr int kSynWarps = 4;
+constexpr int kSynThreads = kSynWarps * 32;
+constexpr int kSynBlock = 30;                    // slots per block: two periods of the circular history
+constexpr int kSynSegSlots = kSynBlock * 24;     // 720 slots = 40 granules per segment
 constexpr int kURow = 36;                        // floats per U row: 16-byte aligned, conflict-free 128-bit stores
-constexpr int kSynSmemBytes = 2 * kSynThreads * kURow * 4 + kSynThreads;
+constexpr int kSynWarpWords = 2 * kSynBlock * kURow + 8;  // U[2][30][36] + flags[30] (8 words)
+constexpr int kSynSmemBytes = kSynWarps * kSynWarpWords * 4;
 
 __device__ __forceinline__ int pcm_from_float(float sum) {
     // frame.go:663-668: int(sum * 32767) truncates toward zero, then clamps to +-32767.  The clamp is done in float
@@ -610,13 +613,15 @@ __device__ __forceinline__ void lee_dct(const float (&x)[N], float (&X)[N]) {
 }
 #endif
 
-__device__ __forceinline__ void matrix_slot(const float *__restrict__ src, float *urow) {
-    float s[32];
+__device__ __forceinline__ void load_slot(const float *__restrict__ src, float (&s)[32]) {
 #pragma unroll
     for (int q = 0; q < 8; q++) {
         const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + q);
         s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
     }
+}
+
+__device__ __forceinline__ void matrix_slot(const float (&s)[32], float *urow) {
 #if MP3GPU_EXACT
     // rows 0..16 -> U[0..16]; rows 33..48 -> U[17..32]
     matrix_rows<0, 4>(s, urow, 0);   matrix_rows<4, 4>(s, urow, 4);   matrix_rows<8, 4>(s, urow, 8);
@@ -701,39 +706,52 @@ __device__ __forceinline__ void synth_window_block(const float *U0, const float 
 #undef MP3_SLOT
 }
 
-__global__ void __launch_bounds__(kSynThreads, 2)
+// Phase A for the block rows [0, n_rows): lane r handles wave-local slot sigma0 + r.
+__device__ __forceinline__ void synth_matrix_block(const mp3gpu_unit *__restrict__ units, long long first_granule, long long n_slots,
+                                                   const WaveBufs &B, float *U0, float *U1, uint8_t *flags, long long sigma0,
+                                                   int n_rows, int lane) {
+    const long long sigma = sigma0 + lane;
+    const bool in_range = lane < n_rows && sigma >= -18 && sigma < n_slots && (first_granule * 18 + sigma) >= 0;
+    int f = 0;
+    if (in_range) {
+        const long long g = sigma >= 0 ? sigma / 18 : -1;
+        const int t = (int)(sigma - g * 18);
+        const mp3gpu_unit *ug = units + (first_granule + g) * 2;
+        const uint32_t w2a = __ldg(&ug[0].w2), w2b = __ldg(&ug[1].w2);
+        if (u_valid(w2a)) {
+            f = 1 | (u_valid(w2b) ? 2 : 0) | ((u_zero(w2a) && t == 0) ? 4 : 0);
+#if MP3GPU_EXACT
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ch++)  // not unrolled: the 1,056 immediate FFMAs exist once in the code
+                if (f & (1 << ch)) {
+                    float s[32];
+                    load_slot(B.hyb + ((g * 2 + ch) * 18 + t) * 32, s);
+                    matrix_slot(s, (ch ? U1 : U0) + lane * kURow);
+                }
+#else
+            // both channels' loads are in flight before the first DCT
+            float s0[32], s1[32];
+            load_slot(B.hyb + ((g * 2) * 18 + t) * 32, s0);
+            if (f & 2) load_slot(B.hyb + ((g * 2 + 1) * 18 + t) * 32, s1);
+            matrix_slot(s0, U0 + lane * kURow);
+            if (f & 2) matrix_slot(s1, U1 + lane * kURow);
+#endif
+        }
+    }
+    if (lane < kSynBlock) flags[lane] = (uint8_t)f;
+}
+
+__global__ void __launch_bounds__(kSynThreads, 3)
 k_synth(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_granules, WaveBufs B,
         int16_t *__restrict__ pcm /* wave-local: [n_granules][576][2] */) {
-    extern __shared__ __align__(16) float s_u[];  // U[2][256][36], then flags[256]
-    float *U0 = s_u, *U1 = s_u + kSynThreads * kURow;
-    uint8_t *flags = reinterpret_cast<uint8_t *>(s_u + 2 * kSynThreads * kURow);
-    const int tid = threadIdx.x;
+    extern __shared__ __align__(16) float s_u[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *U0 = s_u + warp * kSynWarpWords, *U1 = U0 + kSynBlock * kURow;
+    uint8_t *flags = reinterpret_cast<uint8_t *>(U0 + 2 * kSynBlock * kURow);
     const long long n_slots = (long long)n_granules * 18;
-    const long long cta_first = (long long)blockIdx.x * kSynOut - kSynHalo;  // wave-local slot of row 0
+    const long long seg_first = ((long long)blockIdx.x * kSynWarps + warp) * kSynSegSlots;  // wave-local slot
+    if (seg_first >= n_slots) return;
 
-    // ---------------- phase A: matrixing, thread = slot ---------------------------------------------
-    {
-        const long long sigma = cta_first + tid;
-        const bool in_range = sigma >= -18 && sigma < n_slots && (first_granule * 18 + sigma) >= 0;
-        int f = 0;
-        if (in_range) {
-            const long long g = sigma >= 0 ? sigma / 18 : -1;
-            const int t = (int)(sigma - g * 18);
-            const mp3gpu_unit *ug = units + (first_granule + g) * 2;
-            const uint32_t w2a = __ldg(&ug[0].w2), w2b = __ldg(&ug[1].w2);
-            if (u_valid(w2a)) {
-                f = 1 | (u_valid(w2b) ? 2 : 0) | ((u_zero(w2a) && t == 0) ? 4 : 0);
-#pragma unroll 1
-                for (int ch = 0; ch < 2; ch++)  // not unrolled: the 1,056 immediate FFMAs exist once in the code
-                    if (f & (1 << ch)) matrix_slot(B.hyb + ((g * 2 + ch) * 18 + t) * 32, (ch ? U1 : U0) + tid * kURow);
-            }
-        }
-        flags[tid] = (uint8_t)f;
-    }
-    __syncthreads();
-
-    // ---------------- phase B: window + int16 store, warp = 30 slots, lane = output index -----------
-    const int lane = tid & 31, warp = tid >> 5;
     // V[i] = i <= 16 ? U[i] : -U[32-i];  V[32+i] = i == 0 ? -U[0] : i <= 16 ? U[16+i] : U[48-i].  A lane's sign is the
     // same for all its even taps (V[i]) and for all its odd taps (V[32+i]), so it is folded into the window
     // coefficients: fma(-u, D, acc) == fma(u, -D, acc) exactly, and a zero's sign never reaches a sum that starts at +0.
@@ -751,22 +769,31 @@ k_synth(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_gr
     float A0[15], B0[15], A1[15], B1[15];
 #pragma unroll
     for (int i = 0; i < 15; i++) { A0[i] = B0[i] = A1[i] = B1[i] = 0.f; }
-    const int r0 = kSynHalo + warp * 30;  // first output row of this warp
     uint32_t *pcm32 = reinterpret_cast<uint32_t *>(pcm);
-    // Blocks of 15 rows: warm-up (the 15 slots in front; slot -15+p sits at circular position p), then two output
-    // blocks.  A block whose rows are all plain stereo slots takes the branch-free FAST path.
+
+    // warm-up: the 15 slots in front of the segment (slot seg_first - 15 + p sits at circular position p)
+    synth_matrix_block(units, first_granule, n_slots, B, U0, U1, flags, seg_first - 15, 15, lane);
+    __syncwarp();
+    {
+        const bool plain = __all_sync(0xffffffffu, lane >= 15 || flags[lane] == 3);
+        if (plain) synth_window_block<true, true>(U0, U1, flags, 0, L, dw, A0, B0, A1, B1, pcm32, seg_first - 15, n_slots, lane);
+        else synth_window_block<false, true>(U0, U1, flags, 0, L, dw, A0, B0, A1, B1, pcm32, seg_first - 15, n_slots, lane);
+    }
+    __syncwarp();
 #pragma unroll 1
-    for (int blk = -1; blk < 2; blk++) {
-        const int rb = r0 + blk * 15;
-        const bool plain = __all_sync(0xffffffffu, lane >= 15 || flags[rb + lane] == 3);
-        const long long sb = cta_first + rb;
-        if (blk < 0) {
-            if (plain) synth_window_block<true, true>(U0, U1, flags, rb, L, dw, A0, B0, A1, B1, pcm32, sb, n_slots, lane);
-            else synth_window_block<false, true>(U0, U1, flags, rb, L, dw, A0, B0, A1, B1, pcm32, sb, n_slots, lane);
-        } else {
-            if (plain) synth_window_block<true, false>(U0, U1, flags, rb, L, dw, A0, B0, A1, B1, pcm32, sb, n_slots, lane);
-            else synth_window_block<false, false>(U0, U1, flags, rb, L, dw, A0, B0, A1, B1, pcm32, sb, n_slots, lane);
+    for (int blk = 0; blk < kSynSegSlots / kSynBlock; blk++) {
+        const long long sigma0 = seg_first + (long long)blk * kSynBlock;
+        if (sigma0 >= n_slots) break;
+        synth_matrix_block(units, first_granule, n_slots, B, U0, U1, flags, sigma0, kSynBlock, lane);
+        __syncwarp();
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+            const int rb = half * 15;
+            const bool plain = __all_sync(0xffffffffu, lane >= 15 || flags[rb + lane] == 3);
+            if (plain) synth_window_block<true, false>(U0, U1, flags, rb, L, dw, A0, B0, A1, B1, pcm32, sigma0 + rb, n_slots, lane);
+            else synth_window_block<false, false>(U0, U1, flags, rb, L, dw, A0, B0, A1, B1, pcm32, sigma0 + rb, n_slots, lane);
         }
+        __syncwarp();
     }
 }
 

@@ -308,7 +308,8 @@ static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, size_t main_len, 
     if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][2], s));
     {
         const long long slots = (long long)n * 18;
-        const int grid = (int)((slots + kSynOut - 1) / kSynOut);
+        const long long segs = (slots + kSynSegSlots - 1) / kSynSegSlots;
+        const int grid = (int)((segs + kSynWarps - 1) / kSynWarps);
         k_synth<<<grid, kSynThreads, kSynSmemBytes, s>>>(d_units, first, n, B, d_pcm_wave);
     }
     if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][3], s));
