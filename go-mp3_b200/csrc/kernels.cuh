@@ -550,7 +550,7 @@ constexpr int kSynThreads = kSynWarps * 32;
 constexpr int kSynBlock = 30;                    // slots per block: two periods of the circular history
 constexpr int kSynSegSlots = kSynBlock * 24;     // 720 slots = 40 granules per segment
 constexpr int kURow = 36;                        // floats per U row: 16-byte aligned, conflict-free 128-bit stores
-constexpr int kSynWarpWords = 2 * kSynBlock * kURow + 8;  // U[2][30][36] + flags[30] (8 words)
+constexpr int kSynWarpWords = 4 * kSynBlock * kURow + 8;  // U[2][30][36], staging S[2][30][36], flags[30] (8 words)
 constexpr int kSynSmemBytes = kSynWarps * kSynWarpWords * 4;
 
 __device__ __forceinline__ int pcm_from_float(float sum) {
@@ -706,39 +706,41 @@ __device__ __forceinline__ void synth_window_block(const float *U0, const float 
 #undef MP3_SLOT
 }
 
-// Phase A for the block rows [0, n_rows): lane r handles wave-local slot sigma0 + r.
-__device__ __forceinline__ void synth_matrix_block(const mp3gpu_unit *__restrict__ units, long long first_granule, long long n_slots,
-                                                   const WaveBufs &B, float *U0, float *U1, uint8_t *flags, long long sigma0,
-                                                   int n_rows, int lane) {
-    const long long sigma = sigma0 + lane;
-    const bool in_range = lane < n_rows && sigma >= -18 && sigma < n_slots && (first_granule * 18 + sigma) >= 0;
-    int f = 0;
-    if (in_range) {
-        const long long g = sigma >= 0 ? sigma / 18 : -1;
-        const int t = (int)(sigma - g * 18);
-        const mp3gpu_unit *ug = units + (first_granule + g) * 2;
-        const uint32_t w2a = __ldg(&ug[0].w2), w2b = __ldg(&ug[1].w2);
-        if (u_valid(w2a)) {
-            f = 1 | (u_valid(w2b) ? 2 : 0) | ((u_zero(w2a) && t == 0) ? 4 : 0);
-#if MP3GPU_EXACT
-#pragma unroll 1
-            for (int ch = 0; ch < 2; ch++)  // not unrolled: the 1,056 immediate FFMAs exist once in the code
-                if (f & (1 << ch)) {
-                    float s[32];
-                    load_slot(B.hyb + ((g * 2 + ch) * 18 + t) * 32, s);
-                    matrix_slot(s, (ch ? U1 : U0) + lane * kURow);
-                }
-#else
-            // both channels' loads are in flight before the first DCT
-            float s0[32], s1[32];
-            load_slot(B.hyb + ((g * 2) * 18 + t) * 32, s0);
-            if (f & 2) load_slot(B.hyb + ((g * 2 + 1) * 18 + t) * 32, s1);
-            matrix_slot(s0, U0 + lane * kURow);
-            if (f & 2) matrix_slot(s1, U1 + lane * kURow);
-#endif
-        }
+// Slot flags of wave-local slot sigma: bit 0 / 1 = channel 0 / 1 present, bit 2 = first slot of a ZERO_STATE granule;
+// 0 outside the submission.
+__device__ __forceinline__ int synth_slot_flags(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_slots, int sigma) {
+    if (sigma < -18 || sigma >= n_slots || first_granule * 18 + sigma < 0) return 0;
+    const int g = (sigma + 18) / 18 - 1;
+    const mp3gpu_unit *ug = units + (first_granule + g) * 2;
+    const uint32_t w2a = __ldg(&ug[0].w2), w2b = __ldg(&ug[1].w2);
+    if (!u_valid(w2a)) return 0;
+    return 1 | (u_valid(w2b) ? 2 : 0) | ((u_zero(w2a) && sigma == g * 18) ? 4 : 0);
+}
+// Subband samples of (slot sigma, channel ch) in hyb (one look-back granule in front: sigma >= -18)
+__device__ __forceinline__ const float *synth_slot_src(const WaveBufs &B, int sigma, int ch) {
+    const int g = (sigma + 18) / 18 - 1;
+    const int t = sigma - g * 18;
+    return B.hyb + ((long long)(g * 2 + ch) * 18 + t) * 32;
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+// Starts the copy of the block's 2 x 30 input rows (128 B each) into the staging rows S[ch][row][0..31]: 480 chunks
+// of 16 bytes, consecutive lanes on consecutive chunks.  Rows outside the submission are skipped (phase A does not
+// read them); rows of an absent channel are copied as they are and ignored.
+__device__ __forceinline__ void synth_stage_block(const WaveBufs &B, long long first_granule, int n_slots, float *S, int sigma0, int lane) {
+#pragma unroll
+    for (int it = 0; it < 15; it++) {
+        const int c = it * 32 + lane;
+        const int ch = c >= 8 * kSynBlock ? 1 : 0;
+        const int rem = c - ch * 8 * kSynBlock;
+        const int row = rem >> 3, q = rem & 7;
+        const int sigma = sigma0 + row;
+        if (sigma < n_slots && first_granule * 18 + sigma >= 0)
+            cp_async16(S + (ch * kSynBlock + row) * kURow + q * 4, synth_slot_src(B, sigma, ch) + q * 4);
     }
-    if (lane < kSynBlock) flags[lane] = (uint8_t)f;
+    asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(kSynThreads, 3)
@@ -747,10 +749,14 @@ k_synth(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_gr
     extern __shared__ __align__(16) float s_u[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *U0 = s_u + warp * kSynWarpWords, *U1 = U0 + kSynBlock * kURow;
-    uint8_t *flags = reinterpret_cast<uint8_t *>(U0 + 2 * kSynBlock * kURow);
-    const long long n_slots = (long long)n_granules * 18;
-    const long long seg_first = ((long long)blockIdx.x * kSynWarps + warp) * kSynSegSlots;  // wave-local slot
-    if (seg_first >= n_slots) return;
+    float *S = U0 + 2 * kSynBlock * kURow;  // staging rows of the next block, same shape as U
+    uint8_t *flags = reinterpret_cast<uint8_t *>(S + 2 * kSynBlock * kURow);
+    const int n_slots = n_granules * 18;  // < 2^31: a wave is at most a few million granules
+    const long long seg_ll = ((long long)blockIdx.x * kSynWarps + warp) * kSynSegSlots;
+    if (seg_ll >= n_slots) return;
+    const int seg_first = (int)seg_ll;  // wave-local slot
+
+    synth_stage_block(B, first_granule, n_slots, S, seg_first, lane);  // block 0, in flight during the warm-up
 
     // V[i] = i <= 16 ? U[i] : -U[32-i];  V[32+i] = i == 0 ? -U[0] : i <= 16 ? U[16+i] : U[48-i].  A lane's sign is the
     // same for all its even taps (V[i]) and for all its odd taps (V[32+i]), so it is folded into the window
@@ -771,21 +777,54 @@ k_synth(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_gr
     for (int i = 0; i < 15; i++) { A0[i] = B0[i] = A1[i] = B1[i] = 0.f; }
     uint32_t *pcm32 = reinterpret_cast<uint32_t *>(pcm);
 
-    // warm-up: the 15 slots in front of the segment (slot seg_first - 15 + p sits at circular position p)
-    synth_matrix_block(units, first_granule, n_slots, B, U0, U1, flags, seg_first - 15, 15, lane);
-    __syncwarp();
+    // warm-up: the 15 slots in front of the segment (slot seg_first - 15 + p sits at circular position p), straight
+    // from global memory
     {
+        const int f = lane < 15 ? synth_slot_flags(units, first_granule, n_slots, seg_first - 15 + lane) : 0;
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ch++)
+            if (f & (1 << ch)) {
+                float s[32];
+                load_slot(synth_slot_src(B, seg_first - 15 + lane, ch), s);
+                matrix_slot(s, (ch ? U1 : U0) + lane * kURow);
+            }
+        if (lane < kSynBlock) flags[lane] = (uint8_t)f;
+        __syncwarp();
         const bool plain = __all_sync(0xffffffffu, lane >= 15 || flags[lane] == 3);
         if (plain) synth_window_block<true, true>(U0, U1, flags, 0, L, dw, A0, B0, A1, B1, pcm32, seg_first - 15, n_slots, lane);
         else synth_window_block<false, true>(U0, U1, flags, 0, L, dw, A0, B0, A1, B1, pcm32, seg_first - 15, n_slots, lane);
+        __syncwarp();
     }
-    __syncwarp();
+    int f_next = lane < kSynBlock ? synth_slot_flags(units, first_granule, n_slots, seg_first + lane) : 0;
 #pragma unroll 1
     for (int blk = 0; blk < kSynSegSlots / kSynBlock; blk++) {
-        const long long sigma0 = seg_first + (long long)blk * kSynBlock;
+        const int sigma0 = seg_first + blk * kSynBlock;
         if (sigma0 >= n_slots) break;
-        synth_matrix_block(units, first_granule, n_slots, B, U0, U1, flags, sigma0, kSynBlock, lane);
+        const int f = f_next;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
+        // ---- phase A: lane = slot sigma0 + lane, rows from the staging buffer ----
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ch++)
+            if (f & (1 << ch)) {
+                float s[32];
+                const float4 *src = reinterpret_cast<const float4 *>(S + (ch * kSynBlock + lane) * kURow);
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const float4 v = src[q];
+                    s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
+                }
+                matrix_slot(s, (ch ? U1 : U0) + lane * kURow);
+            }
+        if (lane < kSynBlock) flags[lane] = (uint8_t)f;
+        __syncwarp();
+        // ---- next block: start its copy and its flag loads, both consumed after phase B ----
+        const bool more = blk + 1 < kSynSegSlots / kSynBlock && sigma0 + kSynBlock < n_slots;
+        if (more) {
+            synth_stage_block(B, first_granule, n_slots, S, sigma0 + kSynBlock, lane);
+            f_next = lane < kSynBlock ? synth_slot_flags(units, first_granule, n_slots, sigma0 + kSynBlock + lane) : 0;
+        }
+        // ---- phase B ----
 #pragma unroll 1
         for (int half = 0; half < 2; half++) {
             const int rb = half * 15;
