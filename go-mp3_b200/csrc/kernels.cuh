@@ -707,20 +707,24 @@ __device__ __forceinline__ void synth_window_block(const float *U0, const float 
 }
 
 // Slot flags of wave-local slot sigma: bit 0 / 1 = channel 0 / 1 present, bit 2 = first slot of a ZERO_STATE granule;
-// 0 outside the submission.
-__device__ __forceinline__ int synth_slot_flags(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_slots, int sigma) {
-    if (sigma < -18 || sigma >= n_slots || first_granule * 18 + sigma < 0) return 0;
+// 0 outside the submission.  Split in two so that the descriptor loads can be issued a block ahead of their use:
+// synth_flag_words() only loads (bit 31 of the result: slot inside the submission), synth_flags_of() decodes.
+__device__ __forceinline__ uint2 synth_flag_words(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_slots, int sigma) {
+    if (sigma < -18 || sigma >= n_slots || first_granule * 18 + sigma < 0) return make_uint2(0u, 0u);
     const int g = (sigma + 18) / 18 - 1;
     const mp3gpu_unit *ug = units + (first_granule + g) * 2;
-    const uint32_t w2a = __ldg(&ug[0].w2), w2b = __ldg(&ug[1].w2);
-    if (!u_valid(w2a)) return 0;
-    return 1 | (u_valid(w2b) ? 2 : 0) | ((u_zero(w2a) && sigma == g * 18) ? 4 : 0);
+    return make_uint2(__ldg(&ug[0].w2), __ldg(&ug[1].w2));
 }
-// Subband samples of (slot sigma, channel ch) in hyb (one look-back granule in front: sigma >= -18)
-__device__ __forceinline__ const float *synth_slot_src(const WaveBufs &B, int sigma, int ch) {
+__device__ __forceinline__ int synth_flags_of(uint2 w, int sigma) {
+    if (!u_valid(w.x)) return 0;
     const int g = (sigma + 18) / 18 - 1;
-    const int t = sigma - g * 18;
-    return B.hyb + ((long long)(g * 2 + ch) * 18 + t) * 32;
+    return 1 | (u_valid(w.y) ? 2 : 0) | ((u_zero(w.x) && sigma == g * 18) ? 4 : 0);
+}
+// Subband samples of (slot sigma, channel ch) in hyb (one look-back granule in front: sigma >= -18).
+// Row ((g*2 + ch)*18 + t) with g = sigma / 18, t = sigma % 18 is row 2*sigma - t + 18*ch.
+__device__ __forceinline__ const float *synth_slot_src(const WaveBufs &B, int sigma, int ch) {
+    const int t = (sigma + 18) % 18;
+    return B.hyb + (long long)(2 * sigma - t + 18 * ch) * 32;
 }
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
@@ -780,7 +784,7 @@ k_synth(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_gr
     // warm-up: the 15 slots in front of the segment (slot seg_first - 15 + p sits at circular position p), straight
     // from global memory
     {
-        const int f = lane < 15 ? synth_slot_flags(units, first_granule, n_slots, seg_first - 15 + lane) : 0;
+        const int f = lane < 15 ? synth_flags_of(synth_flag_words(units, first_granule, n_slots, seg_first - 15 + lane), seg_first - 15 + lane) : 0;
 #pragma unroll 1
         for (int ch = 0; ch < 2; ch++)
             if (f & (1 << ch)) {
@@ -795,12 +799,12 @@ k_synth(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_gr
         else synth_window_block<false, true>(U0, U1, flags, 0, L, dw, A0, B0, A1, B1, pcm32, seg_first - 15, n_slots, lane);
         __syncwarp();
     }
-    int f_next = lane < kSynBlock ? synth_slot_flags(units, first_granule, n_slots, seg_first + lane) : 0;
+    uint2 fw_next = synth_flag_words(units, first_granule, n_slots, lane < kSynBlock ? seg_first + lane : n_slots);
 #pragma unroll 1
     for (int blk = 0; blk < kSynSegSlots / kSynBlock; blk++) {
         const int sigma0 = seg_first + blk * kSynBlock;
         if (sigma0 >= n_slots) break;
-        const int f = f_next;
+        const int f = synth_flags_of(fw_next, sigma0 + lane);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         // ---- phase A: lane = slot sigma0 + lane, rows from the staging buffer ----
@@ -822,7 +826,7 @@ k_synth(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_gr
         const bool more = blk + 1 < kSynSegSlots / kSynBlock && sigma0 + kSynBlock < n_slots;
         if (more) {
             synth_stage_block(B, first_granule, n_slots, S, sigma0 + kSynBlock, lane);
-            f_next = lane < kSynBlock ? synth_slot_flags(units, first_granule, n_slots, sigma0 + kSynBlock + lane) : 0;
+            fw_next = synth_flag_words(units, first_granule, n_slots, lane < kSynBlock ? sigma0 + kSynBlock + lane : n_slots);
         }
         // ---- phase B ----
 #pragma unroll 1
