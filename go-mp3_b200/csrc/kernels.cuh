@@ -50,6 +50,7 @@ __device__ __forceinline__ float mac(float a, float b, float sum) {
 // ------------------------------------------------------------------------------------------
 #include "const_tables.inc"
 __constant__ float c_win[4 * 36];  // IMDCT window rows, indexed by the run-time block type (warp-uniform except quirk Q15)
+__constant__ float c_winz[4 * 36]; // fast build: window x output scale/sign of the fast 36-point IMDCT (imdct36_emit)
 
 // Wave-local intermediate buffers.  Index j = local granule (g - wave_first).  k_hybrid looks one
 // granule back (halo) and k_synth 16 time slots, so K1's outputs and hyb have valid look-back slots in
@@ -187,6 +188,7 @@ struct HybridSink {
 
 // 36-point IMDCT + window (imdct.go:99-107).  The window row `bt` is a run-time value (warp-uniform except for
 // the mixed-flag quirk of frame.go:462-466), looked up in the constant bank; the cosines are immediates.
+#if MP3GPU_EXACT
 __device__ __forceinline__ void imdct36_emit(const float (&in)[18], const HybridSink &k, int bt) {
     const float *w = c_win + bt * 36;
     if (k.first_half) {
@@ -211,6 +213,63 @@ __device__ __forceinline__ void imdct36_emit(const float (&in)[18], const Hybrid
         k.second(17 - q, __fmul_rn(v[q], w[35 - q]));      // cos36[m][53-p] == cos36[m][p] bitwise
     }
 }
+#else
+// Fast build.  out[p] = sum_m in[m] cos(pi/72 (2p + 19)(2m + 1)) is an 18-point DCT-IV y[k] = sum_m in[m]
+// cos(pi/72 (2k+1)(2m+1)) read out as out[p] = y[p+9] (p < 9), -y[26-p] (9 <= p < 27), -y[p-27] (p >= 27).
+// With 2 cos(a) cos(b) = cos(a+b) + cos(a-b):
+//   2 cos(pi (2k+1) / 72) y[k] = z[k] = sum_m x'[m] cos(pi m (2k+1) / 36),  x'[m] = in[m] + in[m-1]
+//   z[k], z[17-k] = E[k] +- O[k]  with E the 9-point DCT-III of x'[even] and, by the same identity once more,
+//   2 cos(pi (2k+1) / 36) O[k] = the 9-point DCT-III of x'[2j+1] + x'[2j-1].
+// 176 operations instead of 378.  The factor 1 / (2 cos(pi (2k+1) / 72)), the read-out sign and the window are one
+// table, c_winz (mp3gpu.cu).  Results differ from the direct sum by float32 rounding only (PCM +-1 LSB; tests).
+__device__ __forceinline__ void dct3_9(const float (&a)[9], float (&D)[9]) {
+    // D[k] = sum_j a[j] cos(pi j (2k+1) / 18); cos(pi j (2(8-k)+1) / 18) = (-1)^j cos(pi j (2k+1) / 18)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        float e = a[0], o = a[1] * kDct9[1][k];
+#pragma unroll
+        for (int j = 2; j < 9; j += 2) e = fmaf(a[j], kDct9[j][k], e);
+#pragma unroll
+        for (int j = 3; j < 9; j += 2) o = fmaf(a[j], kDct9[j][k], o);
+        D[k] = e + o;
+        D[8 - k] = e - o;
+    }
+    D[4] = ((a[0] - a[2]) + (a[4] - a[6])) + a[8];
+}
+__device__ __forceinline__ void imdct36_emit(const float (&in)[18], const HybridSink &k, int bt) {
+    const float *w = c_winz + bt * 36;
+    float a[9], b[9], E[9], O[9];
+    a[0] = in[0];
+    b[0] = in[1] + in[0];
+#pragma unroll
+    for (int j = 1; j < 9; j++) {
+        a[j] = in[2 * j] + in[2 * j - 1];                                      // x'[2j]
+        b[j] = (in[2 * j + 1] + in[2 * j]) + (in[2 * j - 1] + in[2 * j - 2]);  // x'[2j+1] + x'[2j-1]
+    }
+    dct3_9(a, E);
+    dct3_9(b, O);
+    float z[18];
+#pragma unroll
+    for (int q = 0; q < 9; q++) {
+        const float o = O[q] * kSec36[0][q];
+        z[q] = E[q] + o;
+        z[17 - q] = E[q] - o;
+    }
+    if (k.first_half) {
+#pragma unroll
+        for (int p = 0; p < 9; p++) {
+            k.first(p, z[9 + p] * w[p]);
+            k.first(17 - p, z[9 + p] * w[17 - p]);
+        }
+    }
+    // the second half overwrites the overlap that first() has just consumed
+#pragma unroll
+    for (int q = 0; q < 9; q++) {
+        k.second(q, z[8 - q] * w[18 + q]);
+        k.second(17 - q, z[8 - q] * w[35 - q]);
+    }
+}
+#endif
 
 // Short blocks (imdct.go:86-98): three 12-point transforms, windowed and overlapped into out[6..29];
 // out[0..5] and out[30..35] stay 0.  raw[j] accumulates in window order i = 0, 1, 2 like the reference.

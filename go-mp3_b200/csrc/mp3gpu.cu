@@ -119,6 +119,17 @@ static int upload_tables(mp3gpu_ctx *ctx) {
         }
     }
     CK(cudaMemcpyToSymbol(c_win, h.imdct_win, sizeof h.imdct_win));
+    {   // fast IMDCT read-out (kernels.cuh, imdct36_emit): windowed out[p] = z[idx(p)] * winz[bt][p]
+        float winz[4 * 36];
+        const double pi = 3.14159265358979323846;
+        for (int bt = 0; bt < 4; bt++)
+            for (int p = 0; p < 36; p++) {
+                const int kk = p < 9 ? p + 9 : (p < 27 ? 26 - p : p - 27);
+                const double sec = 1.0 / (2.0 * cos(pi * (2 * kk + 1) / 72.0));
+                winz[bt * 36 + p] = (float)((p < 9 ? sec : -sec) * (double)h.imdct_win[bt * 36 + p]);
+            }
+        CK(cudaMemcpyToSymbol(c_winz, winz, sizeof winz));
+    }
     // the symmetric matrixing of k_synth relies on these identities holding bitwise in the float32 table
     for (int j = 0; j < 32; j++) {
         for (int i = 0; i <= 15; i++)
