@@ -322,6 +322,7 @@ __device__ constexpr float kCa[8] = {-0.514496f, -0.471732f, -0.313377f, -0.1819
 // where lane = subband — the lane's own 18 lines (9 int16 pairs) of both channels.
 struct GranulePre {
     uint32_t w0a, w1a, w2a, w0b, w1b, w2b, meta0, meta1;
+    uint32_t sfw;        // lanes 0..15: word (lane & 7) of channel (lane >> 3)'s packed scalefactors
     uint32_t isw[2][9];
 };
 __device__ __forceinline__ void prefetch_granule(GranulePre &P, const mp3gpu_unit *__restrict__ units, long long first_granule, int g,
@@ -336,6 +337,7 @@ __device__ __forceinline__ void prefetch_granule(GranulePre &P, const mp3gpu_uni
     P.w0b = __ldg(&ug[1].w0); P.w1b = __ldg(&ug[1].w1); P.w2b = __ldg(&ug[1].w2);
     P.meta0 = __ldg(B.meta + (long long)g * 2);
     P.meta1 = __ldg(B.meta + (long long)g * 2 + 1);
+    P.sfw = __ldg(B.sfpack + (long long)g * 16 + (lane & 15));
     const uint32_t *is2 = reinterpret_cast<const uint32_t *>(B.is16 + (long long)g * 2 * 576) + lane * 9;
 #pragma unroll
     for (int q = 0; q < 9; q++) {
@@ -388,7 +390,7 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
             __syncwarp();
 
             const int cfg = u_lsf(w2a) * 3 + u_sfreq(w2a);
-            if (lane < 16) s_pk[lane >> 3][lane & 7] = __ldg(B.sfpack + ((long long)g * 2 + (lane >> 3)) * 8 + (lane & 7));
+            if (lane < 16) s_pk[lane >> 3][lane & 7] = C.sfw;
             const GranuleChan c0 = make_chan(w0a, w1a, w2a, C.meta0);
             const GranuleChan c1 = make_chan(w0b, w1b, w2b, valid_b ? C.meta1 : 0u);
             __syncwarp();
