@@ -708,18 +708,55 @@ __device__ __forceinline__ void matrix_slot(const float (&s)[32], float *urow) {
 #endif
 }
 
-template <int P>
-__device__ __forceinline__ float window_sum(const float (&A)[15], const float (&Bh)[15], const float (&dw)[16]) {
-    // out[i] = sum_d V_{t-d}[(d odd ? 32 : 0) + i] * D[32 d + i], d ascending (U construction, frame.go:651-661).
-    // Slot t-d lives at circular position (P - d) mod 15; A[P] already holds slot t, Bh[P] still holds slot t-15.
-    float sum = 0.0f;
+// V history of one lane (phase B) and its window coefficients.
+//   out[i] = sum_d V_{t-d}[(d odd ? 32 : 0) + i] * D[32 d + i], d = 0..15 (U construction, frame.go:651-661).
+// Slot t-d lives at circular position (P - d) mod 15: when slot t arrives at position P, its V[i] part is stored
+// before the sum and its V[32+i] part after it, because that place still holds slot t-15's, the d = 15 tap.
+#if MP3GPU_EXACT
+struct SynHist {
+    float A[2][15], B[2][15];  // [channel][position]: V[i] and V[32+i] of the slot at that position
+    float dw[16];
+    __device__ __forceinline__ void set_coef(int d, float v) { dw[d] = v; }
+    __device__ __forceinline__ void clear() {
 #pragma unroll
-    for (int d = 0; d < 16; d++) {
-        const int h = (P - d + 30) % 15;
-        sum = mac((d & 1) ? Bh[h] : A[h], dw[d], sum);
+        for (int i = 0; i < 15; i++) { A[0][i] = B[0][i] = A[1][i] = B[1][i] = 0.f; }
     }
-    return sum;
-}
+    template <int P, int CH> __device__ __forceinline__ void put_a(float a) { A[CH][P] = a; }
+    template <int P, int CH> __device__ __forceinline__ void put_b(float b) { B[CH][P] = b; }
+    template <int P, int CH> __device__ __forceinline__ float sum() const {  // d ascending, one chain: the reference's order
+        float acc = 0.0f;
+#pragma unroll
+        for (int d = 0; d < 16; d++) {
+            const int h = (P - d + 30) % 15;
+            acc = mac((d & 1) ? B[CH][h] : A[CH][h], dw[d], acc);
+        }
+        return acc;
+    }
+};
+#else
+// Fast build: taps (d, d+1), d even, are one packed FFMA2 — half the issue slots on the same FMA pipe.  The pair
+// (V_{t-d}[i], V_{t-d-1}[32+i]) is (slot at position j, slot at position j-1) for every P, so it can live in one
+// 64-bit register pair H[j]; the coefficient pair (D[32d+i], D[32(d+1)+i]) is adjacent anyway.  Even and odd taps
+// accumulate in two chains that are added at the end (a different rounding order than the reference's single chain;
+// the exact build keeps that one).
+struct SynHist {
+    float2 H[2][15];  // [channel][j] = (V[i] of the slot at position j, V[32+i] of the slot at position j-1)
+    float2 dw2[8];
+    __device__ __forceinline__ void set_coef(int d, float v) { if (d & 1) dw2[d >> 1].y = v; else dw2[d >> 1].x = v; }
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < 15; i++) { H[0][i] = make_float2(0.f, 0.f); H[1][i] = make_float2(0.f, 0.f); }
+    }
+    template <int P, int CH> __device__ __forceinline__ void put_a(float a) { H[CH][P].x = a; }
+    template <int P, int CH> __device__ __forceinline__ void put_b(float b) { H[CH][(P + 1) % 15].y = b; }
+    template <int P, int CH> __device__ __forceinline__ float sum() const {
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int d = 0; d < 16; d += 2) acc = __ffma2_rn(H[CH][(P - d + 30) % 15], dw2[d >> 1], acc);
+        return acc.x + acc.y;
+    }
+};
+#endif
 
 struct SynLane {  // where lane i finds V[i] and V[32+i] in a U row
     int ai, bi;
@@ -729,27 +766,23 @@ struct SynLane {  // where lane i finds V[i] and V[32+i] in a U row
 // block are plain stereo slots (both channels present, no state reset), so there are no flag tests at all.
 template <int P, bool FAST, bool WARMUP>
 __device__ __forceinline__ void synth_window_slot(const float *U0, const float *U1, const uint8_t *flags, int row, const SynLane &L,
-                                                  const float (&dw)[16], float (&A0)[15], float (&B0)[15], float (&A1)[15], float (&B1)[15],
-                                                  uint32_t *pcm32, long long sigma, long long n_slots, int lane) {
+                                                  SynHist &h, uint32_t *pcm32, long long sigma, long long n_slots, int lane) {
     const int f = FAST ? 3 : flags[row];
-    if (!FAST && (f & 4)) {  // first slot of a ZERO_STATE granule: Frame.vVec is zero (frame.go:49)
-#pragma unroll
-        for (int i = 0; i < 15; i++) { A0[i] = B0[i] = A1[i] = B1[i] = 0.f; }
-    }
+    if (!FAST && (f & 4)) h.clear();  // first slot of a ZERO_STATE granule: Frame.vVec is zero (frame.go:49)
     uint32_t pl = 0, pr = 0;
     if (f & 1) {
         const float a = U0[row * kURow + L.ai];
         const float b = U0[row * kURow + L.bi];
-        A0[P] = a;
-        if (!WARMUP) pl = (uint32_t)pcm_from_float(window_sum<P>(A0, B0, dw)) & 0xffffu;
-        B0[P] = b;
+        h.template put_a<P, 0>(a);
+        if (!WARMUP) pl = (uint32_t)pcm_from_float(h.template sum<P, 0>()) & 0xffffu;
+        h.template put_b<P, 0>(b);
     }
     if (f & 2) {
         const float a = U1[row * kURow + L.ai];
         const float b = U1[row * kURow + L.bi];
-        A1[P] = a;
-        if (!WARMUP) pr = (uint32_t)pcm_from_float(window_sum<P>(A1, B1, dw)) & 0xffffu;
-        B1[P] = b;
+        h.template put_a<P, 1>(a);
+        if (!WARMUP) pr = (uint32_t)pcm_from_float(h.template sum<P, 1>()) & 0xffffu;
+        h.template put_b<P, 1>(b);
     } else {
         pr = pl;  // mono: both output channels carry channel 0 (frame.go:671-678)
     }
@@ -759,9 +792,8 @@ __device__ __forceinline__ void synth_window_slot(const float *U0, const float *
 // 15 consecutive rows starting at `rb` (circular positions 0..14).
 template <bool FAST, bool WARMUP>
 __device__ __forceinline__ void synth_window_block(const float *U0, const float *U1, const uint8_t *flags, int rb, const SynLane &L,
-                                                   const float (&dw)[16], float (&A0)[15], float (&B0)[15], float (&A1)[15], float (&B1)[15],
-                                                   uint32_t *pcm32, long long sb, long long n_slots, int lane) {
-#define MP3_SLOT(Pp) synth_window_slot<Pp, FAST, WARMUP>(U0, U1, flags, rb + Pp, L, dw, A0, B0, A1, B1, pcm32, sb + Pp, n_slots, lane);
+                                                   SynHist &h, uint32_t *pcm32, long long sb, long long n_slots, int lane) {
+#define MP3_SLOT(Pp) synth_window_slot<Pp, FAST, WARMUP>(U0, U1, flags, rb + Pp, L, h, pcm32, sb + Pp, n_slots, lane);
     MP3_SLOT(0) MP3_SLOT(1) MP3_SLOT(2) MP3_SLOT(3) MP3_SLOT(4) MP3_SLOT(5) MP3_SLOT(6) MP3_SLOT(7)
     MP3_SLOT(8) MP3_SLOT(9) MP3_SLOT(10) MP3_SLOT(11) MP3_SLOT(12) MP3_SLOT(13) MP3_SLOT(14)
 #undef MP3_SLOT
@@ -834,12 +866,10 @@ k_synth(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_gr
 #else
     const float sa = lane <= 16 ? 1.0f : -1.0f, sb = -1.0f;  // U[17..32] hold +c[15..0] (matrix_slot): V[32+i] = -U[bi] for every lane
 #endif
-    float dw[16];
+    SynHist h;
 #pragma unroll
-    for (int d = 0; d < 16; d++) dw[d] = __ldg(B.synth_d + 32 * d + lane) * ((d & 1) ? sb : sa);
-    float A0[15], B0[15], A1[15], B1[15];
-#pragma unroll
-    for (int i = 0; i < 15; i++) { A0[i] = B0[i] = A1[i] = B1[i] = 0.f; }
+    for (int d = 0; d < 16; d++) h.set_coef(d, __ldg(B.synth_d + 32 * d + lane) * ((d & 1) ? sb : sa));
+    h.clear();
     uint32_t *pcm32 = reinterpret_cast<uint32_t *>(pcm);
 
     // warm-up: the 15 slots in front of the segment (slot seg_first - 15 + p sits at circular position p), straight
@@ -856,8 +886,8 @@ k_synth(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_gr
         if (lane < kSynBlock) flags[lane] = (uint8_t)f;
         __syncwarp();
         const bool plain = __all_sync(0xffffffffu, lane >= 15 || flags[lane] == 3);
-        if (plain) synth_window_block<true, true>(U0, U1, flags, 0, L, dw, A0, B0, A1, B1, pcm32, seg_first - 15, n_slots, lane);
-        else synth_window_block<false, true>(U0, U1, flags, 0, L, dw, A0, B0, A1, B1, pcm32, seg_first - 15, n_slots, lane);
+        if (plain) synth_window_block<true, true>(U0, U1, flags, 0, L, h, pcm32, seg_first - 15, n_slots, lane);
+        else synth_window_block<false, true>(U0, U1, flags, 0, L, h, pcm32, seg_first - 15, n_slots, lane);
         __syncwarp();
     }
     uint2 fw_next = synth_flag_words(units, first_granule, n_slots, lane < kSynBlock ? seg_first + lane : n_slots);
@@ -894,8 +924,8 @@ k_synth(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_gr
         for (int half = 0; half < 2; half++) {
             const int rb = half * 15;
             const bool plain = __all_sync(0xffffffffu, lane >= 15 || flags[rb + lane] == 3);
-            if (plain) synth_window_block<true, false>(U0, U1, flags, rb, L, dw, A0, B0, A1, B1, pcm32, sigma0 + rb, n_slots, lane);
-            else synth_window_block<false, false>(U0, U1, flags, rb, L, dw, A0, B0, A1, B1, pcm32, sigma0 + rb, n_slots, lane);
+            if (plain) synth_window_block<true, false>(U0, U1, flags, rb, L, h, pcm32, sigma0 + rb, n_slots, lane);
+            else synth_window_block<false, false>(U0, U1, flags, rb, L, h, pcm32, sigma0 + rb, n_slots, lane);
         }
         __syncwarp();
     }
