@@ -356,7 +356,7 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
     float(*s_x)[kXrFloats] = reinterpret_cast<float(*)[kXrFloats]>(s_base);                 // spectrum staging (short-block path)
     float(*s_ov)[18 * 32] = reinterpret_cast<float(*)[18 * 32]>(s_base + 2 * kXrFloats);   // IMDCT overlap (Frame.store)
     uint32_t(*s_pk)[8] = reinterpret_cast<uint32_t(*)[8]>(s_base + 2 * kXrFloats + 2 * 18 * 32);
-    double(*s_scale)[64] = reinterpret_cast<double(*)[64]>(s_base + 2 * kXrFloats + 2 * 18 * 32 + 16);  // 2^(k/4) per band
+    ScaleEnt(*s_scale)[64] = reinterpret_cast<ScaleEnt(*)[64]>(s_base + 2 * kXrFloats + 2 * 18 * 32 + 16);  // 2^(k/4) per band
 
     int sfb_cfg = -1;      // sampling-rate configuration the lane's band codes below belong to
     uint32_t sfb_q[9];     // long-block scalefactor band of the lane's pairs 9*lane .. 9*lane+8 (fast path)
@@ -415,13 +415,13 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
                         const int p = lane * 9 + q;
                         // a pair at or above count1 is read as (0, 0): powtab34[0] = 0 and scale * 0 = +0
                         const uint32_t wa = p < np0 ? C.isw[0][q] : 0u;
-                        const double sa = s_scale[0][sfb_q[q]];
+                        const ScaleEnt sa = s_scale[0][sfb_q[q]];
                         x0[2 * q] = requant_value(T, sa, (int)(int16_t)(wa & 0xffffu));
                         x0[2 * q + 1] = requant_value(T, sa, (int)(int16_t)(wa >> 16));
                         x1[2 * q] = x1[2 * q + 1] = 0.0f;
                         if (valid_b) {
                             const uint32_t wb = p < np1 ? C.isw[1][q] : 0u;
-                            const double sb = s_scale[1][sfb_q[q]];
+                            const ScaleEnt sb = s_scale[1][sfb_q[q]];
                             x1[2 * q] = requant_value(T, sb, (int)(int16_t)(wb & 0xffffu));
                             x1[2 * q + 1] = requant_value(T, sb, (int)(int16_t)(wb >> 16));
                         }
@@ -500,7 +500,7 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
                         float x0 = 0.0f, x1 = 0.0f;  // lines at or above count1 stay +0 (maindata/huffman.go:130-134)
                         if (p < npair) {
                             const uint32_t w = __ldg(is2 + p);
-                            const double sc = s_scale[ch][e];
+                            const ScaleEnt sc = s_scale[ch][e];
                             x0 = requant_value(T, sc, (int)(int16_t)(w & 0xffffu));
                             x1 = requant_value(T, sc, (int)(int16_t)(w >> 16));
                         }

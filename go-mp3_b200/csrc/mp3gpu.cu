@@ -153,6 +153,7 @@ static int upload_tables(mp3gpu_ctx *ctx) {
     };
     size_t o_pow2 = put(h.pow2q, sizeof h.pow2q);
     size_t o_p34 = put(h.powtab34.data(), h.powtab34.size() * sizeof(double));
+    size_t o_pq4 = put(h.powq4.data(), h.powq4.size() * sizeof(float));
     size_t o_lsl = put(h.line_sfb_long, sizeof h.line_sfb_long);
     size_t o_lss = put(h.line_sfb_short, sizeof h.line_sfb_short);
     size_t o_lws = put(h.line_win_short, sizeof h.line_win_short);
@@ -178,6 +179,8 @@ static int upload_tables(mp3gpu_ctx *ctx) {
     uint8_t *b = (uint8_t *)ctx->d_tab_blob;
     ctx->T.pow2q = (const double *)(b + o_pow2);
     ctx->T.powtab34 = (const double *)(b + o_p34);
+    ctx->T.powq4 = (const float *)(b + o_pq4);
+    ctx->T.pretab_pack = h.pretab_pack;
     ctx->T.line_sfb_long = b + o_lsl;
     ctx->T.line_sfb_short = b + o_lss;
     ctx->T.line_win_short = b + o_lws;

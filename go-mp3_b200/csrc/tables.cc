@@ -157,6 +157,16 @@ void build_host_tables(HostTables &t) {
     // frame.go:36-40
     t.powtab34.resize(8207);
     for (int i = 0; i < 8207; i++) t.powtab34[i] = std::pow((double)i, 4.0 / 3.0);
+    // Requantisation (frame.go:146-155) is float32(2^(k/4) * |is|^(4/3)) with the product taken in float64.  With
+    // k = 4e + q the first factor is 2^e * 2^(q/4) exactly (checked here), and a power of two commutes with both
+    // roundings, so the value is float32(2^(q/4) * |is|^(4/3)) * 2^e: one table row per q and an exact float scale.
+    for (int k = 0; k < kPow2N; k++) {
+        const int k4 = k - kPow2Off, e = k4 >> 2, q = k4 & 3;
+        if (t.pow2q[k] != std::ldexp(t.pow2q[kPow2Off + q], e)) throw std::runtime_error("2^(k/4) is not 2^e * 2^(q/4)");
+    }
+    t.powq4.assign((size_t)4 * kPowRow, 0.0f);
+    for (int q = 0; q < 4; q++)
+        for (int i = 0; i < 8207; i++) t.powq4[(size_t)q * kPowRow + i] = (float)(t.pow2q[kPow2Off + q] * t.powtab34[i]);
     // frame.go:422-425 (decimal literals rounded once to float32)
     const float cs[8] = {0.857493f, 0.881742f, 0.949629f, 0.983315f, 0.995518f, 0.999161f, 0.999899f, 0.999993f};
     const float ca[8] = {-0.514496f, -0.471732f, -0.313377f, -0.181913f, -0.094574f, -0.040966f, -0.014199f, -0.003700f};
@@ -175,6 +185,11 @@ void build_host_tables(HostTables &t) {
     t.is_ratio_r[7] = 1.0f;
     memset(t.pretab, 0, sizeof t.pretab);
     for (int i = 0; i < 22; i++) t.pretab[i] = (uint8_t)kPretab[i];
+    t.pretab_pack = 0;
+    for (int i = 0; i < 22; i++) {
+        if (kPretab[i] > 3) throw std::runtime_error("pretab entry does not fit 2 bits");
+        t.pretab_pack |= (uint64_t)kPretab[i] << (2 * i);
+    }
     for (int a = 0; a < 3; a++)
         for (int b = 0; b < 6; b++)
             for (int c = 0; c < 4; c++) t.sfsize_mpeg2[a][b][c] = (uint8_t)kSfSizeMpeg2[a][b][c];

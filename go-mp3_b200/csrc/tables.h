@@ -17,6 +17,7 @@ namespace mp3gpu {
 
 constexpr int kPow2Off = 336;   // pow2q index = 4*idx + kPow2Off ; 4*idx in [-326, 45]
 constexpr int kPow2N = 400;
+constexpr int kPowRow = 8208;   // row length of powq4 (8,207 values of |is| + padding)
 constexpr int kNumCfg = 6;      // cfg = lsf*3 + sampling_frequency index
 
 // Huffman LUT entry (uint32).  Every tree's root table is indexed by the first kHuffRootBits bits of the code stream.
@@ -39,6 +40,8 @@ struct HostTables {
     float synth_d[512];
     double pow2q[kPow2N];
     std::vector<double> powtab34;  // 8207
+    std::vector<float> powq4;      // [4][kPowRow]: float32(2^(q/4) * powtab34[v]) — requantisation without the f64 multiply
+    uint64_t pretab_pack;          // pretab[sfb] in bits 2*sfb .. 2*sfb+1
     float cs[8], ca[8];
     float is_ratio_l[8], is_ratio_r[8];  // index = is_pos 0..6
     uint8_t pretab[24];

@@ -28,6 +28,7 @@ namespace mp3gpu {
 struct DeviceTables {
     const double *pow2q;            // [kPow2N], index 4*idx + pow2_off
     const double *powtab34;         // [8207]
+    const float *powq4;             // [4][kPowRow] float32(2^(q/4) * powtab34[v]), tables.cc
     const uint8_t *line_sfb_long;   // [6][576]
     const uint8_t *line_sfb_short;  // [6][576]
     const uint8_t *line_win_short;  // [6][576]
@@ -48,6 +49,7 @@ struct DeviceTables {
     const uint8_t *slen_mpeg1;      // [16][2]
     const float *cs;                // [8]
     const float *ca;                // [8]
+    uint64_t pretab_pack;           // pretab[sfb] in bits 2*sfb .. 2*sfb+1
     int huff_lut_n;
     int pow2_off;
 };
@@ -472,50 +474,49 @@ MP3_HD GranuleChan make_chan(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t met
     return c;
 }
 
-// Requantise line i (frame.go:140-255) and return its position after reorder (frame.go:257-302).
-// Lines at or above count1 hold 0 (rzero) and requantise to +0.0 exactly as the untouched zeros
-// of the reference do.
-MP3_HD float requant_line(const DeviceTables &T, int cfg, const GranuleChan &c, const uint32_t *pk, int i, int is_val, int *dst) {
-    const int mult = u_sfscale(c.w2) ? 4 : 2;  // 4 * sfMult
-    const int gg = u_ggain(c.w0) - 210;
-    int v = i < c.cnt1 ? is_val : 0;
-    int k4;
-    if (c.is_short && (!c.mixed || i >= 36)) {
-        int sfb = T.line_sfb_short[cfg * 576 + i], win = T.line_win_short[cfg * 576 + i];
-        k4 = gg - 8 * u_sbg(c.w2, win) - mult * sf_nib(pk, 22 + sfb * 3 + win);
-        *dst = T.reorder_dst[cfg * 576 + i];
-    } else {
-        int sfb = T.line_sfb_long[cfg * 576 + i];
-        k4 = gg - mult * (sf_nib(pk, sfb) + c.preflag * (int)T.pretab[sfb]);
-        *dst = i;
-    }
-    double a = T.powtab34[v < 0 ? -v : v];
-    return d_mul_to_f(T.pow2q[k4 + T.pow2_off], v < 0 ? -a : a);
-}
-
-
 // ---- K2, scale-table form ------------------------------------------------------------------------
 // The requantisation exponent is constant per scalefactor band (long) or per band x window (short), so K2
 // first tabulates 2^(k/4) per band (64 doubles: [0..21] long sfb, [24..62] short sfb*3+win) and then handles
 // the lines two at a time: every band boundary is even, so lines 2p and 2p+1 share their table entry.
 constexpr int kScaleShortBase = 24;
 
-// Table entry e of one channel (frame.go:146-148 long, :161-166 short); 0 where the entry is not used.
-MP3_HD double scale_entry(const DeviceTables &T, const GranuleChan &c, const uint32_t *pk, int e) {
+// Table entry e of one channel (frame.go:146-148 long, :161-166 short): the scale 2^(k4/4), k4 = 4e + q, as the exact
+// float 2^e and the row q of powq4 (tables.cc); {0, row 0} where the entry is not used.
+constexpr int kPowRowLen = 8208;  // == tables.h kPowRow
+struct ScaleEnt {
+    float s;
+    uint32_t row;
+};
+MP3_HD float exp2_int(int e) {  // 2^e, -126 <= e <= 127
+#if defined(__CUDA_ARCH__)
+    return __int_as_float((e + 127) << 23);
+#else
+    union { uint32_t u; float f; } c;
+    c.u = (uint32_t)(e + 127) << 23;
+    return c.f;
+#endif
+}
+MP3_HD ScaleEnt scale_entry(const DeviceTables &T, const GranuleChan &c, const uint32_t *pk, int e) {
     const int mult = u_sfscale(c.w2) ? 4 : 2;  // 4 * sfMult
     const int gg = u_ggain(c.w0) - 210;
+    ScaleEnt r;
+    r.s = 0.0f;
+    r.row = 0;
     int k4;
     if (e < 22) {
-        if (c.is_short && !c.mixed) return 0.0;
-        k4 = gg - mult * (sf_nib(pk, e) + c.preflag * (int)T.pretab[e]);
+        if (c.is_short && !c.mixed) return r;
+        const int pre = (int)((T.pretab_pack >> (2 * e)) & 3);
+        k4 = gg - mult * (sf_nib(pk, e) + c.preflag * pre);
     } else if (e >= kScaleShortBase && e < kScaleShortBase + 39) {
-        if (!c.is_short) return 0.0;
+        if (!c.is_short) return r;
         const int code = e - kScaleShortBase, win = code % 3;
         k4 = gg - 8 * u_sbg(c.w2, win) - mult * sf_nib(pk, 22 + code);
     } else {
-        return 0.0;
+        return r;
     }
-    return T.pow2q[k4 + T.pow2_off];
+    r.s = exp2_int(k4 >> 2);  // k4 >= -338: far above the float exponent range's lower end
+    r.row = (uint32_t)(k4 & 3) * kPowRowLen;
+    return r;
 }
 
 // Table index and reorder destinations of the pair of lines (2p, 2p+1) (frame.go:257-302).
@@ -530,10 +531,11 @@ MP3_HD int pair_lookup(const DeviceTables &T, int cfg, const GranuleChan &c, int
     return T.pair_long[cfg * 288 + p];
 }
 
-// One requantised line: sign(is) * |is|^(4/3) * scale, in double, rounded once (frame.go:146-155).
-MP3_HD float requant_value(const DeviceTables &T, double scale, int v) {
-    // the sign is applied after the single rounding: round-to-nearest is symmetric, so float32(s * -a) == -float32(s * a)
-    const float r = d_mul_to_f(scale, T.powtab34[v < 0 ? -v : v]);
+// One requantised line: sign(is) * float32(|is|^(4/3) * 2^(k4/4)) (frame.go:146-155; the reference multiplies in
+// float64 and rounds once — the table row holds that product for 2^(q/4), the power of two is exact).
+MP3_HD float requant_value(const DeviceTables &T, ScaleEnt sc, int v) {
+    // the sign is applied after the rounding: round-to-nearest is symmetric, so float32(s * -a) == -float32(s * a)
+    const float r = f_mul(T.powq4[sc.row + (uint32_t)(v < 0 ? -v : v)], sc.s);
     return v < 0 ? -r : r;
 }
 

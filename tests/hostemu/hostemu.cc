@@ -23,6 +23,8 @@ void ensure() {
     HostTables &h = *g_h;
     g_T.pow2q = h.pow2q;
     g_T.powtab34 = h.powtab34.data();
+    g_T.powq4 = h.powq4.data();
+    g_T.pretab_pack = h.pretab_pack;
     g_T.line_sfb_long = &h.line_sfb_long[0][0];
     g_T.line_sfb_short = &h.line_sfb_short[0][0];
     g_T.line_win_short = &h.line_win_short[0][0];
@@ -91,7 +93,7 @@ void emu_requant(const mp3gpu_unit *units, long long n_granules, const int16_t *
         c[0] = make_chan(ug[0].w0, ug[0].w1, ug[0].w2, meta[g * 2]);
         c[1] = make_chan(ug[1].w0, ug[1].w1, ug[1].w2, valid_b ? meta[g * 2 + 1] : 0u);
         float *x[2] = {x0, x1};
-        double scale[2][64];
+        ScaleEnt scale[2][64];
         for (int ch = 0; ch < 2; ch++) {
             if (ch == 1 && !valid_b) break;
             for (int e = 0; e < 64; e++) scale[ch][e] = scale_entry(g_T, c[ch], pk[ch], e);
