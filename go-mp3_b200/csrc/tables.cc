@@ -262,7 +262,7 @@ void build_host_tables(HostTables &t) {
             LutBuilder b(t.huff_lut, d.codes, d.n, tab >= 32, d.linbits != 0);
             if (b.base * 4 > 0xffffff) throw std::runtime_error("huffman LUT base overflow");
             t.huff_lut.resize(t.huff_lut.size() + ((size_t)1 << kHuffRootBits), 0);
-            b.fill(0, kHuffRootBits, 0, 0, 6);
+            b.fill(0, kHuffRootBits, 0, 0, 11);  // 19 - 8: every sub-table resolves the rest of its codes, so there are two levels at most
             desc = (uint32_t)b.base * 4u;
             seen[nseen] = d.codes;
             seen_desc[nseen] = desc;

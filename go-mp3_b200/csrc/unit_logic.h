@@ -187,12 +187,9 @@ MP3_HD uint32_t lut_at(const uint32_t *lut, uint32_t byte_off) {
 // Leaf entry of the code word at the head of w (MSB first); d = byte offset of the tree's root table.
 MP3_HD uint32_t huff_lookup(const uint32_t *lut, uint32_t d, uint32_t w) {
     uint32_t e = lut_at(lut, d + ((w >> (32 - kRootBits)) << 2));
-    int used = kRootBits;
-    while ((int32_t)e < 0) {  // rare: code longer than the root index
-        const int sb = (int)((e >> 16) & 0x1f);
-        const uint32_t idx = (e & 0xffff) + ((w << used) >> (32 - sb));
+    if ((int32_t)e < 0) {  // code longer than the root index: one sub-table resolves the rest (tables.cc)
+        const uint32_t idx = (e & 0xffff) + funnel_l(0u, w << kRootBits, (int)((e >> 16) & 31));
         e = lut_at(lut, d + (idx << 2));
-        used += sb;
     }
     return e;
 }
@@ -266,25 +263,51 @@ struct PairSink {
 
 MP3_HD void sf_put(uint32_t *pk, int n, int v) { pk[n >> 3] |= (uint32_t)v << (4 * (n & 7)); }
 MP3_HD int sf_nib(const uint32_t *pk, int n) { return (int)((pk[n >> 3] >> (4 * (n & 7))) & 0xf); }
+// Sequential nibble writer: a word is stored once, when it is complete (or at flush), so that K1's scalefactor loops
+// carry no load-modify-store chain through the (local-memory) pk array.  pk must start zeroed, and every word is
+// written by one run of consecutive nibbles only (true for all callers: long 0..20, mixed 0..7 then 31..57, short 22..57).
+struct NibWriter {
+    uint32_t *pk;
+    uint32_t acc;
+    int n;
+    MP3_HD void init(uint32_t *p, int n0) { pk = p; acc = 0; n = n0; }
+    MP3_HD void put(int v) {
+        acc |= (uint32_t)v << (4 * (n & 7));
+        n++;
+        if ((n & 7) == 0) {
+            pk[(n >> 3) - 1] = acc;
+            acc = 0;
+        }
+    }
+    MP3_HD void flush() {
+        if (n & 7) pk[n >> 3] = acc;
+        acc = 0;
+    }
+    MP3_HD void seek(int n1) { flush(); n = n1; }
+};
 
 // Scalefactors of an MPEG-1 unit that reads all of them itself: gr 0, or gr 1 short blocks, or
 // gr 1 with no scfsi band set (maindata.go:204-232 and the read arms of :233-279).
 MP3_HD void sf_mpeg1_read_all(const DeviceTables &T, BitCursor &bc, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t *pk) {
     int sfc = u_sfcomp(w1) & 15;
     int slen1 = T.slen_mpeg1[sfc * 2], slen2 = T.slen_mpeg1[sfc * 2 + 1];
+    NibWriter nw;
+    nw.init(pk, 0);
     if (u_winsw(w0) == 1 && u_btype(w0) == 2) {
         int sfb0 = 0;
         if (u_mixed(w2)) {
 #pragma unroll 1
-            for (int sfb = 0; sfb < 8; sfb++) sf_put(pk, sfb, bc.bits(slen1));
+            for (int sfb = 0; sfb < 8; sfb++) nw.put(bc.bits(slen1));
             sfb0 = 3;
         }
+        nw.seek(22 + sfb0 * 3);
 #pragma unroll 1
-        for (int n = sfb0 * 3; n < 36; n++) sf_put(pk, 22 + n, bc.bits(n < 18 ? slen1 : slen2));
+        for (int n = sfb0 * 3; n < 36; n++) nw.put(bc.bits(n < 18 ? slen1 : slen2));
     } else {
 #pragma unroll 1
-        for (int sfb = 0; sfb < 21; sfb++) sf_put(pk, sfb, bc.bits(sfb < 11 ? slen1 : slen2));
+        for (int sfb = 0; sfb < 21; sfb++) nw.put(bc.bits(sfb < 11 ? slen1 : slen2));
     }
+    nw.flush();
 }
 
 // K1 for one unit, in two stages so that a CTA can re-deal its units to threads in between (kernels.cuh):
@@ -351,7 +374,9 @@ MP3_HD uint32_t huffman_stage_a(const DeviceTables &T, const uint32_t *lut, cons
             if (u_mixed(w2)) n++;
         }
         int d = (slen >> 12) & 7;
-        int idx = 0;
+        // long blocks fill scalefac_l[idx]; short fill scalefac_s[idx/3][idx%3] (maindata.go:169-179)
+        NibWriter nw;
+        nw.init(pk, n == 0 ? 0 : 22);
 #pragma unroll 1
         for (int i = 0; i < 4; i++) {
             int num = slen & 7;
@@ -360,12 +385,10 @@ MP3_HD uint32_t huffman_stage_a(const DeviceTables &T, const uint32_t *lut, cons
 #pragma unroll 1
             for (int k = 0; k < cnt; k++) {
                 int v = num > 0 ? bc.bits(num) : 0;
-                // long blocks fill scalefac_l[idx]; short fill scalefac_s[idx/3][idx%3] (maindata.go:169-179)
-                int nib = (n == 0) ? idx : 22 + idx;
-                if (nib < 64) sf_put(pk, nib, v);
-                idx++;
+                if (nw.n < 64) nw.put(v);
             }
         }
+        if (nw.n < 64) nw.flush();
     } else if (u_gr(w2) == 0 || (u_winsw(w0) == 1 && u_btype(w0) == 2) || u_scfsi(w2) == 0) {
         sf_mpeg1_read_all(T, bc, w0, w1, w2, pk);
     } else {
@@ -381,6 +404,8 @@ MP3_HD uint32_t huffman_stage_a(const DeviceTables &T, const uint32_t *lut, cons
         int sfc = u_sfcomp(w1) & 15;
         int slen1 = T.slen_mpeg1[sfc * 2], slen2 = T.slen_mpeg1[sfc * 2 + 1];
         int scfsi = u_scfsi(w2);
+        NibWriter nw;
+        nw.init(pk, 0);
 #pragma unroll 1
         for (int sfb = 0; sfb < 21; sfb++) {
             int band = sfb < 6 ? 0 : (sfb < 11 ? 1 : (sfb < 16 ? 2 : 3));
@@ -389,8 +414,9 @@ MP3_HD uint32_t huffman_stage_a(const DeviceTables &T, const uint32_t *lut, cons
                 v = sf_nib(pk0, sfb);
             else
                 v = bc.bits(sfb < 11 ? slen1 : slen2);
-            sf_put(pk, sfb, v);
+            nw.put(v);
         }
+        nw.flush();
     }
 
     // ---- part 3: Huffman (maindata/huffman.go:27-138), whole groups of four pairs ---------------
