@@ -36,12 +36,16 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "decoded_stereo_pcm_msamples_per_s"
 UNIT = "Msamples/s"
 
-# Algorithmic work per granule-channel (SURVEY.md 8d / DESIGN.md): bytes each kernel must move and flops of the
-# reference's direct forms (long blocks).  bits = main-data bytes per unit, measured from the batch.
-# k_hybrid = K2 (requantise 576 + MS 1,152 + alias 744) + K3 (IMDCT 41,472 + window 1,152 + overlap 576);
-# k_synth = K4 (matrixing 73,728 + window 9,216 + 16-tap sums 9,216): flop counts of the reference's direct forms.
-# The kernels execute fewer (bitwise-exact table symmetries halve the IMDCT and matrixing multiply-adds).
-FLOPS = {"k1_huffman": 0.0, "k_hybrid": 2472.0 + 43200.0, "k_synth": 92160.0}
+# Algorithmic work per granule-channel (SURVEY.md 8d / DESIGN.md): bytes each kernel must move, and flops.
+# bits = main-data bytes per unit, measured from the batch.
+# FLOPS_REFERENCE = the reference's direct forms (long blocks): k_hybrid = K2 (requantise 576 + MS 1,152 + alias 744)
+#   + K3 (IMDCT 41,472 + window 1,152 + overlap 576); k_synth = K4 (matrixing 73,728 + window 9,216 + sums 9,216).
+# FLOPS = what the shipped (fused-multiply-add) build executes: K3 is an 18-point DCT-IV through two 9-point DCT-IIIs
+#   (258 flops per subband incl. window and overlap-add), K4's matrixing a 32-point Lee DCT (80 mul + 209 add per
+#   slot) followed by the 512-tap window (1,024 flops) and the scale (2).  fp32 fractions use FLOPS; the roofline
+#   picks, per kernel, whichever of HBM and FP32 it sits closer to.
+FLOPS_REFERENCE = {"k1_huffman": 0.0, "k_hybrid": 2472.0 + 43200.0, "k_synth": 92160.0}
+FLOPS = {"k1_huffman": 0.0, "k_hybrid": 2472.0 + 32 * 258.0, "k_synth": 18 * (289.0 + 1024.0 + 2.0)}
 
 
 def kernel_bytes(main_bytes_per_unit):
@@ -365,7 +369,8 @@ def run_ours(args, rank, world, local_rank):
         gbs = kb[k] * n_units_valid / (ms * 1e-3) / 1e9
         tfs = FLOPS[k] * n_units_valid / (ms * 1e-3) / 1e12
         kernels[k] = {"ms_per_step": ms, "ms_per_launch": per_launch_ms, "share": ms / step_kernel_ms,
-                      "alg_bytes_per_unit": kb[k], "alg_flops_per_unit": FLOPS[k], "hbm_gbs": gbs,
+                      "alg_bytes_per_unit": kb[k], "alg_flops_per_unit": FLOPS[k],
+                      "reference_direct_form_flops_per_unit": FLOPS_REFERENCE[k], "hbm_gbs": gbs,
                       "hbm_frac": gbs / hbm_peak, "fp32_tflops": tfs, "fp32_frac": tfs / fp32_peak}
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
     kd = kernels[dom]

@@ -712,7 +712,6 @@ __device__ __forceinline__ void matrix_slot(const float (&s)[32], float *urow) {
 //   out[i] = sum_d V_{t-d}[(d odd ? 32 : 0) + i] * D[32 d + i], d = 0..15 (U construction, frame.go:651-661).
 // Slot t-d lives at circular position (P - d) mod 15: when slot t arrives at position P, its V[i] part is stored
 // before the sum and its V[32+i] part after it, because that place still holds slot t-15's, the d = 15 tap.
-#if MP3GPU_EXACT
 struct SynHist {
     float A[2][15], B[2][15];  // [channel][position]: V[i] and V[32+i] of the slot at that position
     float dw[16];
@@ -733,30 +732,9 @@ struct SynHist {
         return acc;
     }
 };
-#else
-// Fast build: taps (d, d+1), d even, are one packed FFMA2 — half the issue slots on the same FMA pipe.  The pair
-// (V_{t-d}[i], V_{t-d-1}[32+i]) is (slot at position j, slot at position j-1) for every P, so it can live in one
-// 64-bit register pair H[j]; the coefficient pair (D[32d+i], D[32(d+1)+i]) is adjacent anyway.  Even and odd taps
-// accumulate in two chains that are added at the end (a different rounding order than the reference's single chain;
-// the exact build keeps that one).
-struct SynHist {
-    float2 H[2][15];  // [channel][j] = (V[i] of the slot at position j, V[32+i] of the slot at position j-1)
-    float2 dw2[8];
-    __device__ __forceinline__ void set_coef(int d, float v) { if (d & 1) dw2[d >> 1].y = v; else dw2[d >> 1].x = v; }
-    __device__ __forceinline__ void clear() {
-#pragma unroll
-        for (int i = 0; i < 15; i++) { H[0][i] = make_float2(0.f, 0.f); H[1][i] = make_float2(0.f, 0.f); }
-    }
-    template <int P, int CH> __device__ __forceinline__ void put_a(float a) { H[CH][P].x = a; }
-    template <int P, int CH> __device__ __forceinline__ void put_b(float b) { H[CH][(P + 1) % 15].y = b; }
-    template <int P, int CH> __device__ __forceinline__ float sum() const {
-        float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int d = 0; d < 16; d += 2) acc = __ffma2_rn(H[CH][(P - d + 30) % 15], dw2[d >> 1], acc);
-        return acc.x + acc.y;
-    }
-};
-#endif
+// (Measured and dropped: pairing taps (d, d+1) into packed FFMA2, and two scalar chains per channel.  Both leave the
+// kernel time unchanged within 1 %: with three warps per scheduler the window phase waits on the FMA pipe and on
+// fixed-latency dependencies, not on issue slots.)
 
 struct SynLane {  // where lane i finds V[i] and V[32+i] in a U row
     int ai, bi;

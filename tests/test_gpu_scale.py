@@ -40,7 +40,7 @@ def test_batch_position_independence_and_oracle_spot_checks(pkg):
         worst = max(worst, mx)
         fracs.append(frac)
     print(f"max|diff| = {worst} LSB, exact-match fraction min {min(fracs):.6f}")
-    assert worst <= 1 and min(fracs) > 0.999   # tolerance: +-1 LSB of int16
+    assert worst <= 1 and min(fracs) > 0.998   # tolerance: +-1 LSB of int16; measured 0.99931 (fast DCT + fast IMDCT + FFMA)
     big.close(); small.close()
 
 
