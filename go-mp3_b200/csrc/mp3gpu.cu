@@ -436,6 +436,7 @@ extern "C" int mp3gpu_decode(mp3gpu_ctx *ctx, const uint8_t *main_data, size_t m
         ctx->err = "null pointer";
         return MP3GPU_E_INVALID;
     }
+
     int rc = ensure_cap(ctx, &ctx->d_main, &ctx->d_main_cap, main_data_len + 64);
     if (rc) return rc;
     rc = ensure_cap(ctx, (uint8_t **)&ctx->d_units, &ctx->d_units_cap, n_granules * 2 * sizeof(mp3gpu_unit));

@@ -180,6 +180,12 @@ struct BitCursor {
 };
 
 // ---- Huffman code words (LUT entry layout: tables.h) -------------------------------------------------------------
+// the top (n mod 32) bits of x, as a number
+#if defined(__CUDA_ARCH__)
+MP3_HD uint32_t hi_bits_mod32(uint32_t x, uint32_t n) { return __funnelshift_l(x, 0u, n); }
+#else
+MP3_HD uint32_t hi_bits_mod32(uint32_t x, uint32_t n) { n &= 31; return n ? x >> (32 - n) : 0u; }
+#endif
 constexpr int kRootBits = 8;  // == tables.h kHuffRootBits
 MP3_HD uint32_t lut_at(const uint32_t *lut, uint32_t byte_off) {
     return *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(lut) + byte_off);
@@ -188,13 +194,17 @@ MP3_HD uint32_t lut_at(const uint32_t *lut, uint32_t byte_off) {
 MP3_HD uint32_t huff_lookup(const uint32_t *lut, uint32_t d, uint32_t w) {
     uint32_t e = lut_at(lut, d + ((w >> (32 - kRootBits)) << 2));
     if ((int32_t)e < 0) {  // code longer than the root index: one sub-table resolves the rest (tables.cc)
-        const uint32_t idx = (e & 0xffff) + funnel_l(0u, w << kRootBits, (int)((e >> 16) & 31));
+        const uint32_t idx = (e & 0xffff) + hi_bits_mod32(w << kRootBits, e >> 16);
         e = lut_at(lut, d + (idx << 2));
     }
     return e;
 }
 // x << (n mod 32): the LUT's shift-count fields are used without masking their neighbours off
+#if defined(__CUDA_ARCH__)
+MP3_HD uint32_t shl_mod32(uint32_t x, uint32_t n) { return __funnelshift_l(0u, x, n); }  // the funnel shift wraps its count itself
+#else
 MP3_HD uint32_t shl_mod32(uint32_t x, uint32_t n) { return funnel_l(x, 0u, (int)(n & 31)); }
+#endif
 
 // One big_values pair (huffman.go:404-416).  Returns x | y<<16 (int16 halves).  linbits() is only evaluated for an
 // escape (x or y == 15 in a table with linbits).
@@ -320,7 +330,8 @@ MP3_HD void sf_mpeg1_read_all(const DeviceTables &T, BitCursor &bc, uint32_t w0,
 // instead of K1 writing zeros.
 struct HuffRegions {  // region starts in PAIRS (all sfb boundaries are even) and the three trees
     int r1h, r2h, nbig;
-    uint32_t e0, e1, e2;  // huff_desc of the three regions
+    uint32_t d0, d1, d2;  // byte offset of the root table of each region's tree
+    uint32_t lin;         // linbits of the three regions, 4 bits each
 };
 MP3_HD HuffRegions huff_regions(const DeviceTables &T, const uint32_t *huff_desc, uint32_t w0, uint32_t w1, uint32_t w2) {
     HuffRegions R;
@@ -336,15 +347,17 @@ MP3_HD HuffRegions huff_regions(const DeviceTables &T, const uint32_t *huff_desc
     }
     R.nbig = u_bigval(w0);
     if (R.nbig > 288) R.nbig = 288;  // the host rejects such frames (huffman.go:68-70); never reached
-    R.e0 = huff_desc[u_tsel(w1, 0)];
-    R.e1 = huff_desc[u_tsel(w1, 1)];
-    R.e2 = huff_desc[u_tsel(w1, 2)];
+    const uint32_t e0 = huff_desc[u_tsel(w1, 0)], e1 = huff_desc[u_tsel(w1, 1)], e2 = huff_desc[u_tsel(w1, 2)];
+    R.d0 = e0 & 0xffffffu;
+    R.d1 = e1 & 0xffffffu;
+    R.d2 = e2 & 0xffffffu;
+    R.lin = (e0 >> 24) | ((e1 >> 24) << 4) | ((e2 >> 24) << 8);
     return R;
 }
 MP3_HD uint32_t huff_pair_at(const uint32_t *lut, const HuffRegions &R, int k, BitCursor &bc) {
     const bool in0 = k < R.r1h, in1 = k < R.r2h;
-    return huff_pair(lut, (in0 ? R.e0 : (in1 ? R.e1 : R.e2)) & 0xffffffu,
-                     [&] { return (int)((in0 ? R.e0 : (in1 ? R.e1 : R.e2)) >> 24); }, bc);
+    return huff_pair(lut, in0 ? R.d0 : (in1 ? R.d1 : R.d2),
+                     [&] { return (int)((R.lin >> (in0 ? 0 : (in1 ? 4 : 8))) & 0xf); }, bc);
 }
 
 // State handed from stage A to stage B: bits 0..29 logical cursor position (relative to bit_start), bit 30 preflag,
