@@ -76,52 +76,63 @@ struct WaveBufs {
 // sort balanced better but lost that locality and was slower on VBR streams.)
 constexpr int kHuffThreads = 256;
 
+// The grid is persistent (a few CTAs per SM, each walking tiles of 256 units with a grid stride), so the 33 KB of code
+// tables are staged into shared memory once per CTA and not once per tile.
 __global__ void __launch_bounds__(kHuffThreads)
 k_huffman(const uint8_t *__restrict__ main_data, unsigned long long main_bits, const mp3gpu_unit *__restrict__ units,
           long long first_unit, int n_units, DeviceTables T, WaveBufs B) {
-    extern __shared__ uint32_t s_lut[];
+    extern __shared__ __align__(16) uint32_t s_lut[];
     __shared__ uint64_t s_quad[256];
     __shared__ uint32_t s_desc[34];
     __shared__ unsigned int s_bin[40];
     __shared__ uint16_t s_order[kHuffThreads];
-    for (int i = threadIdx.x; i < T.huff_lut_n; i += blockDim.x) s_lut[i] = T.huff_lut[i];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(T.huff_lut);  // huff_lut_n is a multiple of 4 (tables.cc)
+        uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
+#pragma unroll 4
+        for (int i = threadIdx.x; i < T.huff_lut_n / 4; i += kHuffThreads) dst[i] = __ldg(src + i);
+    }
     if (threadIdx.x < 34) s_desc[threadIdx.x] = T.huff_desc[threadIdx.x];
     s_quad[threadIdx.x] = T.quad_signs[threadIdx.x];  // kHuffThreads == 256
-    if (threadIdx.x < 40) s_bin[threadIdx.x] = 0;
-    __syncthreads();
-    // ---- work order inside the CTA ----------------------------------------------------------------
-    const int base = blockIdx.x * kHuffThreads;
-    int key = 38;  // beyond the wave
-    {
-        const int ul0 = base + threadIdx.x;
-        if (ul0 < n_units) {
-            const mp3gpu_unit *u = units + first_unit + ul0;
-            const uint32_t w0 = __ldg(&u->w0), w2 = __ldg(&u->w2);
-            key = !u_valid(w2) ? 37 : 36 - ((u_p23len(w0) == 0 ? 0 : imin(u_bigval(w0), 288)) >> 3);
+    const int n_tiles = (n_units + kHuffThreads - 1) / kHuffThreads;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (threadIdx.x < 40) s_bin[threadIdx.x] = 0;
+        __syncthreads();  // also: the previous tile's s_order reads are done, the tables are staged
+        // ---- work order inside the tile ------------------------------------------------------------
+        const int base = tile * kHuffThreads;
+        int key = 38;  // beyond the wave
+        {
+            const int ul0 = base + threadIdx.x;
+            if (ul0 < n_units) {
+                const mp3gpu_unit *u = units + first_unit + ul0;
+                const uint32_t w0 = __ldg(&u->w0), w2 = __ldg(&u->w2);
+                key = !u_valid(w2) ? 37 : 36 - ((u_p23len(w0) == 0 ? 0 : imin(u_bigval(w0), 288)) >> 3);
+            }
         }
+        const unsigned int rank = atomicAdd(&s_bin[key], 1u);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int acc = 0;
+            for (int i = 0; i < 39; i++) { const unsigned int c = s_bin[i]; s_bin[i] = acc; acc += c; }
+        }
+        __syncthreads();
+        s_order[s_bin[key] + rank] = (uint16_t)threadIdx.x;
+        __syncthreads();
+        const int ul = base + s_order[threadIdx.x];  // wave-local unit index
+        if (ul >= n_units) continue;
+        if (!u_valid(units[first_unit + ul].w2)) {
+            B.meta[ul] = 0;
+            continue;
+        }
+        uint32_t pk[8];
+        uint32_t *out = reinterpret_cast<uint32_t *>(B.is16 + (size_t)ul * 576);
+        uint32_t meta = huffman_unit(T, s_lut, s_desc, s_quad, main_data, main_bits, units, first_unit + ul, pk, out);
+        uint4 *dst = reinterpret_cast<uint4 *>(B.sfpack + (size_t)ul * 8);
+        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        B.meta[ul] = meta;
     }
-    const unsigned int rank = atomicAdd(&s_bin[key], 1u);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int acc = 0;
-        for (int i = 0; i < 39; i++) { const unsigned int c = s_bin[i]; s_bin[i] = acc; acc += c; }
-    }
-    __syncthreads();
-    s_order[s_bin[key] + rank] = (uint16_t)threadIdx.x;
-    __syncthreads();
-    const int ul = base + s_order[threadIdx.x];  // wave-local unit index
-    if (ul >= n_units) return;
-    if (!u_valid(units[first_unit + ul].w2)) {
-        B.meta[ul] = 0;
-        return;
-    }
-    uint32_t pk[8];
-    uint32_t *out = reinterpret_cast<uint32_t *>(B.is16 + (size_t)ul * 576);
-    uint32_t meta = huffman_unit(T, s_lut, s_desc, s_quad, main_data, main_bits, units, first_unit + ul, pk, out);
-    uint4 *dst = reinterpret_cast<uint4 *>(B.sfpack + (size_t)ul * 8);
-    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-    B.meta[ul] = meta;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -40,6 +40,7 @@ struct mp3gpu_ctx {
     void *d_tab_blob = nullptr;
     DeviceTables T{};
     int lut_bytes = 0;
+    int huff_ctas_per_sm = 1;  // resident k_huffman CTAs per SM (occupancy query): the persistent grid is sm_count times this
     // workspace for one wave (+1 granule look-back where needed)
     int16_t *d_is16 = nullptr;
     uint32_t *d_meta = nullptr;
@@ -242,6 +243,8 @@ extern "C" int mp3gpu_create(int device, const mp3gpu_opts *opts, mp3gpu_ctx **o
         for (int i = 0; i < 4; i++) CK(cudaEventCreate(&ctx->ev_copy[i]));
         for (int i = 0; i < 8; i++) CK(cudaEventCreate(&ctx->ev_user[i]));
         CK(cudaFuncSetAttribute(k_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->lut_bytes));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->huff_ctas_per_sm, k_huffman, kHuffThreads, (size_t)ctx->lut_bytes));
+        if (ctx->huff_ctas_per_sm < 1) ctx->huff_ctas_per_sm = 1;
         CK(cudaFuncSetAttribute(k_hybrid<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHybSmemBytes));
         CK(cudaFuncSetAttribute(k_hybrid<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHybSmemBytes));
         CK(cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, kSynSmemBytes));
@@ -304,7 +307,8 @@ static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, size_t main_len, 
     if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][0], s));
     {
         const int nu = 2 * n;
-        k_huffman<<<(nu + kHuffThreads - 1) / kHuffThreads, kHuffThreads, ctx->lut_bytes, s>>>(d_main, (unsigned long long)main_len * 8ull, d_units, first * 2, nu, ctx->T, B);
+        const int tiles = (nu + kHuffThreads - 1) / kHuffThreads;
+        k_huffman<<<std::min(tiles, ctx->sm_count * ctx->huff_ctas_per_sm), kHuffThreads, ctx->lut_bytes, s>>>(d_main, (unsigned long long)main_len * 8ull, d_units, first * 2, nu, ctx->T, B);
     }
     if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][1], s));
     {

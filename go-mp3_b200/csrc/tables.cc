@@ -270,6 +270,7 @@ void build_host_tables(HostTables &t) {
         }
         t.huff_desc[tab] = desc | ((uint32_t)d.linbits << 24);
     }
+    while (t.huff_lut.size() % 4) t.huff_lut.push_back(0);  // staged 16 bytes at a time (k_huffman)
     // count1 sign expansion: index = pattern << 4 | the four bits after the tree bits; value = the two output words
     // (v | w << 16) and (x | y << 16) << 32 with the sign bits dealt to the non-zero values in order (huffman.go:387-403)
     for (int q = 0; q < 16; q++)

@@ -405,14 +405,20 @@ MP3_HD uint32_t huffman_stage_a(const DeviceTables &T, const uint32_t *lut, cons
     } else if (u_gr(w2) == 0 || (u_winsw(w0) == 1 && u_btype(w0) == 2) || u_scfsi(w2) == 0) {
         sf_mpeg1_read_all(T, bc, w0, w1, w2, pk);
     } else {
-        // gr 1, long-type block, at least one scfsi band set: those bands copy ScalefacL[0][ch]
-        // as gr 0's parse left it (zeros if gr 0 was short; sfb 0-7 only if gr 0 was mixed).
-        uint32_t pk0[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        // gr 1, long-type block, at least one scfsi band set: those bands copy ScalefacL[0][ch] as gr 0's parse left it
+        // (21 values if gr 0 was a long-type block, sfb 0-7 only if it was mixed, zeros if it was short).  gr 0's
+        // scalefactor bits are re-read by a second cursor in step with this unit's own.
+        int n0 = 0, s1_0 = 0, s2_0 = 0;
+        BitCursor b0;
+        b0.init(main_data, main_bits, 0, 0);
         if (unit_index >= 2) {  // a submission always starts on a frame boundary; guard against one that does not
             const mp3gpu_unit u0 = units[unit_index - 2];
-            BitCursor b0;
+            const bool short0 = u_winsw(u0.w0) == 1 && u_btype(u0.w0) == 2;
+            n0 = short0 ? (u_mixed(u0.w2) ? 8 : 0) : 21;
+            const int sfc0 = u_sfcomp(u0.w1) & 15;
+            s1_0 = T.slen_mpeg1[sfc0 * 2];
+            s2_0 = T.slen_mpeg1[sfc0 * 2 + 1];
             b0.init(main_data, main_bits, u0.bit_start, u0.buf_end_rel);
-            sf_mpeg1_read_all(T, b0, u0.w0, u0.w1, u0.w2, pk0);
         }
         int sfc = u_sfcomp(w1) & 15;
         int slen1 = T.slen_mpeg1[sfc * 2], slen2 = T.slen_mpeg1[sfc * 2 + 1];
@@ -422,9 +428,10 @@ MP3_HD uint32_t huffman_stage_a(const DeviceTables &T, const uint32_t *lut, cons
 #pragma unroll 1
         for (int sfb = 0; sfb < 21; sfb++) {
             int band = sfb < 6 ? 0 : (sfb < 11 ? 1 : (sfb < 16 ? 2 : 3));
+            const int v0 = sfb < n0 ? b0.bits(sfb < 11 ? s1_0 : s2_0) : 0;
             int v;
             if ((scfsi >> band) & 1)
-                v = sf_nib(pk0, sfb);
+                v = v0;
             else
                 v = bc.bits(sfb < 11 ? slen1 : slen2);
             nw.put(v);
