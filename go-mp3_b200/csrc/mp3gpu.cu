@@ -217,6 +217,7 @@ extern "C" int mp3gpu_create(int device, const mp3gpu_opts *opts, mp3gpu_ctx **o
     ctx->device = device;
     if (opts) ctx->opts = *opts;
     ctx->wave = ctx->opts.wave_granules ? ctx->opts.wave_granules : 2097152u;
+    if (ctx->wave > (1u << 24)) ctx->wave = 1u << 24;  // the kernels index a wave's units and time slots with 32-bit integers
     auto fail = [&](int rc) {
         fprintf(stderr, "mp3gpu_create: %s\n", ctx->err.c_str());
         mp3gpu_destroy(ctx);

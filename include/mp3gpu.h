@@ -109,7 +109,7 @@ typedef struct mp3gpu_unit {
 
 typedef struct mp3gpu_opts {
     uint32_t abi_version;       /* MP3GPU_ABI_VERSION */
-    uint32_t wave_granules;     /* granules decoded per kernel wave (0 = default 2097152); bounds the workspace, which is sized on demand */
+    uint32_t wave_granules;     /* granules decoded per kernel wave (0 = default 2097152, capped at 16777216); bounds the workspace, which is sized on demand */
     uint32_t keep_intermediates;/* 1: keep per-stage buffers of the last wave readable via mp3gpu_debug_read */
     uint32_t reserved;
 } mp3gpu_opts;
