@@ -322,7 +322,7 @@ __device__ __forceinline__ void hybrid_channel(const float (&in)[18], const Hybr
 }
 
 constexpr int kHybWarps = 4;
-constexpr int kHybSmemWords = 2 * kXrFloats + 2 * 18 * 32 + 16 + 2 * 64 * 2 + 72;  // per warp: staging, overlap, scalefactors, scale tables, band codes
+constexpr int kHybSmemWords = 2 * kXrFloats + 2 * 18 * 32 + 16 + 2 * 64 * 2 + 288;  // per warp: staging, overlap, scalefactors, scale tables, pair-table rows
 constexpr int kHybSmemBytes = kHybWarps * kHybSmemWords * 4;
 
 // frame.go:422-425 (6-digit literals); checked against the host tables at mp3gpu_create
@@ -368,7 +368,9 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
     float(*s_ov)[18 * 32] = reinterpret_cast<float(*)[18 * 32]>(s_base + 2 * kXrFloats);   // IMDCT overlap (Frame.store)
     uint32_t(*s_pk)[8] = reinterpret_cast<uint32_t(*)[8]>(s_base + 2 * kXrFloats + 2 * 18 * 32);
     ScaleEnt(*s_scale)[64] = reinterpret_cast<ScaleEnt(*)[64]>(s_base + 2 * kXrFloats + 2 * 18 * 32 + 16);  // 2^(k/4) per band
-    uint8_t *s_pl = reinterpret_cast<uint8_t *>(s_base + 2 * kXrFloats + 2 * 18 * 32 + 16 + 2 * 64 * 2);      // pair_long row of the current cfg
+    uint16_t *s_pd = reinterpret_cast<uint16_t *>(s_base + 2 * kXrFloats + 2 * 18 * 32 + 16 + 2 * 64 * 2);     // pair_dst, pair_long and
+    uint8_t *s_pl = reinterpret_cast<uint8_t *>(s_pd + 288);                                                  // pair_short rows of the
+    uint8_t *s_ps = s_pl + 288;                                                                               // warp's current cfg
 
     int sfb_cfg = -1;      // sampling-rate configuration the lane's band codes below belong to
     uint32_t sfb_q[9];     // long-block scalefactor band of the lane's pairs 9*lane .. 9*lane+8 (fast path)
@@ -406,21 +408,30 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
             const GranuleChan c0 = make_chan(w0a, w1a, w2a, C.meta0);
             const GranuleChan c1 = make_chan(w0b, w1b, w2b, valid_b ? C.meta1 : 0u);
             __syncwarp();
+            if (cfg != sfb_cfg) {
+                // The pair-table rows of this sampling-rate configuration go through shared memory, so that K2 consumes
+                // them by LDS: anything fed by a global load inside this loop shares its scoreboard with the granule
+                // prefetch issued at the top, and its first use then waits for that prefetch to land (measured on the
+                // lane's band codes: 13 % of the kernel's stall samples on one instruction).
+                sfb_cfg = cfg;
+                __syncwarp();
+                for (int i = lane; i < 288; i += 32) {
+                    s_pl[i] = T.pair_long[cfg * 288 + i];
+                    s_ps[i] = T.pair_short[cfg * 288 + i];
+                    s_pd[i] = T.pair_dst[cfg * 288 + i];
+                }
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 9; q++) sfb_q[q] = s_pl[lane * 9 + q];
+            }
+            PairRows rows;
+            rows.pair_long = s_pl;
+            rows.pair_short = s_ps;
+            rows.pair_dst = s_pd;
             const bool fast = !c0.is_short && !(valid_b && c1.is_short);
             float x0[18], x1[18];  // fast path: the lane's subband, both channels
             if (fast) {
                 // ---------------- K2, long blocks: lane = subband, everything in registers ---------------
-                if (cfg != sfb_cfg) {
-                    // Through shared memory, so that the registers below are fed by LDS: a register fed by a global
-                    // load here shares its scoreboard with the granule prefetch issued at the top of the loop, and
-                    // its first use then waits for that prefetch (measured: 13 % of the kernel's stall samples).
-                    sfb_cfg = cfg;
-                    __syncwarp();
-                    for (int i = lane; i < 288; i += 32) s_pl[i] = T.pair_long[cfg * 288 + i];
-                    __syncwarp();
-#pragma unroll
-                    for (int q = 0; q < 9; q++) sfb_q[q] = s_pl[lane * 9 + q];
-                }
                 if (lane < 22) {
                     s_scale[0][lane] = scale_entry(T, c0, s_pk[0], lane);
                     if (valid_b) s_scale[1][lane] = scale_entry(T, c1, s_pk[1], lane);
@@ -514,7 +525,7 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
     #pragma unroll 3
                     for (int p = lane; p < 288; p += 32) {
                         int d0, d1;
-                        const int e = pair_lookup(T, cfg, c, p, &d0, &d1);
+                        const int e = pair_lookup(rows, c, p, &d0, &d1);
                         float x0 = 0.0f, x1 = 0.0f;  // lines at or above count1 stay +0 (maindata/huffman.go:130-134)
                         if (p < npair) {
                             const uint32_t w = __ldg(is2 + p);
@@ -551,7 +562,7 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
                         for (int p = lane; p < 288; p += 32) {
                             int d0, d1;
                             // the window is looked up at the PRE-reorder index although the data is reordered (frame.go:341-357)
-                            const int is_pos = s_isp[pair_lookup(T, cfg, c0, p, &d0, &d1)];
+                            const int is_pos = s_isp[pair_lookup(rows, c0, p, &d0, &d1)];
                             if (is_pos < 7) {
                                 const float rl = T.is_ratio_l[is_pos], rr = T.is_ratio_r[is_pos];
                                 const int q0 = xr_pad(2 * p), q1 = xr_pad(2 * p + 1);
@@ -573,8 +584,8 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
                         const int sb = (b >> 3) + 1, i = b & 7;
                         const int li = 18 * sb - 1 - i + (sb - 1), ui = 18 * sb + i + sb;  // padded positions
                         const float xl = s_x[ch][li], xu = s_x[ch][ui];
-                        s_x[ch][li] = f_sub(f_mul(xl, T.cs[i]), f_mul(xu, T.ca[i]));
-                        s_x[ch][ui] = f_add(f_mul(xu, T.cs[i]), f_mul(xl, T.ca[i]));
+                        s_x[ch][li] = f_sub(f_mul(xl, kCs[i]), f_mul(xu, kCa[i]));
+                        s_x[ch][ui] = f_add(f_mul(xu, kCs[i]), f_mul(xl, kCa[i]));
                     }
                 }
                 __syncwarp();

@@ -565,16 +565,32 @@ MP3_HD ScaleEnt scale_entry(const DeviceTables &T, const GranuleChan &c, const u
     return r;
 }
 
-// Table index and reorder destinations of the pair of lines (2p, 2p+1) (frame.go:257-302).
-MP3_HD int pair_lookup(const DeviceTables &T, int cfg, const GranuleChan &c, int p, int *dst0, int *dst1) {
+// Table index and reorder destinations of the pair of lines (2p, 2p+1) (frame.go:257-302).  The three table rows of
+// the granule's sampling-rate configuration are passed in (k_hybrid keeps them in shared memory).
+struct PairRows {
+    const uint8_t *pair_long;    // [288]
+    const uint8_t *pair_short;   // [288]
+    const uint16_t *pair_dst;    // [288]
+};
+MP3_HD PairRows pair_rows(const DeviceTables &T, int cfg) {
+    PairRows r;
+    r.pair_long = T.pair_long + cfg * 288;
+    r.pair_short = T.pair_short + cfg * 288;
+    r.pair_dst = T.pair_dst + cfg * 288;
+    return r;
+}
+MP3_HD int pair_lookup(const PairRows &R, const GranuleChan &c, int p, int *dst0, int *dst1) {
     if (c.is_short && (!c.mixed || p >= 18)) {
-        *dst0 = T.pair_dst[cfg * 288 + p];
+        *dst0 = R.pair_dst[p];
         *dst1 = *dst0 + 3;
-        return kScaleShortBase + T.pair_short[cfg * 288 + p];
+        return kScaleShortBase + R.pair_short[p];
     }
     *dst0 = 2 * p;
     *dst1 = 2 * p + 1;
-    return T.pair_long[cfg * 288 + p];
+    return R.pair_long[p];
+}
+MP3_HD int pair_lookup(const DeviceTables &T, int cfg, const GranuleChan &c, int p, int *dst0, int *dst1) {
+    return pair_lookup(pair_rows(T, cfg), c, p, dst0, dst1);
 }
 
 // One requantised line: sign(is) * float32(|is|^(4/3) * 2^(k4/4)) (frame.go:146-155; the reference multiplies in
