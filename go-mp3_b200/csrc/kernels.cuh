@@ -385,21 +385,22 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
         const int g0 = seg * seg_len;
         const int g1 = min(g0 + seg_len, n_granules);
         // overlap before the halo granule is irrelevant: the halo's second half replaces it
-#pragma unroll
-        for (int i = 0; i < 18; i++) { s_ov[0][i * 32 + lane] = 0.f; s_ov[1][i * 32 + lane] = 0.f; }
+#pragma unroll 1  // rolled: code size (the kernel competes with itself for the instruction cache on mixed content)
+        for (int i = lane; i < 2 * 18 * 32; i += 32) s_ov[0][i] = 0.f;  // s_ov[0] and s_ov[1] are contiguous
 
         GranulePre P;
-        prefetch_granule(P, units, first_granule, g0 - 1, B, lane);
-        for (int g = g0 - 1; g < g1; g++) {
+        P.w2a = 0;  // "nothing there": the first trip of the loop (g = g0 - 2) only issues the first prefetch
+#pragma unroll 1
+        for (int g = g0 - 2; g < g1; g++) {
             const GranulePre C = P;                                                      // this granule
             if (g + 1 < g1) prefetch_granule(P, units, first_granule, g + 1, B, lane);   // next one, in flight during this one
             const uint32_t w0a = C.w0a, w1a = C.w1a, w2a = C.w2a, w0b = C.w0b, w1b = C.w1b, w2b = C.w2b;
-            if (first_granule + g < 0 || !u_valid(w2a)) continue;  // a granule always has channel 0
+            if (g < g0 - 1 || first_granule + g < 0 || !u_valid(w2a)) continue;  // a granule always has channel 0
             const bool valid_b = u_valid(w2b);
             const bool need_first = g >= g0;  // the halo granule only contributes its overlap
             if (u_zero(w2a)) {  // start of a stream / of a Seek: Frame.store is zero (frame.go:48)
-#pragma unroll
-                for (int i = 0; i < 18; i++) { s_ov[0][i * 32 + lane] = 0.f; s_ov[1][i * 32 + lane] = 0.f; }
+#pragma unroll 1
+                for (int i = lane; i < 2 * 18 * 32; i += 32) s_ov[0][i] = 0.f;
             }
             __syncwarp();
 
