@@ -132,13 +132,18 @@ inline int read_frame_header(Source &s, Header *h, int64_t *start_pos) {
 }
 
 // ---- MSB-first reader for the 9/17/32 side-info bytes (bits.go:58-77; never out of bounds here) --
-struct SideBits {
-    const uint8_t *p;
+struct SideBits {  // MSB-first reader over a private, zero-padded copy of the side info (at most 32 bytes)
+    uint8_t buf[40];
     int pos = 0;
-    explicit SideBits(const uint8_t *q) : p(q) {}
-    int get(int n) {
-        int v = 0;
-        for (int i = 0; i < n; i++, pos++) v = (v << 1) | ((p[pos >> 3] >> (7 - (pos & 7))) & 1);
+    SideBits(const uint8_t *q, int n) {
+        memset(buf, 0, sizeof buf);
+        memcpy(buf, q, (size_t)(n < 32 ? n : 32));
+    }
+    int get(int n) {  // 1 <= n <= 25
+        const uint8_t *b = buf + (pos >> 3);
+        const uint32_t w = ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | (uint32_t)b[3];
+        const int v = (int)((w << (pos & 7)) >> (32 - n));
+        pos += n;
         return v;
     }
 };
@@ -225,7 +230,7 @@ public:
         if (framesize > 2000) return MP3_ERR_FRAMESIZE;
         const int si_size = h.side_info_size();
         if (src.read_full(&b, si_size) < si_size) return MP3_ERR_UNEXPECTED_EOF;
-        SideBits sb(b);
+        SideBits sb(b, si_size);
         const bool mpeg1 = h.lsf() == 0;
         const int main_data_begin = sb.get(mpeg1 ? 9 : 8);
         if (h.mode() == 3) sb.get(mpeg1 ? 5 : 1); else sb.get(mpeg1 ? 3 : 2);
