@@ -9,6 +9,9 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -279,39 +282,176 @@ extern "C" void mp3_parsed_free(mp3_parsed *p) {
 }
 
 // ---- DecodeBatch -----------------------------------------------------------------------------------
+namespace {
+
+// Upper bound of the unit slots a stream will produce: the frame walk of parse_whole_stream without side info
+// and main data (a frame that later fails to parse only makes the real count smaller).
+size_t unit_slots_upper_bound(const uint8_t *data, size_t len) {
+    Source s;
+    s.data = data;
+    s.len = len;
+    if (s.skip_tags() != MP3_OK) return 0;
+    size_t slots = 0;
+    for (;;) {
+        Header h;
+        int64_t fpos;
+        if (read_frame_header(s, &h, &fpos) != MP3_OK) break;
+        if (h.id() == 0 || h.layer() != 1) break;
+        const int fs = h.frame_size();
+        if (fs > 2000 || fs < 4 || s.pos + (fs - 4) > (int64_t)len) break;
+        s.pos += fs - 4;
+        slots += (size_t)h.granules() * 2;
+    }
+    return slots;
+}
+
+struct DeviceJob {
+    const uint8_t *main_data;
+    size_t main_len;
+    const mp3gpu_unit *units;
+    size_t n_granules;
+    int16_t *pcm;
+};
+
+}  // namespace
+
+// Large batches are cut into chunks of streams: while the device decodes chunk k (the PCIe-bound part), the host
+// threads parse and gather chunk k+1 straight behind it in the same pinned arenas.
 extern "C" int mp3_decode_batch(mp3_engine *e, const uint8_t *const *data, const size_t *lens, size_t n,
                                 mp3_stream_result *results, const uint8_t **pcm_base, mp3_batch_timings *timings) {
     if (!e || !results || !pcm_base || (n && (!data || !lens))) return MP3_ERR_INVALID;
     const double t0 = now_s();
-    std::vector<ParsedStream> ps;
-    parse_all(data, lens, n, e->opts.host_threads, ps);
-    const double t1 = now_s();
-    BatchLayout L = layout_batch(ps);
-    int rc = e->ensure(e->a_main, L.m_total + 64);
-    if (rc == MP3_OK) rc = e->ensure(e->a_units, sizeof(mp3gpu_unit) * L.u_total + 64);
-    const size_t n_granules = L.u_total / 2;
-    if (rc == MP3_OK) rc = e->ensure(e->a_pcm, n_granules * MP3GPU_PCM_BYTES_PER_GRANULE + 64);
-    if (rc != MP3_OK) return rc;
-    gather_batch(ps, L, (uint8_t *)e->a_main.p, (mp3gpu_unit *)e->a_units.p, results, e->opts.host_threads);
-    ps.clear();
-    ps.shrink_to_fit();
-    const double t2 = now_s();
-    int grc = e->api.decode(e->gpu, (const uint8_t *)e->a_main.p, L.m_total, (const mp3gpu_unit *)e->a_units.p, n_granules,
-                            (int16_t *)e->a_pcm.p);
+    const size_t n_chunks = n >= 256 ? std::min<size_t>(8, n / 128) : 1;
+    // ---- arena sizes: main data never exceeds the input bytes; unit slots from a header-only frame walk ----
+    size_t main_ub = 64 * (n_chunks + 1), slots_ub = 0;
+    {
+        std::vector<size_t> ub(n);
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (;;) {
+                size_t i = next.fetch_add(1);
+                if (i >= n) break;
+                ub[i] = n_chunks > 1 ? unit_slots_upper_bound(data[i], lens[i]) : 0;
+            }
+        };
+        int nt = (int)std::min<size_t>((size_t)hw_threads(e->opts.host_threads), n ? n : 1);
+        if (n_chunks > 1 && nt > 1) {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nt; t++) th.emplace_back(work);
+            for (auto &t : th) t.join();
+        } else {
+            work();
+        }
+        for (size_t i = 0; i < n; i++) {
+            main_ub += (lens[i] + 3) & ~size_t(3);
+            slots_ub += ub[i];
+        }
+    }
+    double parse_s = 0, gather_s = 0, device_s = 0;
+    size_t m_cursor = 0, u_cursor = 0;  // bytes into a_main (64-byte aligned per chunk), unit slots into a_units
+    int dev_rc = MP3GPU_OK;
+    std::string dev_err;
+
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<DeviceJob> jobs;
+    bool closed = false;
+    std::thread worker;
+    auto run_job = [&](const DeviceJob &j) {
+        if (dev_rc != MP3GPU_OK || j.n_granules == 0) return;
+        const double a = now_s();
+        int rc = e->api.decode(e->gpu, j.main_data, j.main_len, j.units, j.n_granules, j.pcm);
+        device_s += now_s() - a;
+        if (rc != MP3GPU_OK) {
+            dev_rc = rc;
+            dev_err = e->api.last_error(e->gpu);
+        }
+    };
+
+    for (size_t c = 0; c < n_chunks; c++) {
+        const size_t i0 = n * c / n_chunks, i1 = n * (c + 1) / n_chunks;
+        const double ta = now_s();
+        std::vector<ParsedStream> ps;
+        parse_all(data + i0, lens + i0, i1 - i0, e->opts.host_threads, ps);
+        const double tb = now_s();
+        parse_s += tb - ta;
+        BatchLayout L = layout_batch(ps);
+        if (n_chunks == 1) {  // sizes are exact here
+            int rc = e->ensure(e->a_main, L.m_total + 64);
+            if (rc == MP3_OK) rc = e->ensure(e->a_units, sizeof(mp3gpu_unit) * L.u_total + 64);
+            if (rc == MP3_OK) rc = e->ensure(e->a_pcm, (L.u_total / 2) * MP3GPU_PCM_BYTES_PER_GRANULE + 64);
+            if (rc != MP3_OK) return rc;
+        } else if (c == 0) {  // before the worker exists: growing an arena moves it
+            int rc = e->ensure(e->a_main, main_ub);
+            if (rc == MP3_OK) rc = e->ensure(e->a_units, sizeof(mp3gpu_unit) * slots_ub + 64);
+            if (rc == MP3_OK) rc = e->ensure(e->a_pcm, (slots_ub / 2) * MP3GPU_PCM_BYTES_PER_GRANULE + 64);
+            if (rc != MP3_OK) return rc;
+            worker = std::thread([&]() {
+                for (;;) {
+                    DeviceJob j;
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [&] { return closed || !jobs.empty(); });
+                        if (jobs.empty()) return;
+                        j = jobs.front();
+                        jobs.pop_front();
+                    }
+                    run_job(j);
+                }
+            });
+        }
+        if (n_chunks > 1 && (m_cursor + L.m_total + 64 > e->a_main.cap || u_cursor + L.u_total > slots_ub)) {
+            // cannot happen (the bounds are bounds); refuse rather than overrun
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                closed = true;
+            }
+            cv.notify_all();
+            worker.join();
+            e->err = "DecodeBatch arena bound exceeded";
+            return MP3_ERR_INVALID;
+        }
+        uint8_t *m_dst = (uint8_t *)e->a_main.p + m_cursor;
+        mp3gpu_unit *u_dst = (mp3gpu_unit *)e->a_units.p + u_cursor;
+        gather_batch(ps, L, m_dst, u_dst, results + i0, e->opts.host_threads);
+        const int64_t pcm_off = (int64_t)(u_cursor / 2) * MP3GPU_PCM_BYTES_PER_GRANULE;
+        for (size_t i = i0; i < i1; i++) results[i].pcm_offset += pcm_off;
+        gather_s += now_s() - tb;
+        DeviceJob j{m_dst, L.m_total, u_dst, L.u_total / 2, (int16_t *)((uint8_t *)e->a_pcm.p + pcm_off)};
+        if (n_chunks == 1) {
+            run_job(j);
+        } else {
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                jobs.push_back(j);
+            }
+            cv.notify_one();
+        }
+        m_cursor += (L.m_total + 64 + 63) & ~size_t(63);
+        u_cursor += L.u_total;
+    }
+    if (worker.joinable()) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            closed = true;
+        }
+        cv.notify_all();
+        worker.join();
+    }
     const double t3 = now_s();
-    if (grc != MP3GPU_OK) {
-        e->err = e->api.last_error(e->gpu);
+    if (dev_rc != MP3GPU_OK) {
+        e->err = dev_err;
         return MP3_ERR_DEVICE;
     }
     *pcm_base = (const uint8_t *)e->a_pcm.p;
     if (timings) {
-        timings->parse_s = t1 - t0;
-        timings->gather_s = t2 - t1;
-        timings->device_s = t3 - t2;
+        timings->parse_s = parse_s;     // summed over the chunks; chunks after the first overlap the device call
+        timings->gather_s = gather_s;
+        timings->device_s = device_s;   // summed device-call time (worker thread)
         timings->total_s = t3 - t0;
-        timings->main_data_bytes = L.m_total;
-        timings->n_granules = n_granules;
-        timings->pcm_bytes = (uint64_t)n_granules * MP3GPU_PCM_BYTES_PER_GRANULE;
+        timings->main_data_bytes = m_cursor;
+        timings->n_granules = u_cursor / 2;
+        timings->pcm_bytes = (uint64_t)(u_cursor / 2) * MP3GPU_PCM_BYTES_PER_GRANULE;
     }
     return MP3_OK;
 }

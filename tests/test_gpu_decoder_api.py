@@ -191,3 +191,34 @@ def test_decode_batch_matches_oracle(pkg, classic_lame, mpeg2):
     assert res[-2]["status"] == 1 and res[-1]["status"] == 1 and res[-1]["pcm_bytes"] == 0  # io.EOF from NewDecoder
     assert tm["n_granules"] * 2304 == tm["pcm_bytes"]
     e.close()
+
+
+def test_decode_batch_chunked_pipeline_equals_single_call(pkg, classic_lame):
+    """Batches of >= 256 streams are cut into chunks whose parse/gather overlaps the previous chunk's device call
+    (mp3host.cc).  The result must be byte-identical to decoding the same streams in small (single-chunk) batches,
+    with every stream's PCM laid out back to back; empty / junk / truncated streams ride along."""
+    streams = []
+    for i in range(300):
+        c = synth.cfg4(1000 + i, 6 + i % 5) if i % 3 else synth.cfg3(2000 + i, 5 + i % 7)
+        streams.append(synth.stream(c))
+    streams[17] = b""
+    streams[130] = b"junk" * 64
+    streams[131] = classic_lame[:5000]          # cut inside a frame
+    streams[299] = classic_lame[:20000]
+    e = pkg.Engine(0, host_threads=4, exact=True)
+    res, pcm, tm = e.decode_batch(streams)
+    got = [bytes(pcm[r["pcm_offset"]:r["pcm_offset"] + r["pcm_bytes"]]) for r in res]
+    stat = [(r["status"], r["frames"], r["sample_rate"], r["pcm_bytes"]) for r in res]
+    # back to back, in order
+    off = 0
+    for r in res:
+        assert r["pcm_offset"] == off
+        off += r["pcm_bytes"]
+    assert off == tm["pcm_bytes"] == tm["n_granules"] * 2304
+    for lo in range(0, 300, 100):                # 100 streams per call: the single-chunk path
+        res1, pcm1, _ = e.decode_batch(streams[lo:lo + 100])
+        for k, r in enumerate(res1):
+            assert (r["status"], r["frames"], r["sample_rate"], r["pcm_bytes"]) == stat[lo + k], lo + k
+            assert bytes(pcm1[r["pcm_offset"]:r["pcm_offset"] + r["pcm_bytes"]]) == got[lo + k], lo + k
+    assert res[17]["status"] == 1 and res[130]["status"] == 1 and res[131]["pcm_bytes"] > 0
+    e.close()
