@@ -368,10 +368,10 @@ extern "C" int mp3_decode_batch(mp3_engine *e, const uint8_t *const *data, const
         }
     };
 
+    std::vector<ParsedStream> ps;  // reused by every chunk: the per-stream vectors keep their (already touched) capacity
     for (size_t c = 0; c < n_chunks; c++) {
         const size_t i0 = n * c / n_chunks, i1 = n * (c + 1) / n_chunks;
         const double ta = now_s();
-        std::vector<ParsedStream> ps;
         parse_all(data + i0, lens + i0, i1 - i0, e->opts.host_threads, ps);
         const double tb = now_s();
         parse_s += tb - ta;
