@@ -306,6 +306,14 @@ def _result_dict(r: StreamResult) -> dict:
             "frames": r.frames}
 
 
+def unit_slots_upper_bound(stream: bytes) -> int:
+    """The header-only bound DecodeBatch sizes its arenas with (mp3_debug_unit_slots_upper_bound; test hook)."""
+    L = host_lib()
+    L.mp3_debug_unit_slots_upper_bound.argtypes = [C.c_char_p, C.c_size_t]
+    L.mp3_debug_unit_slots_upper_bound.restype = C.c_size_t
+    return int(L.mp3_debug_unit_slots_upper_bound(stream, len(stream)))
+
+
 def parse_streams(streams: Sequence[bytes], host_threads: int = 0) -> ParsedBatch:
     """Host half of DecodeBatch: tags, headers, side info, reservoir -> bit-slices (mp3_parse_streams)."""
     L = host_lib()

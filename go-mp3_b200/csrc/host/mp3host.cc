@@ -315,6 +315,9 @@ struct DeviceJob {
 
 }  // namespace
 
+// Test hook (tests/test_host_and_emulation.py): the arena bound DecodeBatch relies on.
+extern "C" size_t mp3_debug_unit_slots_upper_bound(const uint8_t *data, size_t len) { return unit_slots_upper_bound(data, len); }
+
 // Large batches are cut into chunks of streams: while the device decodes chunk k (the PCIe-bound part), the host
 // threads parse and gather chunk k+1 straight behind it in the same pinned arenas.
 extern "C" int mp3_decode_batch(mp3_engine *e, const uint8_t *const *data, const size_t *lens, size_t n,

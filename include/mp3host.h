@@ -106,6 +106,10 @@ typedef struct mp3_batch_timings {
 int mp3_decode_batch(mp3_engine *e, const uint8_t *const *data, const size_t *lens, size_t n,
                      mp3_stream_result *results, const uint8_t **pcm_base, mp3_batch_timings *timings);
 
+/* Test hook: upper bound of the unit slots (2 per granule) mp3_parse_streams / mp3_decode_batch produce for one
+ * stream, from a header-only frame walk; DecodeBatch sizes its pinned arenas with it. */
+size_t mp3_debug_unit_slots_upper_bound(const uint8_t *data, size_t len);
+
 /* Host-only stage of DecodeBatch (no GPU): parse + reservoir resolution into caller-visible arrays.
  * Used by tests (host logic) and by bench.py to stage device-resident inputs.  Buffers are owned by
  * the engine-independent parse result; free with mp3_parsed_free. */

@@ -127,6 +127,26 @@ def test_batch_layout(pkg, classic_lame):
     assert off_gr == pb.n_granules
 
 
+def test_decode_batch_arena_bound_covers_every_stream(pkg, classic_lame, mpeg2):
+    """DecodeBatch sizes its pinned arenas from a header-only frame walk before parsing (mp3host.cc): the bound must
+    never be below what the parser produces — on well-formed streams it is exact, on truncated, fuzzed and malformed
+    ones it may only be larger."""
+    cases = dict(edge_streams())
+    cases.update({"classic_lame": classic_lame, "mpeg2": mpeg2, "cut": classic_lame[:12345], "empty": b""})
+    for i in range(40):
+        cases[f"fuzz{i}"] = synth.stream(synth.fuzz(i))
+        cases[f"wild{i}"] = synth.stream(synth.wild(i, 12))
+    for i in range(8):
+        cases[f"cfg4_{i}"] = synth.stream(synth.cfg4(i, 25))
+    exact = 0
+    for name, data in cases.items():
+        ub = pkg.unit_slots_upper_bound(data)
+        n = pkg.parse_streams([data]).n_granules * 2
+        assert ub >= n, (name, ub, n)
+        exact += ub == n
+    assert exact >= len(cases) // 2
+
+
 # ---- Huffman LUT == reference tree walk ----------------------------------------------------------------
 def test_huffman_lut_equals_tree_walk_exhaustive():
     L, E = oracle.lib(), hostemu_lib.lib()
