@@ -221,3 +221,28 @@ def test_table_symmetries_used_by_the_kernels():
     for k in range(1, 16):
         assert np.array_equal(N[48 + k], N[48 - k])
     assert np.all(N[48] == -1.0) and np.all(np.abs(N[16]) < 1e-13) and np.any(N[16] != 0)
+
+
+def test_unit_logic_sweep_vs_oracle(pkg):
+    """A wider net than the parametrised cases above: 540 more synthetic / wild / fuzzed streams (64 k units) through
+    the host stage and the K1/K2 unit logic, every Huffman integer, count1, scalefactor and requantised/stereo/alias
+    spectrum value bit-identical to the oracle's taps."""
+    cases = [synth.wild(i, 40) for i in range(16, 216)] + [synth.fuzz(i, 30) for i in range(24, 224)]
+    cases += [synth.cfg4(i, 50) for i in range(60, 160)] + [synth.cfg3(i, 30) for i in range(2, 42)]
+    units = 0
+    for cfg in cases:
+        data = synth.stream(cfg)
+        pb = pkg.parse_streams([data])
+        dec, pcm, err, taps = oracle.decode_with_taps(data, cfg.n_frames + 2, stages=True)
+        if dec is None or pb.n_granules == 0:
+            continue
+        o = common.oracle_units_view(taps, taps.n_frames)
+        assert len(pb.units) == len(o["live"])
+        is16, meta, sf = hostemu_lib.huffman(pb.main_data, pb.units)
+        assert np.array_equal(is16, o["is_"]) and np.array_equal(meta & 0x3FF, o["count1"])
+        assert np.array_equal(sf[:, :22], o["scalefac_l"]) and np.array_equal(sf[:, 22:61], o["scalefac_s"])
+        xr = hostemu_lib.requant(pb.units, is16, meta, sf).reshape(-1, 576)
+        same = (xr.view(np.uint32) == o["xr_alias"].view(np.uint32)) | (np.isnan(xr) & np.isnan(o["xr_alias"]))
+        assert same.all()
+        units += len(pb.units)
+    assert units > 60000
