@@ -68,53 +68,93 @@ struct WaveBufs {
 // ------------------------------------------------------------------------------------------
 // K1: scalefactors + Huffman.  One thread per unit slot; per-unit logic in unit_logic.h.
 // ------------------------------------------------------------------------------------------
-// A unit's decode time is proportional to its number of code words, and the 32 lanes of a warp wait for the slowest:
-// with units in stream order a warp's lanes were busy 37 % of the time (ncu: 12 of 32 threads per instruction).
-// Each CTA therefore deals its 256 consecutive units to its threads in order of big_values (a counting sort in
-// shared memory, 8-pair bins, largest first), so the lanes of a warp get units of similar length while the CTA
-// still reads one contiguous stretch of main data and writes one contiguous stretch of output.  (A wave-wide
-// sort balanced better but lost that locality and was slower on VBR streams.)
-constexpr int kHuffThreads = 256;
-
-// The grid is persistent (a few CTAs per SM, each walking tiles of 256 units with a grid stride), so the 33 KB of code
-// tables are staged into shared memory once per CTA and not once per tile.
-__global__ void __launch_bounds__(kHuffThreads)
+// The grid is persistent (a few CTAs per SM, each walking tiles of THREADS units with a grid stride), so the 33 KB of
+// code tables are staged into shared memory once per CTA and not once per tile.  Per tile:
+//  1. Work order.  A unit's decode time is proportional to its number of code words, and the 32 lanes of a warp wait
+//     for the slowest: with units in stream order a warp's lanes were busy 37 % of the time.  The CTA deals the tile's
+//     consecutive units to its threads in order of big_values (a counting sort in shared memory, 8-pair bins, largest
+//     first), so the lanes of a warp get units of similar length while the CTA still reads one contiguous stretch of
+//     main data and writes one contiguous stretch of output.
+//  2. Staging.  The units of a tile are consecutive in stream order, so the bits they read are one contiguous stretch
+//     of main_data (streams lie back to back).  The CTA copies that stretch into shared memory with coalesced 16-byte
+//     loads, byte-swapped once into big-endian bit order; a unit's cursor is then a plain bit position
+//     (StagedCursor, unit_logic.h) — no register window, no divergent refill.  What lies outside the stretch (a tile
+//     whose stretch exceeds the staging capacity, malformed descriptors) is read from global memory word by word.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 k_huffman(const uint8_t *__restrict__ main_data, unsigned long long main_bits, const mp3gpu_unit *__restrict__ units,
-          long long first_unit, int n_units, DeviceTables T, WaveBufs B) {
-    extern __shared__ __align__(16) uint32_t s_lut[];
+          long long first_unit, int n_units, DeviceTables T, WaveBufs B, int stage_cap16) {
+    extern __shared__ __align__(16) uint32_t s_dyn32[];  // pair-tree code tables (uint16 entries), then the staged stretch
     __shared__ uint64_t s_quad[256];
+    __shared__ uint32_t s_qlut[512];
     __shared__ uint32_t s_desc[34];
     __shared__ unsigned int s_bin[40];
-    __shared__ uint16_t s_order[kHuffThreads];
+    __shared__ unsigned int s_lohi[2];
+    __shared__ uint16_t s_order[THREADS];
+    const SmemRef s_lut = SmemRef::of(s_dyn32);
+    uint32_t *const s_stage = s_dyn32 + T.huff_lut_n / 2;  // huff_lut_n is a multiple of 8 entries (tables.cc): 16-byte aligned
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(T.huff_lut);  // huff_lut_n is a multiple of 4 (tables.cc)
-        uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
+        const uint4 *src = reinterpret_cast<const uint4 *>(T.huff_lut);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_dyn32);
 #pragma unroll 4
-        for (int i = threadIdx.x; i < T.huff_lut_n / 4; i += kHuffThreads) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < T.huff_lut_n / 8; i += THREADS) dst[i] = __ldg(src + i);
     }
+    for (int i = threadIdx.x; i < 512; i += THREADS) s_qlut[i] = T.quad_lut[i];
     if (threadIdx.x < 34) s_desc[threadIdx.x] = T.huff_desc[threadIdx.x];
-    s_quad[threadIdx.x] = T.quad_signs[threadIdx.x];  // kHuffThreads == 256
-    const int n_tiles = (n_units + kHuffThreads - 1) / kHuffThreads;
+    if (threadIdx.x < 256) s_quad[threadIdx.x] = T.quad_signs[threadIdx.x];
+    const int n_tiles = (n_units + THREADS - 1) / THREADS;
+    const uint32_t main16 = (uint32_t)(((main_bits >> 3) + 48) >> 4);  // 16-byte chunks that may be read: main_data is followed by 64 bytes of padding
 #pragma unroll 1
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         if (threadIdx.x < 40) s_bin[threadIdx.x] = 0;
-        __syncthreads();  // also: the previous tile's s_order reads are done, the tables are staged
-        // ---- work order inside the tile ------------------------------------------------------------
-        const int base = tile * kHuffThreads;
+        if (threadIdx.x == 0) { s_lohi[0] = 0xffffffffu; s_lohi[1] = 0u; }
+        __syncthreads();  // also: the previous tile's s_order / s_stage reads are done, the tables are staged
+        // ---- work order inside the tile, and the stretch of main data the tile reads ---------------------
+        const int base = tile * THREADS;
         int key = 38;  // beyond the wave
+        uint32_t lo16 = 0xffffffffu, hi16 = 0u;
         {
             const int ul0 = base + threadIdx.x;
             if (ul0 < n_units) {
-                const mp3gpu_unit *u = units + first_unit + ul0;
-                const uint32_t w0 = __ldg(&u->w0), w2 = __ldg(&u->w2);
-                key = !u_valid(w2) ? 37 : 36 - ((u_p23len(w0) == 0 ? 0 : imin(u_bigval(w0), 288)) >> 3);
+                const mp3gpu_unit u = units[first_unit + ul0];
+                key = 37;
+                if (u_valid(u.w2)) {
+                    key = 36 - ((u_p23len(u.w0) == 0 ? 0 : imin(u_bigval(u.w0), 288)) >> 3);
+                    stage_reach(u, main_bits, &lo16, &hi16);
+                }
             }
+        }
+        lo16 = __reduce_min_sync(0xffffffffu, lo16);
+        hi16 = __reduce_max_sync(0xffffffffu, hi16);
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&s_lohi[0], lo16);
+            atomicMax(&s_lohi[1], hi16);
         }
         const unsigned int rank = atomicAdd(&s_bin[key], 1u);
         __syncthreads();
         if (threadIdx.x == 0) {
             unsigned int acc = 0;
             for (int i = 0; i < 39; i++) { const unsigned int c = s_bin[i]; s_bin[i] = acc; acc += c; }
+        }
+        StageCtx S;
+        S.sw = s_lut.plus((uint32_t)T.huff_lut_n * 2u);
+        S.gw = reinterpret_cast<const uint32_t *>(main_data);
+        S.main_bits = main_bits;
+        {
+            const uint32_t lo = s_lohi[0];
+            uint32_t hi = s_lohi[1] < main16 ? s_lohi[1] : main16;
+            uint32_t n16 = hi > lo ? hi - lo : 0u;   // no valid unit in the tile: lo = ~0
+            if (n16 > (uint32_t)stage_cap16) n16 = (uint32_t)stage_cap16;
+            S.n_words = (int)(n16 * 4);
+            S.lo_word = (unsigned long long)lo * 4ull;
+            const uint4 *src = reinterpret_cast<const uint4 *>(main_data) + lo;
+            uint4 *dst = reinterpret_cast<uint4 *>(s_stage);
+#pragma unroll 4
+            for (uint32_t i = threadIdx.x; i < n16; i += THREADS) {
+                uint4 v = __ldg(src + i);
+                v.x = be32(v.x); v.y = be32(v.y); v.z = be32(v.z); v.w = be32(v.w);
+                dst[i] = v;
+            }
         }
         __syncthreads();
         s_order[s_bin[key] + rank] = (uint16_t)threadIdx.x;
@@ -127,7 +167,7 @@ k_huffman(const uint8_t *__restrict__ main_data, unsigned long long main_bits, c
         }
         uint32_t pk[8];
         uint32_t *out = reinterpret_cast<uint32_t *>(B.is16 + (size_t)ul * 576);
-        uint32_t meta = huffman_unit(T, s_lut, s_desc, s_quad, main_data, main_bits, units, first_unit + ul, pk, out);
+        const uint32_t meta = huffman_unit_staged(T, s_lut, s_qlut, s_desc, s_quad, S, units, first_unit + ul, pk, out);
         uint4 *dst = reinterpret_cast<uint4 *>(B.sfpack + (size_t)ul * 8);
         dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);

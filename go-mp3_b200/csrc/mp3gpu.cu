@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -40,7 +41,9 @@ struct mp3gpu_ctx {
     void *d_tab_blob = nullptr;
     DeviceTables T{};
     int lut_bytes = 0;
-    int huff_ctas_per_sm = 1;  // resident k_huffman CTAs per SM (occupancy query): the persistent grid is sm_count times this
+    int smem_per_sm = 0, smem_per_cta_max = 0;  // shared-memory budget (bytes) of an SM / of one CTA (opt-in maximum)
+    int huff_static_smem[3] = {0, 0, 0};        // static shared memory of k_huffman<256 / 512 / 1024>
+    int k1_threads_override = 0, k1_stage_kb_override = 0;  // experiments: MP3GPU_K1_THREADS / MP3GPU_K1_STAGE_KB
     // workspace for one wave (+1 granule look-back where needed)
     int16_t *d_is16 = nullptr;
     uint32_t *d_meta = nullptr;
@@ -165,7 +168,8 @@ static int upload_tables(mp3gpu_ctx *ctx) {
     size_t o_sl = put(h.sfb_long, sizeof h.sfb_long);
     size_t o_ss = put(h.sfb_short, sizeof h.sfb_short);
     size_t o_ns = put(h.nslen2, sizeof h.nslen2);
-    size_t o_lut = put(h.huff_lut.data(), h.huff_lut.size() * sizeof(uint32_t));
+    size_t o_lut = put(h.huff_lut.data(), h.huff_lut.size() * sizeof(uint16_t));
+    size_t o_ql = put(h.quad_lut, sizeof h.quad_lut);
     size_t o_qs = put(h.quad_signs, sizeof h.quad_signs);
     size_t o_rl = put(h.is_ratio_l, sizeof h.is_ratio_l);
     size_t o_rr = put(h.is_ratio_r, sizeof h.is_ratio_r);
@@ -192,7 +196,8 @@ static int upload_tables(mp3gpu_ctx *ctx) {
     ctx->T.sfb_long = (const uint16_t *)(b + o_sl);
     ctx->T.sfb_short = (const uint16_t *)(b + o_ss);
     ctx->T.nslen2 = (const uint16_t *)(b + o_ns);
-    ctx->T.huff_lut = (const uint32_t *)(b + o_lut);
+    ctx->T.huff_lut = (const uint16_t *)(b + o_lut);
+    ctx->T.quad_lut = (const uint32_t *)(b + o_ql);
     ctx->T.quad_signs = (const uint64_t *)(b + o_qs);
     ctx->T.is_ratio_l = (const float *)(b + o_rl);
     ctx->T.is_ratio_r = (const float *)(b + o_rr);
@@ -204,7 +209,7 @@ static int upload_tables(mp3gpu_ctx *ctx) {
     ctx->T.ca = (const float *)(b + o_ca);
     ctx->T.huff_lut_n = (int)h.huff_lut.size();
     ctx->T.pow2_off = kPow2Off;
-    ctx->lut_bytes = (int)(h.huff_lut.size() * sizeof(uint32_t));
+    ctx->lut_bytes = (int)(h.huff_lut.size() * sizeof(uint16_t));
     return MP3GPU_OK;
 }
 
@@ -243,9 +248,22 @@ extern "C" int mp3gpu_create(int device, const mp3gpu_opts *opts, mp3gpu_ctx **o
             for (int j = 0; j < 4; j++) CK(cudaEventCreate(&ctx->ev_t[i][j]));
         for (int i = 0; i < 4; i++) CK(cudaEventCreate(&ctx->ev_copy[i]));
         for (int i = 0; i < 8; i++) CK(cudaEventCreate(&ctx->ev_user[i]));
-        CK(cudaFuncSetAttribute(k_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->lut_bytes));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->huff_ctas_per_sm, k_huffman, kHuffThreads, (size_t)ctx->lut_bytes));
-        if (ctx->huff_ctas_per_sm < 1) ctx->huff_ctas_per_sm = 1;
+        ctx->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
+        ctx->smem_per_cta_max = (int)prop.sharedMemPerBlockOptin;
+        {
+            cudaFuncAttributes fa;
+            CK(cudaFuncGetAttributes(&fa, k_huffman<256>));
+            ctx->huff_static_smem[0] = (int)fa.sharedSizeBytes;
+            CK(cudaFuncGetAttributes(&fa, k_huffman<512>));
+            ctx->huff_static_smem[1] = (int)fa.sharedSizeBytes;
+            CK(cudaFuncGetAttributes(&fa, k_huffman<1024>));
+            ctx->huff_static_smem[2] = (int)fa.sharedSizeBytes;
+            CK(cudaFuncSetAttribute(k_huffman<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_per_cta_max - ctx->huff_static_smem[0]));
+            CK(cudaFuncSetAttribute(k_huffman<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_per_cta_max - ctx->huff_static_smem[1]));
+            CK(cudaFuncSetAttribute(k_huffman<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_per_cta_max - ctx->huff_static_smem[2]));
+            if (const char *e = getenv("MP3GPU_K1_THREADS")) ctx->k1_threads_override = atoi(e);
+            if (const char *e = getenv("MP3GPU_K1_STAGE_KB")) ctx->k1_stage_kb_override = atoi(e);
+        }
         CK(cudaFuncSetAttribute(k_hybrid<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHybSmemBytes));
         CK(cudaFuncSetAttribute(k_hybrid<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHybSmemBytes));
         CK(cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, kSynSmemBytes));
@@ -295,7 +313,7 @@ extern "C" const char *mp3gpu_last_error(const mp3gpu_ctx *ctx) { return ctx ? c
 // Launch the four kernels for granules [first, first+n) of the submission on s_compute.
 // d_pcm_wave points at the PCM of granule `first`.  `slot` selects the timing events (or -1).
 static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, size_t main_len, const mp3gpu_unit *d_units, long long first, int n,
-                       int16_t *d_pcm_wave, int slot) {
+                       int16_t *d_pcm_wave, int slot, double bytes_per_unit) {
     WaveBufs B;
     B.is16 = ctx->d_is16 + 2 * 2 * 576;  // granules -2, -1 live in front
     B.meta = ctx->d_meta + 2 * 2;
@@ -307,9 +325,38 @@ static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, size_t main_len, 
     cudaStream_t s = ctx->s_compute;
     if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][0], s));
     {
+        // k_huffman stages the stretch of main data a tile of units reads in shared memory: the staging area is sized
+        // from the call's average bytes per unit (x 1.25 for tile-to-tile variation; a tile that needs more reads its
+        // tail from global memory), and the CTA size is the one that keeps the most warps resident next to the 33 KB of
+        // code tables each CTA holds.
         const int nu = 2 * n;
-        const int tiles = (nu + kHuffThreads - 1) / kHuffThreads;
-        k_huffman<<<std::min(tiles, ctx->sm_count * ctx->huff_ctas_per_sm), kHuffThreads, ctx->lut_bytes, s>>>(d_main, (unsigned long long)main_len * 8ull, d_units, first * 2, nu, ctx->T, B);
+        const unsigned long long main_bits = (unsigned long long)main_len * 8ull;
+        int best_t = 256, best_ctas = 1, best_stage = 0;
+        {
+            const double avg = bytes_per_unit > 1.0 ? bytes_per_unit : 1.0;
+            int best_warps = -1;
+            for (int ti = 0; ti < 3; ti++) {
+                const int t = 256 << ti;
+                if (ctx->k1_threads_override && t != ctx->k1_threads_override) continue;
+                const int fixed = ctx->lut_bytes + ctx->huff_static_smem[ti] + 1024;  // + the per-CTA reservation
+                int stage = (int)(avg * t * 1.25) + 2048;
+                if (ctx->k1_stage_kb_override) stage = ctx->k1_stage_kb_override * 1024;
+                const int cap = ctx->smem_per_cta_max - ctx->huff_static_smem[ti] - ctx->lut_bytes;
+                if (stage > cap) stage = cap;
+                stage &= ~15;
+                int ctas = ctx->smem_per_sm / (fixed + stage);
+                if (ctas < 1) ctas = 1;
+                if (ctas > 1024 / t) ctas = 1024 / t;  // 64 registers per thread: 1,024 threads per SM
+                const int warps = ctas * t / 32;
+                if (warps > best_warps) { best_warps = warps; best_t = t; best_ctas = ctas; best_stage = stage; }
+            }
+        }
+        const int tiles = (nu + best_t - 1) / best_t;
+        const int grid = std::min(tiles, ctx->sm_count * best_ctas);
+        const size_t dyn = (size_t)ctx->lut_bytes + (size_t)best_stage;
+        if (best_t == 256) k_huffman<256><<<grid, 256, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, best_stage / 16);
+        else if (best_t == 512) k_huffman<512><<<grid, 512, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, best_stage / 16);
+        else k_huffman<1024><<<grid, 1024, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, best_stage / 16);
     }
     if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][1], s));
     {
@@ -384,7 +431,7 @@ extern "C" int mp3gpu_decode_device_async(mp3gpu_ctx *ctx, const uint8_t *d_main
     for (size_t first = 0; first < n_granules; first += ctx->ws_granules) {
         int n = (int)std::min<size_t>(ctx->ws_granules, n_granules - first);
         int rc = launch_wave(ctx, d_main_data, main_data_len, d_units, (long long)first, n, d_pcm_out + first * 1152,
-                             slot < kTimingSlots ? slot : -1);
+                             slot < kTimingSlots ? slot : -1, (double)main_data_len / (2.0 * (double)n_granules));
         if (rc) return rc;
         if (slot < kTimingSlots) slot++;
         ctx->last.waves++;
@@ -491,7 +538,7 @@ extern "C" int mp3gpu_decode(mp3gpu_ctx *ctx, const uint8_t *main_data, size_t m
         CK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_in[r], 0));
         if (widx >= 3) CK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_out[r], 0));
         rc = launch_wave(ctx, ctx->d_main, main_data_len, ctx->d_units, (long long)first, n, ctx->d_pcm_ring[r],
-                         slot < kTimingSlots ? slot : -1);
+                         slot < kTimingSlots ? slot : -1, (double)main_data_len / (2.0 * (double)n_granules));
         if (rc) return rc;
         if (slot < kTimingSlots) slot++;
         CK(cudaEventRecord(ctx->ev_k[r], ctx->s_compute));

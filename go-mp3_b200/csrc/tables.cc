@@ -42,70 +42,87 @@ const int kSfSizeMpeg2[3][6][4] = {
 const long double kPiL = 3.14159265358979323846264338327950288L;
 
 // ---- Huffman LUT construction ------------------------------------------------
-// Entry formats: tables.h.  `pairs` trees carry (x, y); the two count1 trees carry the 4-bit (v w x y) pattern in the
-// x field.  `esc` marks x == 15 or y == 15 in the two trees every linbits table shares.
-struct LutBuilder {
-    std::vector<uint32_t> &lut;
+// Entry formats: tables.h.
+// Pair trees: every code word is extended by its sign bits (x's first, then y's: huffman.go:404-416) into 1, 2 or 4
+// "extended codes" whose leaves hold the signed pair; code words that take the linbits escape stay as they are.
+struct ExtCode {
+    uint32_t bits;   // the extended code, right-aligned
+    int len;
+    uint16_t entry;  // the leaf / escape entry
+};
+struct PairLutBuilder {
+    std::vector<uint16_t> &lut;
     size_t base;
-    const huff_code_t *codes;
-    int n;
-    bool quad, esc_tree;
-    LutBuilder(std::vector<uint32_t> &l, const huff_code_t *c, int n_, bool quad_, bool esc_tree_)
-        : lut(l), base(l.size()), codes(c), n(n_), quad(quad_), esc_tree(esc_tree_) {}
-
-    uint32_t leaf(const huff_code_t &c) const {
-        const int x = c.x, y = c.y, tlen = c.hlen;
-        int signs;
-        uint32_t e;
-        if (quad) {
-            const int q = y & 0xf;  // count1 tables are stored as (x = 0, y = v<<3 | w<<2 | x<<1 | y)
-            signs = ((q >> 3) & 1) + ((q >> 2) & 1) + ((q >> 1) & 1) + (q & 1);
-            e = (uint32_t)q;
-        } else {
-            signs = (x != 0) + (y != 0);
-            e = (uint32_t)x | ((uint32_t)y << 8);
-            if (esc_tree && (x == 15 || y == 15)) e |= 1u << 4;
-        }
-        const int total = tlen + signs;
-        e |= (uint32_t)tlen << 16;
-        e |= (uint32_t)((total - 1) & 31) << 21;
-        e |= (uint32_t)total << 26;
-        return e;
-    }
-
-    // Fill a table of `bits` index bits for all codes whose first `plen` bits equal `prefix`.
-    void fill(size_t off, int bits, uint32_t prefix, int plen, int sub_cap) {
-        for (uint32_t idx = 0; idx < (1u << bits); idx++) {
-            // Is there a code of length <= plen+bits that is a prefix of (prefix,idx)?
-            int found = -1;
-            for (int i = 0; i < n; i++) {
-                int L = codes[i].hlen;
-                if (L <= plen || L > plen + bits) continue;
-                uint32_t full = (prefix << bits) | idx;            // plen+bits bits
-                if ((full >> (plen + bits - L)) == codes[i].hcod) { found = i; break; }
-            }
-            if (found >= 0) {
-                lut[base + off + idx] = leaf(codes[found]);
+    std::vector<ExtCode> codes;
+    PairLutBuilder(std::vector<uint16_t> &l, const huff_code_t *c, int n, bool esc_tree) : lut(l), base(l.size()) {
+        for (int i = 0; i < n; i++) {
+            const int x = c[i].x, y = c[i].y, tlen = c[i].hlen;
+            if (esc_tree && (x == 15 || y == 15)) {
+                const int other = x == 15 ? y : x;
+                codes.push_back({c[i].hcod, tlen,
+                                 (uint16_t)(0xc000u | (uint32_t)tlen | (x == 15 ? 0x20u : 0u) | (y == 15 ? 0x40u : 0u) |
+                                            ((uint32_t)(other & 15) << 7))});
                 continue;
             }
-            // Need a sub-table: longest remaining length among codes with this (plen+bits)-bit prefix.
-            uint32_t full = (prefix << bits) | idx;
+            const int nsx = x != 0, nsy = y != 0;
+            for (int sx = 0; sx <= nsx; sx++)
+                for (int sy = 0; sy <= nsy; sy++) {
+                    const int xs = sx ? -x : x, ys = sy ? -y : y;
+                    uint32_t bits = c[i].hcod;
+                    int len = tlen;
+                    if (nsx) { bits = (bits << 1) | (uint32_t)sx; len++; }
+                    if (nsy) { bits = (bits << 1) | (uint32_t)sy; len++; }
+                    codes.push_back({bits, len, (uint16_t)(((uint32_t)xs & 31u) | (((uint32_t)ys & 31u) << 5) | ((uint32_t)len << 10))});
+                }
+        }
+    }
+    // Fill a table of `bits` index bits for all extended codes whose first `plen` bits equal `prefix`.
+    void fill(size_t off, int bits, uint32_t prefix, int plen) {
+        for (uint32_t idx = 0; idx < (1u << bits); idx++) {
+            const uint32_t full = (prefix << bits) | idx;  // plen + bits bits
+            int found = -1;
+            for (size_t i = 0; i < codes.size(); i++) {
+                const int L = codes[i].len;
+                if (L <= plen || L > plen + bits) continue;
+                if ((full >> (plen + bits - L)) == codes[i].bits) { found = (int)i; break; }
+            }
+            if (found >= 0) {
+                lut[base + off + idx] = codes[(size_t)found].entry;
+                continue;
+            }
             int maxrem = 0;
-            for (int i = 0; i < n; i++) {
-                int L = codes[i].hlen;
+            for (size_t i = 0; i < codes.size(); i++) {
+                const int L = codes[i].len;
                 if (L <= plen + bits) continue;
-                if ((codes[i].hcod >> (L - plen - bits)) == full) maxrem = std::max(maxrem, L - plen - bits);
+                if ((codes[i].bits >> (L - plen - bits)) == full) maxrem = std::max(maxrem, L - plen - bits);
             }
             if (maxrem == 0) throw std::runtime_error("huffman tree not complete");
-            int sb = std::min(maxrem, sub_cap);
-            size_t sub_off = lut.size() - base;
-            if (sub_off > 0xffff) throw std::runtime_error("huffman LUT too large");
-            lut.resize(lut.size() + (1u << sb), 0);
-            lut[base + off + idx] = 0x80000000u | ((uint32_t)sb << 16) | (uint32_t)sub_off;
-            fill(sub_off, sb, full, plen + bits, sub_cap);
+            const int sb = std::min(maxrem, kHuffSubBits);  // longer codes go through another link
+            while ((lut.size() - base) % 16) lut.push_back(0);  // a link addresses its sub-table in units of 16 entries
+            const size_t sub_off = lut.size() - base;
+            if (sub_off / 16 > 0x3ff) throw std::runtime_error("huffman LUT too large");
+            lut.resize(lut.size() + ((size_t)1 << sb), 0);
+            lut[base + off + idx] = (uint16_t)(0x8000u | ((uint32_t)sb << 10) | (uint32_t)(sub_off / 16));
+            fill(sub_off, sb, full, plen + bits);
         }
     }
 };
+
+// Count1 trees: at most 6 tree bits, one root table each (32-bit entries).
+uint32_t quad_leaf(const huff_code_t &c) {
+    const int q = c.y & 0xf;  // count1 tables are stored as (x = 0, y = v<<3 | w<<2 | x<<1 | y)
+    const int signs = ((q >> 3) & 1) + ((q >> 2) & 1) + ((q >> 1) & 1) + (q & 1);
+    return (uint32_t)q | ((uint32_t)c.hlen << 16) | ((uint32_t)(c.hlen + signs) << 26);
+}
+void fill_quad_root(uint32_t *root, const huff_code_t *codes, int n) {
+    for (uint32_t idx = 0; idx < (1u << kHuffRootBits); idx++) {
+        int found = -1;
+        for (int i = 0; i < n; i++)
+            if (codes[i].hlen <= kHuffRootBits && (idx >> (kHuffRootBits - codes[i].hlen)) == codes[i].hcod) { found = i; break; }
+        if (found < 0) throw std::runtime_error("count1 tree not complete within the root table");
+        root[idx] = quad_leaf(codes[found]);
+    }
+}
 
 }  // namespace
 
@@ -242,13 +259,13 @@ void build_host_tables(HostTables &t) {
     // Huffman LUTs: one per distinct tree; tables sharing a tree share the LUT.  Every root table is indexed by the
     // same kHuffRootBits bits, so the kernel's root lookup needs no per-table shift.
     t.huff_lut.clear();
-    // entries 0..2^root-1: the "empty table" LUT (zero-length zero leaves: total = 0, x = y = 0)
-    t.huff_lut.resize((size_t)1 << kHuffRootBits, (uint32_t)(31u << 21));
+    // entries 0..2^root-1: the "empty table" LUT (zero-length zero leaves: nothing consumed, x = y = 0)
+    t.huff_lut.resize((size_t)1 << kHuffRootBits, (uint16_t)0);
     const uint32_t empty_desc = 0u;
     const huff_code_t *seen[34];
     uint32_t seen_desc[34];
     int nseen = 0;
-    for (int tab = 0; tab < 34; tab++) {
+    for (int tab = 0; tab < 32; tab++) {
         const huff_table_desc_t &d = HUFF_TABLES[tab];
         if (d.codes == nullptr) {
             t.huff_desc[tab] = empty_desc;
@@ -259,18 +276,23 @@ void build_host_tables(HostTables &t) {
         for (int s = 0; s < nseen; s++)
             if (seen[s] == d.codes) { desc = seen_desc[s]; have = true; }
         if (!have) {
-            LutBuilder b(t.huff_lut, d.codes, d.n, tab >= 32, d.linbits != 0);
-            if (b.base * 4 > 0xffffff) throw std::runtime_error("huffman LUT base overflow");
+            while (t.huff_lut.size() % 16) t.huff_lut.push_back(0);
+            PairLutBuilder b(t.huff_lut, d.codes, d.n, d.linbits != 0);
+            if (b.base * 2 > 0xffffff) throw std::runtime_error("huffman LUT base overflow");
             t.huff_lut.resize(t.huff_lut.size() + ((size_t)1 << kHuffRootBits), 0);
-            b.fill(0, kHuffRootBits, 0, 0, 11);  // 19 - 8: every sub-table resolves the rest of its codes, so there are two levels at most
-            desc = (uint32_t)b.base * 4u;
+            b.fill(0, kHuffRootBits, 0, 0);
+            desc = (uint32_t)b.base * 2u;
             seen[nseen] = d.codes;
             seen_desc[nseen] = desc;
             nseen++;
         }
         t.huff_desc[tab] = desc | ((uint32_t)d.linbits << 24);
     }
-    while (t.huff_lut.size() % 4) t.huff_lut.push_back(0);  // staged 16 bytes at a time (k_huffman)
+    while (t.huff_lut.size() % 8) t.huff_lut.push_back(0);  // staged 16 bytes at a time (k_huffman)
+    for (int q = 0; q < 2; q++) {
+        fill_quad_root(t.quad_lut + q * 256, HUFF_TABLES[32 + q].codes, HUFF_TABLES[32 + q].n);
+        t.huff_desc[32 + q] = (uint32_t)(q * 256 * 4);
+    }
     // count1 sign expansion: index = pattern << 4 | the four bits after the tree bits; value = the two output words
     // (v | w << 16) and (x | y << 16) << 32 with the sign bits dealt to the non-zero values in order (huffman.go:387-403)
     for (int q = 0; q < 16; q++)

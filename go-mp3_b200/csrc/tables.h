@@ -20,18 +20,28 @@ constexpr int kPow2N = 400;
 constexpr int kPowRow = 8208;   // row length of powq4 (8,207 values of |is| + padding)
 constexpr int kNumCfg = 6;      // cfg = lsf*3 + sampling_frequency index
 
-// Huffman LUT entry (uint32).  Every tree's root table is indexed by the first kHuffRootBits bits of the code stream.
-//   leaf : bit31 = 0
-//          bits 0..3   x (pairs) / the (v w x y) pattern (count1 trees)
-//          bit  4      escape: x == 15 or y == 15 in a tree used with linbits (tables 16..31)
-//          bits 8..11  y
+// Huffman LUTs.  Every tree's root table is indexed by the first kHuffRootBits bits of the code stream.
+//
+// Pair trees (tables 1..31): uint16 entries, and the SIGN BITS that follow a code word are part of the index — a leaf is
+// the finished, signed pair, so the decode step has no sign arithmetic (tables.cc, build_pair_lut):
+//   leaf   : bit15 = 0, bits 0..4 = x, bits 5..9 = y (5-bit two's complement, -15..15), bits 10..14 = bits consumed
+//            (tree bits + sign bits, 0..21; 0 only in the empty tables 0/4/14, which consume nothing: huffman.go:354-356)
+//   link   : bits 15..14 = 10, bits 10..13 = sb in 1..kHuffSubBits: a sub-table of 2^sb entries, indexed by the next sb
+//            bits, starts (bits 0..9) * 16 entries after the tree's base; its entries are leaves, escapes or further links
+//   escape : bits 15..14 = 11: x == 15 or y == 15 in a tree used with linbits (tables 16..31), where linbits sit between
+//            the code word and the signs; bits 0..4 = tree bits, bit 5 = x is 15, bit 6 = y is 15, bits 7..10 = the other
+//            value (unused when both are 15).  Escape code words are indexed by tree bits only.
+//   Read as int16: leaf >= 0, link < -16384 <= escape < 0 — one compare each in the decode loop.
+// Count1 trees (tables 32/33, at most 6 tree bits): uint32 entries in a separate 2 x 256 table (quad_lut):
+//          bits 0..3   the (v w x y) pattern
 //          bits 16..20 tree bits of the code word
-//          bits 21..25 (total - 1) & 31      \  total = tree bits + sign bits that follow when no escape is taken;
-//          bits 26..30 total                 /  the first two fields are used as (mod 32) shift counts
-//   link : bit31 = 1, bits 16..20 = sub-table index bits, bits 0..15 = sub-table offset (entries) from the tree's base
-// Table descriptor (uint32): bits 0..23 = byte offset of the tree's root table in the LUT, bits 24..27 = linbits.
-// Tables 0/4/14 (empty: huffman.go:354-356) map to a root table of zero-length zero leaves: they consume nothing.
+//          bits 26..30 tree bits + sign bits
+// Table descriptor (uint32): bits 0..23 = byte offset of the tree's root table in its LUT, bits 24..27 = linbits.
 constexpr int kHuffRootBits = 8;
+#ifndef MP3_HUFF_SUB_BITS
+#define MP3_HUFF_SUB_BITS 8
+#endif
+constexpr int kHuffSubBits = MP3_HUFF_SUB_BITS;   // index bits of a sub-table at most (codes reach 21 bits with their signs: up to three levels)
 struct HostTables {
     float cos36[18 * 36];
     float cos12[6 * 12];
@@ -56,8 +66,9 @@ struct HostTables {
     uint16_t pair_dst[kNumCfg][288];
     uint16_t nslen2[512];
     uint8_t sfsize_mpeg2[3][6][4];
-    std::vector<uint32_t> huff_lut;
-    uint64_t quad_signs[256];       // count1 sign expansion, see tables.cc
+    std::vector<uint16_t> huff_lut;   // pair trees (16-bit entries, see above); size is a multiple of 8 entries
+    uint32_t quad_lut[2 * 256];       // count1 trees
+    uint64_t quad_signs[256];         // count1 sign expansion, see tables.cc
     uint32_t huff_desc[34];
 };
 

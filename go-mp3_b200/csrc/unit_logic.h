@@ -39,7 +39,8 @@ struct DeviceTables {
     const uint16_t *sfb_long;       // [6][24]
     const uint16_t *sfb_short;      // [6][16]
     const uint16_t *nslen2;         // [512]
-    const uint32_t *huff_lut;       // LUT entries (see tables.h)
+    const uint16_t *huff_lut;       // pair-tree LUT entries (see tables.h)
+    const uint32_t *quad_lut;       // [2][256] count1-tree LUT entries
     const uint32_t *huff_desc;      // [34]
     const uint64_t *quad_signs;     // [256] count1 sign expansion
     const float *is_ratio_l;        // [8]
@@ -50,7 +51,7 @@ struct DeviceTables {
     const float *cs;                // [8]
     const float *ca;                // [8]
     uint64_t pretab_pack;           // pretab[sfb] in bits 2*sfb .. 2*sfb+1
-    int huff_lut_n;
+    int huff_lut_n;                 // uint16 entries, a multiple of 8
     int pow2_off;
 };
 
@@ -111,6 +112,7 @@ MP3_HD uint32_t funnel_l(uint32_t hi, uint32_t lo, int s) { s &= 31; return s ? 
 #endif
 
 struct BitCursor {
+    static constexpr bool kFast = false;  // no unchecked fast path (see StagedCursor)
     const uint32_t *wp;     // next 32-bit word of main_data to prefetch
     uint32_t w0, w1;        // current window (big-endian bit order, masked at the buffer end)
     uint32_t nxt;           // the word after w1 as loaded (raw byte order, unmasked; 0 when at/after the buffer end)
@@ -179,6 +181,133 @@ struct BitCursor {
     }
 };
 
+// ---- staged cursor: the same bits.go semantics over a stretch of main data staged in shared memory ----------------
+// k_huffman copies the stretch of main_data its tile of units refers to into shared memory (coalesced 16-byte
+// loads, byte-swapped once into big-endian bit order) and every unit reads its code stream from there.  The cursor is
+// then nothing but a bit position: peek32() is two shared-memory loads and one funnel shift, skip() is an addition.
+// There is no window to refill, which in the register-window cursor above was a divergent branch taken by one
+// lane in four at every code word (26 % of K1's issue slots in ncu, profiles/).  Positions outside the staged stretch
+// (malformed descriptors, a unit whose buffer reaches further than its tile's stretch, the scfsi look-back of a
+// tile's first units) fall back to global loads word by word: rare, slow and exact.
+// A read-only array in the kernel's shared memory.  On the device it is held as the 32-bit shared-window address and read
+// with explicit ld.shared: handed a generic pointer, the compiler re-derives that address at every use (four instructions
+// per code word in K1's inner loop).  In the host emulation it is a plain pointer.
+#if defined(__CUDA_ARCH__)
+struct SmemRef {
+    uint32_t a;
+    MP3_HD static SmemRef of(const void *p) { SmemRef r; r.a = (uint32_t)__cvta_generic_to_shared(p); return r; }
+    MP3_HD SmemRef plus(uint32_t bytes) const { SmemRef r; r.a = a + bytes; return r; }
+    MP3_HD int lds16(uint32_t off) const {  // sign-extended
+        int v;
+        asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a + off));
+        return v;
+    }
+    MP3_HD uint32_t ld32(uint32_t off) const {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a + off));
+        return v;
+    }
+    MP3_HD void ld32x2(uint32_t off, uint32_t &w0, uint32_t &w1) const {
+        asm volatile("ld.shared.u32 %0, [%2];\n\tld.shared.u32 %1, [%2+4];" : "=r"(w0), "=r"(w1) : "r"(a + off));
+    }
+};
+#else
+struct SmemRef {
+    const uint8_t *a;
+    MP3_HD static SmemRef of(const void *p) { SmemRef r; r.a = static_cast<const uint8_t *>(p); return r; }
+    MP3_HD SmemRef plus(uint32_t bytes) const { SmemRef r; r.a = a + bytes; return r; }
+    MP3_HD int lds16(uint32_t off) const { int16_t v; __builtin_memcpy(&v, a + off, 2); return v; }
+    MP3_HD uint32_t ld32(uint32_t off) const { uint32_t v; __builtin_memcpy(&v, a + off, 4); return v; }
+    MP3_HD void ld32x2(uint32_t off, uint32_t &w0, uint32_t &w1) const { w0 = ld32(off); w1 = ld32(off + 4); }
+};
+#endif
+
+struct StageCtx {
+    SmemRef sw;                   // staged words: word i = bits [32 i, 32 i + 32) of the stretch, MSB first
+    int n_words;                  // staged words
+    unsigned long long lo_word;   // index (in 32-bit words of main_data) of staged word 0
+    const uint32_t *gw;           // main_data as words (fallback)
+    unsigned long long main_bits;
+};
+// Stretch of main data one unit may touch, in 16-byte chunks [lo16, hi16): from its first part2 bit to the end of
+// part 3 (a part2_3_length of 0 still reads its scalefactors, quirk Q1), never beyond the frame's buffer end.  A unit
+// that runs past that (big_values never checks the bit budget, quirk Q4) leaves the stretch and takes the fallback.
+MP3_HD void stage_reach(const mp3gpu_unit &u, unsigned long long main_bits, uint32_t *lo16, uint32_t *hi16) {
+    unsigned long long start = u.bit_start;
+    if (start > main_bits) start = main_bits;
+    const int ber = u.buf_end_rel > 0 ? u.buf_end_rel : 0;
+    const int want = u_p23len(u.w0) > 256 ? u_p23len(u.w0) : 256;
+    const int reach = (ber < want ? ber : want) + 64;
+    *lo16 = (uint32_t)(start >> 7);
+    *hi16 = (uint32_t)((start + (unsigned)reach + 127) >> 7);
+}
+
+struct StagedCursor {
+    static constexpr bool kFast = true;
+    SmemRef sw;             // staged words, already offset to the word holding the unit's first bit (valid if sidx0 >= 0)
+    int n_words_m1;         // a window needs words si and si + 1
+    const uint32_t *gbase;  // main_data word holding the unit's first bit (fallback)
+    int sidx0;              // staged index of that word; far negative when the unit starts outside the stretch
+    int p;                  // cursor: bits from the MSB of that word (virtual: keeps counting past the buffer end)
+    int off0;               // p at logical position 0
+    int end;                // p of the frame's buffer end; bits at/after it read as 0 (bits.go:46-49,65-68)
+    int lim;                // max(buf_end_rel, 0): the logical position never advances past it
+    int fast_lim;           // p <= fast_lim: the 64 bits from p on lie inside the stretch and before the buffer end, so
+                            // peek32_fast() is exact there, pos() needs no clamp and no Bits(n) <= 32 can be refused
+
+    MP3_HD void init(const StageCtx &S, unsigned long long bit_start, int buf_end_rel) {
+        if (bit_start > S.main_bits) bit_start = S.main_bits;  // same clipping as BitCursor::init
+        const unsigned long long room = S.main_bits - bit_start;
+        if (buf_end_rel > 0 && (unsigned long long)buf_end_rel > room) buf_end_rel = (int)room;
+        const unsigned long long word = bit_start >> 5;
+        n_words_m1 = S.n_words > 0 ? S.n_words - 1 : 0;
+        gbase = S.gw + word;
+        const long long d = (long long)word - (long long)S.lo_word;
+        sidx0 = (d >= 0 && d < (long long)S.n_words) ? (int)d : -(1 << 30);
+        sw = S.sw.plus(sidx0 >= 0 ? (uint32_t)sidx0 * 4u : 0u);
+        off0 = (int)(bit_start & 31);
+        p = off0;
+        end = off0 + buf_end_rel;
+        lim = buf_end_rel > 0 ? buf_end_rel : 0;
+        fast_lim = -(1 << 30);
+        if (sidx0 >= 0) {
+            const int staged_end = (S.n_words - sidx0) * 32;  // p of the first bit behind the staged words
+            fast_lim = (end < staged_end ? end : staged_end) - 64;
+        }
+    }
+    MP3_HD uint32_t peek32_fast() const {  // requires p <= fast_lim
+        uint32_t w0, w1;
+        sw.ld32x2((uint32_t)(p >> 5) * 4u, w0, w1);
+        return funnel_l(w0, w1, p);
+    }
+    MP3_HD uint32_t peek32() const {  // next 32 bits, MSB first
+        const int idx = p >> 5, si = sidx0 + idx;
+        uint32_t w0 = 0, w1 = 0;
+        if ((uint32_t)si < (uint32_t)n_words_m1) {
+            sw.ld32x2((uint32_t)idx * 4u, w0, w1);
+        } else if (p < end) {  // outside the stretch: the two words straight from main_data (a word holding a bit below the buffer end lies inside main_data; the next one inside its tail padding)
+            w0 = be32(load_raw32(gbase + idx));
+            w1 = be32(load_raw32(gbase + idx + 1));
+        }
+        const int rem = end - p;  // bits left before the buffer end
+        return funnel_l(w0, w1, p) & ~ones_shr_clamp(rem > 0 ? rem : 0);
+    }
+    MP3_HD int pos() const { return imin(p - off0, lim); }
+    MP3_HD void skip(int n) { p += n; }
+    MP3_HD int bits(int n) {  // Bits(n), bits.go:58-77: returns 0 WITHOUT advancing when the read would cross the end
+        if (n == 0) return 0;
+        if (pos() + n > lim) return 0;
+        const int v = (int)(peek32() >> (32 - n));
+        p += n;
+        return v;
+    }
+    MP3_HD int bit() {
+        const int v = (int)(peek32() >> 31);
+        p += 1;
+        return v;
+    }
+};
+
 // ---- Huffman code words (LUT entry layout: tables.h) -------------------------------------------------------------
 // the top (n mod 32) bits of x, as a number
 #if defined(__CUDA_ARCH__)
@@ -187,18 +316,6 @@ MP3_HD uint32_t hi_bits_mod32(uint32_t x, uint32_t n) { return __funnelshift_l(x
 MP3_HD uint32_t hi_bits_mod32(uint32_t x, uint32_t n) { n &= 31; return n ? x >> (32 - n) : 0u; }
 #endif
 constexpr int kRootBits = 8;  // == tables.h kHuffRootBits
-MP3_HD uint32_t lut_at(const uint32_t *lut, uint32_t byte_off) {
-    return *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(lut) + byte_off);
-}
-// Leaf entry of the code word at the head of w (MSB first); d = byte offset of the tree's root table.
-MP3_HD uint32_t huff_lookup(const uint32_t *lut, uint32_t d, uint32_t w) {
-    uint32_t e = lut_at(lut, d + ((w >> (32 - kRootBits)) << 2));
-    if ((int32_t)e < 0) {  // code longer than the root index: one sub-table resolves the rest (tables.cc)
-        const uint32_t idx = (e & 0xffff) + hi_bits_mod32(w << kRootBits, e >> 16);
-        e = lut_at(lut, d + (idx << 2));
-    }
-    return e;
-}
 // x << (n mod 32): the LUT's shift-count fields are used without masking their neighbours off
 #if defined(__CUDA_ARCH__)
 MP3_HD uint32_t shl_mod32(uint32_t x, uint32_t n) { return __funnelshift_l(0u, x, n); }  // the funnel shift wraps its count itself
@@ -206,19 +323,49 @@ MP3_HD uint32_t shl_mod32(uint32_t x, uint32_t n) { return __funnelshift_l(0u, x
 MP3_HD uint32_t shl_mod32(uint32_t x, uint32_t n) { return funnel_l(x, 0u, (int)(n & 31)); }
 #endif
 
+MP3_HD uint32_t lut_at(const uint32_t *lut, uint32_t byte_off) {
+    return *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(lut) + byte_off);
+}
+// Pair trees: entry (as int16, tables.h) of the code word — sign bits included — at the head of w (MSB first); `tree` is the
+// tree's root table.  The result is a leaf (>= 0) or an escape entry (< 0).
+MP3_HD int huff_lookup16(SmemRef tree, uint32_t w) {
+    int e = tree.lds16((w >> (31 - kRootBits)) & (((1u << kRootBits) - 1u) << 1));
+    uint32_t rest = w << kRootBits;
+    while (e < -16384) {  // link: the code (with its signs) is longer than the bits indexed so far; three levels at most
+        const uint32_t sb = ((uint32_t)e >> 10) & 15u;
+        e = tree.lds16((((uint32_t)e & 0x3ffu) << 5) + (hi_bits_mod32(rest, sb) << 1));
+        rest = shl_mod32(rest, sb);
+    }
+    return e;
+}
+// Signed 5-bit field of a leaf at bit `pos`, and the packed output word (x | y << 16 as int16 halves).
+#if defined(__CUDA_ARCH__)
+MP3_HD uint32_t leaf_pair(int e) {
+    int x, y;
+    asm("bfe.s32 %0, %1, 0, 5;" : "=r"(x) : "r"(e));
+    asm("bfe.s32 %0, %1, 5, 5;" : "=r"(y) : "r"(e));
+    return __byte_perm((uint32_t)x, (uint32_t)y, 0x5410);
+}
+#else
+MP3_HD uint32_t leaf_pair(int e) {
+    const int x = (int)((uint32_t)e << 27) >> 27, y = (int)((uint32_t)e << 22) >> 27;
+    return ((uint32_t)x & 0xffffu) | ((uint32_t)y << 16);
+}
+#endif
+
 // One big_values pair (huffman.go:404-416).  Returns x | y<<16 (int16 halves).  linbits() is only evaluated for an
 // escape (x or y == 15 in a table with linbits).
-template <class LinbitsFn>
-MP3_HD uint32_t huff_pair(const uint32_t *lut, uint32_t d, LinbitsFn linbits_of, BitCursor &bc) {
-    const uint32_t w = bc.peek32();
-    const uint32_t e = huff_lookup(lut, d, w);
-    int x = (int)(e & 0xf), y = (int)((e >> 8) & 0xf);
-    if (e & 0x10u) {
+template <class BC, class LinbitsFn>
+MP3_HD uint32_t huff_pair(SmemRef tree, LinbitsFn linbits_of, BC &bc) {
+    const int e = huff_lookup16(tree, bc.peek32());
+    if (e < 0) {
         // Escape: x-linbits, x-sign, y-linbits, y-sign (huffman.go:405-416) are at most 2 * 13 + 2 = 28 bits, one window.
         // The reference reads them with Bits(n) / Bit(), which refuse to read (return 0, do not advance) at the end of
         // the frame's buffer (bits.go:45-77); p is that logical cursor.
+        const int other = (e >> 7) & 15;
+        int x = (e & 0x20) ? 15 : other, y = (e & 0x40) ? 15 : other;
         const int linbits = linbits_of();
-        bc.skip((int)((e >> 16) & 0x1f));
+        bc.skip(e & 31);
         const uint32_t v = bc.peek32();
         const int p0 = bc.pos(), lim = bc.lim;
         int p = p0;
@@ -227,23 +374,42 @@ MP3_HD uint32_t huff_pair(const uint32_t *lut, uint32_t d, LinbitsFn linbits_of,
         if (y == 15 && p + linbits <= lim) { y += (int)((v << (p - p0)) >> (32 - linbits)); p += linbits; }
         if (y != 0 && p < lim) { if ((v << (p - p0)) >> 31) y = -y; p++; }
         bc.skip(p - p0);
-    } else {
-        // x's sign bit (if x != 0) follows the tree bits, y's (if y != 0) is the last of the `total` bits; the tree is
-        // at most 19 bits, so both lie inside w.  A zero value ignores the mask it gets: (0 ^ m) - m == 0.
-        const int mx = (int32_t)shl_mod32(w, e >> 16) >> 31;
-        const int my = (int32_t)shl_mod32(w, e >> 21) >> 31;
-        x = (x ^ mx) - mx;
-        y = (y ^ my) - my;
-        bc.skip((int)(e >> 26));
+        return ((uint32_t)x & 0xffffu) | ((uint32_t)y << 16);
     }
-    return ((uint32_t)x & 0xffffu) | ((uint32_t)y << 16);
+    // The sign bits were part of the index (bits at/after the buffer end read as 0, like the reference's Bit()); the
+    // cursor's logical position clamps at the end by itself.
+    bc.skip(e >> 10);
+    return leaf_pair(e);
+}
+
+// The same pair where nothing can touch the buffer end (StagedCursor, bc.p <= bc.fast_lim): no refused reads, no clamp.
+template <class BC, class LinbitsFn>
+MP3_HD uint32_t huff_pair_fast(SmemRef tree, LinbitsFn linbits_of, BC &bc) {
+    const int e = huff_lookup16(tree, bc.peek32_fast());
+    if (e < 0) {
+        const int other = (e >> 7) & 15;
+        int x = (e & 0x20) ? 15 : other, y = (e & 0x40) ? 15 : other;
+        const int linbits = linbits_of();  // >= 1 in every table that has escapes
+        bc.p += e & 31;
+        uint32_t v = bc.peek32_fast();  // at most 19 tree bits were skipped: still inside the 64 bits fast_lim vouches for
+        int n = 0;
+        if (x == 15) { x += (int)(v >> (32 - linbits)); v <<= linbits; n = linbits; }
+        if (x != 0) { if ((int32_t)v < 0) x = -x; v <<= 1; n++; }
+        if (y == 15) { y += (int)(v >> (32 - linbits)); v <<= linbits; n += linbits; }
+        if (y != 0) { if ((int32_t)v < 0) y = -y; n++; }
+        bc.p += n;
+        return ((uint32_t)x & 0xffffu) | ((uint32_t)y << 16);
+    }
+    bc.p += e >> 10;
+    return leaf_pair(e);
 }
 
 // One count1 quadruple (huffman.go:387-403): v, w, x, y each in {-1, 0, 1}; returns (v | w<<16), (x | y<<16).
 // quad_signs[pattern << 4 | next four bits] holds both words with the sign bits dealt out (tables.cc).
-MP3_HD void huff_quad(const uint32_t *lut, const uint64_t *quad_signs, uint32_t d, BitCursor &bc, uint32_t &vw, uint32_t &xy) {
+template <class BC>
+MP3_HD void huff_quad(const uint32_t *qlut, const uint64_t *quad_signs, uint32_t d, BC &bc, uint32_t &vw, uint32_t &xy) {
     const uint32_t wd = bc.peek32();
-    const uint32_t e = huff_lookup(lut, d, wd);                   // <= 6 tree bits, then up to 4 sign bits
+    const uint32_t e = lut_at(qlut, d + ((wd >> (32 - kRootBits)) << 2));  // <= 6 tree bits, then up to 4 sign bits
     const uint32_t four = shl_mod32(wd, e >> 16) >> 28;
     const uint64_t r = quad_signs[((e & 0xf) << 4) | four];
     bc.skip((int)(e >> 26));
@@ -296,9 +462,47 @@ struct NibWriter {
     MP3_HD void seek(int n1) { flush(); n = n1; }
 };
 
+// A run of `count` scalefactors of `slen` bits each (maindata.go:146-162, 207-279).  Bits(n) refuses a read that would
+// cross the buffer end (returns 0, does not advance), value by value; when the whole run lies before the end — every
+// well-formed stream — nothing can be refused and the values are peeled off 32-bit windows, several per peek.
+MP3_HD int sf_per_window(int slen) { return (int)((0x040506080a102000ull >> (8 * slen)) & 0xff); }  // 32 / slen for slen 1..7: 32, 16, 10, 8, 6, 5, 4
+template <class BC>
+MP3_HD void sf_run(BC &bc, NibWriter &nw, int count, int slen) {
+    if (slen == 0 || bc.pos() + count * slen > bc.lim) {
+#pragma unroll 1
+        for (int i = 0; i < count; i++) nw.put(bc.bits(slen));
+        return;
+    }
+    const int per = sf_per_window(slen);
+#pragma unroll 1
+    while (count > 0) {
+        const int m = count < per ? count : per;
+        uint32_t w = bc.peek32();
+#pragma unroll 1
+        for (int j = 0; j < m; j++) {
+            nw.put((int)(w >> (32 - slen)));
+            w <<= slen;
+        }
+        bc.skip(m * slen);
+        count -= m;
+    }
+}
+// The same run read and thrown away (the scfsi look-back cursor passing over a band its unit reads itself).
+template <class BC>
+MP3_HD void sf_skip_run(BC &bc, int count, int slen) {
+    if (slen == 0 || count <= 0) return;
+    if (bc.pos() + count * slen <= bc.lim) {
+        bc.skip(count * slen);
+        return;
+    }
+#pragma unroll 1
+    for (int i = 0; i < count; i++) (void)bc.bits(slen);
+}
+
 // Scalefactors of an MPEG-1 unit that reads all of them itself: gr 0, or gr 1 short blocks, or
 // gr 1 with no scfsi band set (maindata.go:204-232 and the read arms of :233-279).
-MP3_HD void sf_mpeg1_read_all(const DeviceTables &T, BitCursor &bc, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t *pk) {
+template <class BC>
+MP3_HD void sf_mpeg1_read_all(const DeviceTables &T, BC &bc, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t *pk) {
     int sfc = u_sfcomp(w1) & 15;
     int slen1 = T.slen_mpeg1[sfc * 2], slen2 = T.slen_mpeg1[sfc * 2 + 1];
     NibWriter nw;
@@ -306,34 +510,32 @@ MP3_HD void sf_mpeg1_read_all(const DeviceTables &T, BitCursor &bc, uint32_t w0,
     if (u_winsw(w0) == 1 && u_btype(w0) == 2) {
         int sfb0 = 0;
         if (u_mixed(w2)) {
-#pragma unroll 1
-            for (int sfb = 0; sfb < 8; sfb++) nw.put(bc.bits(slen1));
+            sf_run(bc, nw, 8, slen1);
             sfb0 = 3;
         }
         nw.seek(22 + sfb0 * 3);
-#pragma unroll 1
-        for (int n = sfb0 * 3; n < 36; n++) nw.put(bc.bits(n < 18 ? slen1 : slen2));
+        sf_run(bc, nw, 18 - sfb0 * 3, slen1);  // n = sfb*3 + win < 18: slen1
+        sf_run(bc, nw, 18, slen2);
     } else {
-#pragma unroll 1
-        for (int sfb = 0; sfb < 21; sfb++) nw.put(bc.bits(sfb < 11 ? slen1 : slen2));
+        sf_run(bc, nw, 11, slen1);
+        sf_run(bc, nw, 10, slen2);
     }
     nw.flush();
 }
 
-// K1 for one unit, in two stages so that a CTA can re-deal its units to threads in between (kernels.cuh):
-//   stage A  scalefactors + the big_values pairs in whole groups of four   (cost ~ big_values)
-//   stage B  the last big_values % 4 pairs + the count1 quadruples         (cost ~ bits left in part 3)
-// `units` is the whole submission (absolute indexing): a gr-1 unit with scfsi set re-reads gr 0's scalefactor
-// bits (maindata.go:239-278, quirk Q14).
+// K1 for one unit: scalefactors (part 2), then the big_values pairs and the count1 quadruples (part 3), with one
+// cursor from the first part2 bit to the end.  `units` is the whole submission (absolute indexing): a gr-1 unit with
+// scfsi set re-reads gr 0's scalefactor bits (maindata.go:239-278, quirk Q14).  `mk(cursor, bit_start, buf_end_rel)`
+// positions a cursor of type BC (k_huffman: a StagedCursor over the tile's staged stretch of main data).
 // Outputs: pk[8] scalefactor nibbles (n = sfb for scalefac_l, 22 + sfb*3 + win for scalefac_s), is_out[0..count1/2)
-// packed int16 pairs, meta = count1 | preflag << 10.  Lines >= count1 are zero by definition; K2 masks them
+// packed int16 pairs, return value = count1 | preflag << 10.  Lines >= count1 are zero by definition; K2 masks them
 // instead of K1 writing zeros.
 struct HuffRegions {  // region starts in PAIRS (all sfb boundaries are even) and the three trees
     int r1h, r2h, nbig;
-    uint32_t d0, d1, d2;  // byte offset of the root table of each region's tree
+    SmemRef t0, t1, t2;   // root table of each region's tree
     uint32_t lin;         // linbits of the three regions, 4 bits each
 };
-MP3_HD HuffRegions huff_regions(const DeviceTables &T, const uint32_t *huff_desc, uint32_t w0, uint32_t w1, uint32_t w2) {
+MP3_HD HuffRegions huff_regions(const DeviceTables &T, SmemRef lut, const uint32_t *huff_desc, uint32_t w0, uint32_t w1, uint32_t w2) {
     HuffRegions R;
     if (u_winsw(w0) == 1 && u_btype(w0) == 2) {
         R.r1h = 18;
@@ -348,69 +550,67 @@ MP3_HD HuffRegions huff_regions(const DeviceTables &T, const uint32_t *huff_desc
     R.nbig = u_bigval(w0);
     if (R.nbig > 288) R.nbig = 288;  // the host rejects such frames (huffman.go:68-70); never reached
     const uint32_t e0 = huff_desc[u_tsel(w1, 0)], e1 = huff_desc[u_tsel(w1, 1)], e2 = huff_desc[u_tsel(w1, 2)];
-    R.d0 = e0 & 0xffffffu;
-    R.d1 = e1 & 0xffffffu;
-    R.d2 = e2 & 0xffffffu;
+    R.t0 = lut.plus(e0 & 0xffffffu);
+    R.t1 = lut.plus(e1 & 0xffffffu);
+    R.t2 = lut.plus(e2 & 0xffffffu);
     R.lin = (e0 >> 24) | ((e1 >> 24) << 4) | ((e2 >> 24) << 8);
     return R;
 }
-MP3_HD uint32_t huff_pair_at(const uint32_t *lut, const HuffRegions &R, int k, BitCursor &bc) {
+template <class BC>
+MP3_HD uint32_t huff_pair_at(const HuffRegions &R, int k, BC &bc) {
     const bool in0 = k < R.r1h, in1 = k < R.r2h;
-    return huff_pair(lut, in0 ? R.d0 : (in1 ? R.d1 : R.d2),
+    return huff_pair(in0 ? R.t0 : (in1 ? R.t1 : R.t2),
                      [&] { return (int)((R.lin >> (in0 ? 0 : (in1 ? 4 : 8))) & 0xf); }, bc);
 }
+template <class BC>
+MP3_HD uint32_t huff_pair_fast_at(const HuffRegions &R, int k, BC &bc) {
+    const bool in0 = k < R.r1h, in1 = k < R.r2h;
+    return huff_pair_fast(in0 ? R.t0 : (in1 ? R.t1 : R.t2),
+                          [&] { return (int)((R.lin >> (in0 ? 0 : (in1 ? 4 : 8))) & 0xf); }, bc);
+}
 
-// State handed from stage A to stage B: bits 0..29 logical cursor position (relative to bit_start), bit 30 preflag,
-// bit 31 = nothing left to do (part2_3_length == 0, quirk Q1: nothing decoded, Count1 stays 0).
-constexpr uint32_t kHuffDone = 0x80000000u;
-MP3_HD int huff_state_pos(uint32_t st) { return (int)(st & 0x3fffffffu); }
-MP3_HD int huff_state_preflag(uint32_t st) { return (int)((st >> 30) & 1); }
-
-MP3_HD uint32_t huffman_stage_a(const DeviceTables &T, const uint32_t *lut, const uint32_t *huff_desc,
-                                const uint8_t *main_data, uint64_t main_bits, const mp3gpu_unit *units, long long unit_index,
-                                uint32_t *pk, uint32_t *is_out) {
+template <class BC, class MkCursor>
+MP3_HD uint32_t huffman_unit_t(const DeviceTables &T, SmemRef lut, const uint32_t *qlut, const uint32_t *huff_desc, const uint64_t *quad_signs,
+                               const mp3gpu_unit *units, long long unit_index, MkCursor mk, uint32_t *pk, uint32_t *is_out) {
     const mp3gpu_unit u = units[unit_index];
     const uint32_t w0 = u.w0, w1 = u.w1, w2 = u.w2;
-    BitCursor bc;
-    bc.init(main_data, main_bits, u.bit_start, u.buf_end_rel);
+    BC bc;
+    mk(bc, u.bit_start, u.buf_end_rel);
     for (int i = 0; i < 8; i++) pk[i] = 0;
 
     // ---- part 2: scalefactors -------------------------------------------------------------
-    int preflag = u_preflag(w2);
+    uint32_t preflag = (uint32_t)u_preflag(w2);
     if (u_lsf(w2)) {
         // maindata.go:132-179
         int slen = T.nslen2[u_sfcomp(w1)];
-        preflag = (slen >> 15) & 1;
+        preflag = (uint32_t)((slen >> 15) & 1);
         int n = 0;
         if (u_btype(w0) == 2) {
             n++;
             if (u_mixed(w2)) n++;
         }
-        int d = (slen >> 12) & 7;
-        // long blocks fill scalefac_l[idx]; short fill scalefac_s[idx/3][idx%3] (maindata.go:169-179)
+        const int d = (slen >> 12) & 7;
+        // long blocks fill scalefac_l[idx]; short fill scalefac_s[idx/3][idx%3] (maindata.go:169-179).  The four group
+        // sizes of a row add up to at most 36 values (tables.cc kSfSizeMpeg2), so the nibble index stays below 22 + 36.
         NibWriter nw;
         nw.init(pk, n == 0 ? 0 : 22);
 #pragma unroll 1
         for (int i = 0; i < 4; i++) {
-            int num = slen & 7;
+            const int num = slen & 7;
             slen >>= 3;
-            int cnt = T.sfsize_mpeg2[(n * 6 + d) * 4 + i];
-#pragma unroll 1
-            for (int k = 0; k < cnt; k++) {
-                int v = num > 0 ? bc.bits(num) : 0;
-                if (nw.n < 64) nw.put(v);
-            }
+            sf_run(bc, nw, (int)T.sfsize_mpeg2[(n * 6 + d) * 4 + i], num);
         }
-        if (nw.n < 64) nw.flush();
+        nw.flush();
     } else if (u_gr(w2) == 0 || (u_winsw(w0) == 1 && u_btype(w0) == 2) || u_scfsi(w2) == 0) {
         sf_mpeg1_read_all(T, bc, w0, w1, w2, pk);
     } else {
         // gr 1, long-type block, at least one scfsi band set: those bands copy ScalefacL[0][ch] as gr 0's parse left it
         // (21 values if gr 0 was a long-type block, sfb 0-7 only if it was mixed, zeros if it was short).  gr 0's
-        // scalefactor bits are re-read by a second cursor in step with this unit's own.
+        // scalefactor bits are re-read by a second cursor, band by band: a band this unit copies is read from it, a
+        // band this unit reads itself is passed over.
         int n0 = 0, s1_0 = 0, s2_0 = 0;
-        BitCursor b0;
-        b0.init(main_data, main_bits, 0, 0);
+        BC b0;
+        mk(b0, 0, 0);
         if (unit_index >= 2) {  // a submission always starts on a frame boundary; guard against one that does not
             const mp3gpu_unit u0 = units[unit_index - 2];
             const bool short0 = u_winsw(u0.w0) == 1 && u_btype(u0.w0) == 2;
@@ -418,73 +618,74 @@ MP3_HD uint32_t huffman_stage_a(const DeviceTables &T, const uint32_t *lut, cons
             const int sfc0 = u_sfcomp(u0.w1) & 15;
             s1_0 = T.slen_mpeg1[sfc0 * 2];
             s2_0 = T.slen_mpeg1[sfc0 * 2 + 1];
-            b0.init(main_data, main_bits, u0.bit_start, u0.buf_end_rel);
+            mk(b0, u0.bit_start, u0.buf_end_rel);
         }
-        int sfc = u_sfcomp(w1) & 15;
-        int slen1 = T.slen_mpeg1[sfc * 2], slen2 = T.slen_mpeg1[sfc * 2 + 1];
-        int scfsi = u_scfsi(w2);
+        const int sfc = u_sfcomp(w1) & 15;
+        const int slen1 = T.slen_mpeg1[sfc * 2], slen2 = T.slen_mpeg1[sfc * 2 + 1];
+        const int scfsi = u_scfsi(w2);
         NibWriter nw;
         nw.init(pk, 0);
 #pragma unroll 1
-        for (int sfb = 0; sfb < 21; sfb++) {
-            int band = sfb < 6 ? 0 : (sfb < 11 ? 1 : (sfb < 16 ? 2 : 3));
-            const int v0 = sfb < n0 ? b0.bits(sfb < 11 ? s1_0 : s2_0) : 0;
-            int v;
-            if ((scfsi >> band) & 1)
-                v = v0;
-            else
-                v = bc.bits(sfb < 11 ? slen1 : slen2);
-            nw.put(v);
+        for (int band = 0; band < 4; band++) {
+            const int first = band == 0 ? 0 : (band == 1 ? 6 : (band == 2 ? 11 : 16));
+            const int len = band == 0 ? 6 : 5;
+            int have0 = n0 - first;  // values of this band that gr 0's parse read (the rest stayed 0)
+            have0 = have0 < 0 ? 0 : (have0 > len ? len : have0);
+            const int s0 = band < 2 ? s1_0 : s2_0;
+            if ((scfsi >> band) & 1) {
+                sf_run(b0, nw, have0, s0);
+#pragma unroll 1
+                for (int i = have0; i < len; i++) nw.put(0);
+            } else {
+                sf_skip_run(b0, have0, s0);
+                sf_run(bc, nw, len, band < 2 ? slen1 : slen2);
+            }
         }
         nw.flush();
     }
 
-    // ---- part 3: Huffman (maindata/huffman.go:27-138), whole groups of four pairs ---------------
-    if (u_p23len(w0) == 0) return kHuffDone | ((uint32_t)preflag << 30);
-    const HuffRegions R = huff_regions(T, huff_desc, w0, w1, w2);
-    uint4 *dst4 = reinterpret_cast<uint4 *>(is_out);
-    for (int k = 0; k + 4 <= R.nbig; k += 4) {  // four pairs per 16-byte store
-        uint4 v;
-        v.x = huff_pair_at(lut, R, k, bc);
-        v.y = huff_pair_at(lut, R, k + 1, bc);
-        v.z = huff_pair_at(lut, R, k + 2, bc);
-        v.w = huff_pair_at(lut, R, k + 3, bc);
-        dst4[k >> 2] = v;
+    // ---- part 3: Huffman (maindata/huffman.go:27-138) ------------------------------------------
+    if (u_p23len(w0) == 0) return preflag << 10;  // quirk Q1: nothing decoded, the cursor is not moved, Count1 stays 0
+    const int bit_pos_end = u_p23len(w0) - 1;
+    const HuffRegions R = huff_regions(T, lut, huff_desc, w0, w1, w2);
+    int k = 0;
+    if constexpr (BC::kFast) {
+        // Four pairs per 16-byte store while the cursor stays clear of the buffer end and of the end of the staged
+        // stretch: a pair takes at most 19 + 2 * 13 + 2 = 47 bits, so three pairs after a check still see p <= fast_lim.
+        // No bit-budget check (quirk Q4).
+        uint4 *dst4 = reinterpret_cast<uint4 *>(is_out);
+        const int lim4 = bc.fast_lim - 3 * 47;
+        for (; k + 4 <= R.nbig && bc.p <= lim4; k += 4) {
+            uint4 v;
+            v.x = huff_pair_fast_at(R, k, bc);
+            v.y = huff_pair_fast_at(R, k + 1, bc);
+            v.z = huff_pair_fast_at(R, k + 2, bc);
+            v.w = huff_pair_fast_at(R, k + 3, bc);
+            dst4[k >> 2] = v;
+        }
     }
-    return (uint32_t)bc.pos() | ((uint32_t)preflag << 30);
-}
-
-// Bits of part 3 left after stage A: what stage B's cost grows with.
-MP3_HD int huff_bits_left(uint32_t w0, uint32_t st) {
-    if (st & kHuffDone) return 0;
-    const int left = u_p23len(w0) - huff_state_pos(st);
-    return left > 0 ? left : 0;
-}
-
-MP3_HD uint32_t huffman_stage_b(const DeviceTables &T, const uint32_t *lut, const uint32_t *huff_desc, const uint64_t *quad_signs,
-                                const uint8_t *main_data, uint64_t main_bits, const mp3gpu_unit *units, long long unit_index,
-                                uint32_t st, uint32_t *is_out) {
-    const uint32_t preflag = (uint32_t)huff_state_preflag(st);
-    if (st & kHuffDone) return preflag << 10;
-    const mp3gpu_unit u = units[unit_index];
-    const uint32_t w0 = u.w0, w1 = u.w1, w2 = u.w2;
-    // Restart the cursor at the logical position stage A reached.  A cursor that had run past the buffer end reads
-    // zeros and reports the end position; so does one restarted exactly there.
-    const int pos0 = huff_state_pos(st);
-    BitCursor bc;
-    bc.init(main_data, main_bits, u.bit_start + (uint64_t)pos0, u.buf_end_rel - pos0);
-    const int bit_pos_end = u_p23len(w0) - 1 - pos0;  // part2Start is position -pos0 of this cursor
-    const HuffRegions R = huff_regions(T, huff_desc, w0, w1, w2);
-    int k = R.nbig & ~3;
     PairSink sink;
     sink.init(is_out, k);
-    for (; k < R.nbig; k++) sink.put(huff_pair_at(lut, R, k, bc));
+    for (; k < R.nbig; k++) sink.put(huff_pair_at(R, k, bc));  // the careful cursor: bits.go's rules at the buffer end
     int is_pos = R.nbig * 2;
     {
         const uint32_t dq = huff_desc[32 + u_c1tsel(w2)] & 0xffffffu;
+        if constexpr (BC::kFast) {
+            const int p_end = bc.off0 + bit_pos_end;  // inside the fast range pos() is p - off0
+            while (is_pos <= 572 && bc.p <= p_end && bc.p <= bc.fast_lim) {
+                const uint32_t wd = bc.peek32_fast();
+                const uint32_t e = lut_at(qlut, dq + ((wd >> (32 - kRootBits)) << 2));
+                const uint32_t four = shl_mod32(wd, e >> 16) >> 28;
+                const uint64_t r = quad_signs[((e & 0xf) << 4) | four];
+                bc.p += (int)(e >> 26);
+                sink.put((uint32_t)r);
+                sink.put((uint32_t)(r >> 32));
+                is_pos += 4;
+            }
+        }
         while (is_pos <= 572 && bc.pos() <= bit_pos_end) {
             uint32_t vw, xy;
-            huff_quad(lut, quad_signs, dq, bc, vw, xy);
+            huff_quad(qlut, quad_signs, dq, bc, vw, xy);
             sink.put(vw);
             sink.put(xy);
             is_pos += 4;
@@ -496,12 +697,20 @@ MP3_HD uint32_t huffman_stage_b(const DeviceTables &T, const uint32_t *lut, cons
     return (uint32_t)is_pos | (preflag << 10);
 }
 
-// Both stages back to back (host emulation and tests).
-MP3_HD uint32_t huffman_unit(const DeviceTables &T, const uint32_t *lut, const uint32_t *huff_desc, const uint64_t *quad_signs,
+// The register-window cursor over global memory (host emulation and tests; k_huffman uses the staged cursor).
+MP3_HD uint32_t huffman_unit(const DeviceTables &T, SmemRef lut, const uint32_t *qlut, const uint32_t *huff_desc, const uint64_t *quad_signs,
                              const uint8_t *main_data, uint64_t main_bits, const mp3gpu_unit *units, long long unit_index,
                              uint32_t *pk, uint32_t *is_out) {
-    const uint32_t st = huffman_stage_a(T, lut, huff_desc, main_data, main_bits, units, unit_index, pk, is_out);
-    return huffman_stage_b(T, lut, huff_desc, quad_signs, main_data, main_bits, units, unit_index, st, is_out);
+    return huffman_unit_t<BitCursor>(T, lut, qlut, huff_desc, quad_signs, units, unit_index,
+                                     [&](BitCursor &c, uint64_t bit_start, int buf_end_rel) { c.init(main_data, main_bits, bit_start, buf_end_rel); },
+                                     pk, is_out);
+}
+// The staged cursor over one stretch (k_huffman's per-unit call; tests/hostemu emulates the tiling).
+MP3_HD uint32_t huffman_unit_staged(const DeviceTables &T, SmemRef lut, const uint32_t *qlut, const uint32_t *huff_desc, const uint64_t *quad_signs,
+                                    const StageCtx &S, const mp3gpu_unit *units, long long unit_index, uint32_t *pk, uint32_t *is_out) {
+    return huffman_unit_t<StagedCursor>(T, lut, qlut, huff_desc, quad_signs, units, unit_index,
+                                        [&](StagedCursor &c, uint64_t bit_start, int buf_end_rel) { c.init(S, bit_start, buf_end_rel); },
+                                        pk, is_out);
 }
 
 // ---- K2 per-line logic ---------------------------------------------------------------------------

@@ -36,6 +36,7 @@ void ensure() {
     g_T.sfb_short = &h.sfb_short[0][0];
     g_T.nslen2 = h.nslen2;
     g_T.huff_lut = h.huff_lut.data();
+    g_T.quad_lut = h.quad_lut;
     g_T.huff_desc = h.huff_desc;
     g_T.quad_signs = h.quad_signs;
     g_T.is_ratio_l = h.is_ratio_l;
@@ -64,12 +65,62 @@ void emu_huffman(const uint8_t *main_data, unsigned long long main_bits, const m
         uint32_t pk[8];
         alignas(16) uint32_t out[288 + 4];
         memset(out, 0, sizeof out);
-        uint32_t m = huffman_unit(g_T, g_T.huff_lut, g_T.huff_desc, g_T.quad_signs, main_data, main_bits, units, u, pk, out);
+        uint32_t m = huffman_unit(g_T, SmemRef::of(g_T.huff_lut), g_T.quad_lut, g_T.huff_desc, g_T.quad_signs, main_data, main_bits, units, u, pk, out);
         meta[u] = m;
         int c1 = (int)(m & 0x3ff);
         for (int i = 0; i < c1; i++) is16[u * 576 + i] = (int16_t)((out[i >> 1] >> (16 * (i & 1))) & 0xffff);
         for (int k = 0; k < 64; k++) scalefac[u * 64 + k] = (uint8_t)sf_nib(pk, k);
         scalefac[u * 64 + 61] = (uint8_t)((m >> 10) & 1);
+    }
+}
+
+// K1 on the CPU the way k_huffman runs it: tiles of `tile` consecutive units, the stretch of main data a tile reads
+// staged (byte-swapped) into a buffer of at most cap16 16-byte chunks, every unit decoded through a StagedCursor.
+// main_data must be followed by 64 readable bytes, like the device buffer.
+void emu_huffman_staged(const uint8_t *main_data, unsigned long long main_bits, const mp3gpu_unit *units, long long n_units, int tile,
+                        int cap16, int16_t *is16, uint32_t *meta, uint8_t *scalefac) {
+    ensure();
+    const uint32_t main16 = (uint32_t)(((main_bits >> 3) + 48) >> 4);
+    std::vector<uint32_t> stage;
+    for (long long base = 0; base < n_units; base += tile) {
+        uint32_t lo = 0xffffffffu, hi = 0u;
+        for (long long u = base; u < n_units && u < base + tile; u++) {
+            if (!u_valid(units[u].w2)) continue;
+            uint32_t l, h;
+            stage_reach(units[u], main_bits, &l, &h);
+            lo = l < lo ? l : lo;
+            hi = h > hi ? h : hi;
+        }
+        if (hi > main16) hi = main16;
+        uint32_t n16 = hi > lo ? hi - lo : 0u;
+        if (n16 > (uint32_t)cap16) n16 = (uint32_t)cap16;
+        stage.assign((size_t)n16 * 4 + 4, 0xdeadbeefu);  // poisoned past the end: nothing may read it
+        for (size_t i = 0; i < (size_t)n16 * 4; i++) {
+            uint32_t v;
+            memcpy(&v, main_data + (size_t)lo * 16 + i * 4, 4);
+            stage[i] = be32(v);
+        }
+        StageCtx S;
+        S.sw = SmemRef::of(stage.data());
+        S.n_words = (int)(n16 * 4);
+        S.lo_word = (unsigned long long)lo * 4ull;
+        S.gw = reinterpret_cast<const uint32_t *>(main_data);
+        S.main_bits = main_bits;
+        for (long long u = base; u < n_units && u < base + tile; u++) {
+            memset(is16 + u * 576, 0, 576 * sizeof(int16_t));
+            memset(scalefac + u * 64, 0, 64);
+            meta[u] = 0;
+            if (!u_valid(units[u].w2)) continue;
+            uint32_t pk[8];
+            alignas(16) uint32_t out[288 + 4];
+            memset(out, 0, sizeof out);
+            uint32_t m = huffman_unit_staged(g_T, SmemRef::of(g_T.huff_lut), g_T.quad_lut, g_T.huff_desc, g_T.quad_signs, S, units, u, pk, out);
+            meta[u] = m;
+            int c1 = (int)(m & 0x3ff);
+            for (int i = 0; i < c1; i++) is16[u * 576 + i] = (int16_t)((out[i >> 1] >> (16 * (i & 1))) & 0xffff);
+            for (int k = 0; k < 64; k++) scalefac[u * 64 + k] = (uint8_t)sf_nib(pk, k);
+            scalefac[u * 64 + 61] = (uint8_t)((m >> 10) & 1);
+        }
     }
 }
 
@@ -176,13 +227,13 @@ int emu_huff_one(int table, const uint8_t *buf, int len_bytes, int *out4) {
     bc.init(padded.data(), (uint64_t)len_bytes * 8, 0, len_bytes * 8);
     if (table < 32) {
         const uint32_t desc = g_T.huff_desc[table];
-        uint32_t r = huff_pair(g_T.huff_lut, desc & 0xffffffu, [&] { return (int)(desc >> 24); }, bc);
+        uint32_t r = huff_pair(SmemRef::of(g_T.huff_lut).plus(desc & 0xffffffu), [&] { return (int)(desc >> 24); }, bc);
         out4[0] = (int16_t)(r & 0xffff);
         out4[1] = (int16_t)(r >> 16);
         out4[2] = out4[3] = 0;
     } else {
         uint32_t vw, xy;
-        huff_quad(g_T.huff_lut, g_T.quad_signs, g_T.huff_desc[table] & 0xffffffu, bc, vw, xy);
+        huff_quad(g_T.quad_lut, g_T.quad_signs, g_T.huff_desc[table] & 0xffffffu, bc, vw, xy);
         out4[0] = (int16_t)(xy & 0xffff); out4[1] = (int16_t)(xy >> 16);
         out4[2] = (int16_t)(vw & 0xffff); out4[3] = (int16_t)(vw >> 16);
     }

@@ -52,6 +52,15 @@ def stream_cases():
     return cs
 
 
+
+def check_staged_cursor(pb, is16, meta, sf):
+    """k_huffman's staged cursor (tiles of units, the stretch they read staged big-endian; positions outside the stretch
+    read from main_data) decodes exactly what the register-window cursor does — with the whole stretch staged, with a
+    staging area far too small (most reads take the fallback) and with odd tile sizes."""
+    for tile, cap16 in ((256, 1 << 20), (512, 1 << 20), (64, 3), (100, 40), (256, 0)):
+        a, b, c = hostemu_lib.huffman_staged(pb.main_data, pb.units, tile, cap16)
+        assert np.array_equal(a, is16) and np.array_equal(b, meta) and np.array_equal(c, sf), (tile, cap16)
+
 @pytest.mark.parametrize("name,cfg", stream_cases(), ids=[n for n, _ in stream_cases()])
 def test_host_stage_and_unit_logic_vs_oracle(pkg, name, cfg):
     data = synth.stream(cfg)
@@ -66,6 +75,7 @@ def test_host_stage_and_unit_logic_vs_oracle(pkg, name, cfg):
     assert np.array_equal(is16, o["is_"])                      # bit-exact Huffman integers
     assert np.array_equal(meta & 0x3FF, o["count1"])
     assert np.array_equal(sf[:, :22], o["scalefac_l"]) and np.array_equal(sf[:, 22:61], o["scalefac_s"])
+    check_staged_cursor(pb, is16, meta, sf)
     xr = hostemu_lib.requant(pb.units, is16, meta, sf).reshape(-1, 576)
     assert np.array_equal(xr.view(np.uint32), o["xr_alias"].view(np.uint32))  # bit-exact spectrum after K2
 
@@ -78,6 +88,7 @@ def test_fixtures_unit_logic(pkg, classic_lame, mpeg2):
         o = common.oracle_units_view(taps, taps.n_frames)
         is16, meta, sf = hostemu_lib.huffman(pb.main_data, pb.units)
         assert np.array_equal(is16, o["is_"]) and np.array_equal(meta & 0x3FF, o["count1"])
+        check_staged_cursor(pb, is16, meta, sf)
         xr = hostemu_lib.requant(pb.units, is16, meta, sf).reshape(-1, 576)
         assert np.array_equal(xr.view(np.uint32), o["xr_alias"].view(np.uint32))
 
@@ -241,6 +252,10 @@ def test_unit_logic_sweep_vs_oracle(pkg):
         is16, meta, sf = hostemu_lib.huffman(pb.main_data, pb.units)
         assert np.array_equal(is16, o["is_"]) and np.array_equal(meta & 0x3FF, o["count1"])
         assert np.array_equal(sf[:, :22], o["scalefac_l"]) and np.array_equal(sf[:, 22:61], o["scalefac_s"])
+        a, b, c = hostemu_lib.huffman_staged(pb.main_data, pb.units, 256, 1 << 20)
+        assert np.array_equal(a, is16) and np.array_equal(b, meta) and np.array_equal(c, sf)
+        a, b, c = hostemu_lib.huffman_staged(pb.main_data, pb.units, 96, 24)
+        assert np.array_equal(a, is16) and np.array_equal(b, meta) and np.array_equal(c, sf)
         xr = hostemu_lib.requant(pb.units, is16, meta, sf).reshape(-1, 576)
         same = (xr.view(np.uint32) == o["xr_alias"].view(np.uint32)) | (np.isnan(xr) & np.isnan(o["xr_alias"]))
         assert same.all()
