@@ -338,10 +338,10 @@ static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, size_t main_len, 
             for (int ti = 0; ti < 3; ti++) {
                 const int t = 256 << ti;
                 if (ctx->k1_threads_override && t != ctx->k1_threads_override) continue;
-                const int fixed = ctx->lut_bytes + ctx->huff_static_smem[ti] + 1024;  // + the per-CTA reservation
+                const int fixed = ctx->lut_bytes + ctx->huff_static_smem[ti] + 1024 + 16;  // + the per-CTA reservation and the staging pad
                 int stage = (int)(avg * t * 1.25) + 2048;
                 if (ctx->k1_stage_kb_override) stage = ctx->k1_stage_kb_override * 1024;
-                const int cap = ctx->smem_per_cta_max - ctx->huff_static_smem[ti] - ctx->lut_bytes;
+                const int cap = ctx->smem_per_cta_max - ctx->huff_static_smem[ti] - ctx->lut_bytes - 16;
                 if (stage > cap) stage = cap;
                 stage &= ~15;
                 int ctas = ctx->smem_per_sm / (fixed + stage);
@@ -353,7 +353,7 @@ static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, size_t main_len, 
         }
         const int tiles = (nu + best_t - 1) / best_t;
         const int grid = std::min(tiles, ctx->sm_count * best_ctas);
-        const size_t dyn = (size_t)ctx->lut_bytes + (size_t)best_stage;
+        const size_t dyn = (size_t)ctx->lut_bytes + (size_t)best_stage + 16;  // + the padding FastWindow's prefetch may touch
         if (best_t == 256) k_huffman<256><<<grid, 256, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, best_stage / 16);
         else if (best_t == 512) k_huffman<512><<<grid, 512, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, best_stage / 16);
         else k_huffman<1024><<<grid, 1024, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, best_stage / 16);

@@ -308,6 +308,39 @@ struct StagedCursor {
     }
 };
 
+// Register window over the staged stretch for the unchecked fast loops (cursor at p <= fast_lim): three consecutive
+// words, the third a prefetch, so that no shared-memory load sits on the code-word-to-code-word dependency chain —
+// the next code word's position depends on this one's length, and with the window read from shared memory at every
+// step K1 was bound by that latency (ncu: issue slots 51 % busy, short-scoreboard 3.9 stall cycles per issue).
+// A step consumes fewer than 32 bits, so one refill per advance() is enough; the refill is predicated, not a branch.
+// The stretch is followed by four words of padding: the prefetch may run that far past it (never consumed).
+struct FastWindow {
+    uint32_t w0, w1, w2;
+    SmemRef next;  // the word after w2
+    int off;       // cursor inside w0
+    int p;         // the StagedCursor's p, kept alongside for the loop bounds
+    MP3_HD void open(const StagedCursor &bc) {
+        const uint32_t byte = (uint32_t)(bc.p >> 5) * 4u;
+        bc.sw.ld32x2(byte, w0, w1);
+        w2 = bc.sw.ld32(byte + 8u);
+        next = bc.sw.plus(byte + 12u);
+        off = bc.p & 31;
+        p = bc.p;
+    }
+    MP3_HD uint32_t peek() const { return funnel_l(w0, w1, off); }
+    MP3_HD void advance(int n) {  // 0 <= n < 32
+        off += n;
+        p += n;
+        if (off >= 32) {
+            off -= 32;
+            w0 = w1;
+            w1 = w2;
+            w2 = next.ld32(0u);
+            next = next.plus(4u);
+        }
+    }
+};
+
 // ---- Huffman code words (LUT entry layout: tables.h) -------------------------------------------------------------
 // the top (n mod 32) bits of x, as a number
 #if defined(__CUDA_ARCH__)
@@ -382,25 +415,26 @@ MP3_HD uint32_t huff_pair(SmemRef tree, LinbitsFn linbits_of, BC &bc) {
     return leaf_pair(e);
 }
 
-// The same pair where nothing can touch the buffer end (StagedCursor, bc.p <= bc.fast_lim): no refused reads, no clamp.
-template <class BC, class LinbitsFn>
-MP3_HD uint32_t huff_pair_fast(SmemRef tree, LinbitsFn linbits_of, BC &bc) {
-    const int e = huff_lookup16(tree, bc.peek32_fast());
+// The same pair where nothing can touch the buffer end (FastWindow: the cursor is at p <= fast_lim): no refused reads, no
+// clamp, no load on the dependency chain.
+template <class LinbitsFn>
+MP3_HD uint32_t huff_pair_fast(SmemRef tree, LinbitsFn linbits_of, FastWindow &fw) {
+    const int e = huff_lookup16(tree, fw.peek());
     if (e < 0) {
         const int other = (e >> 7) & 15;
         int x = (e & 0x20) ? 15 : other, y = (e & 0x40) ? 15 : other;
         const int linbits = linbits_of();  // >= 1 in every table that has escapes
-        bc.p += e & 31;
-        uint32_t v = bc.peek32_fast();  // at most 19 tree bits were skipped: still inside the 64 bits fast_lim vouches for
+        fw.advance(e & 31);                // at most 19 tree bits
+        uint32_t v = fw.peek();            // still inside the 64 bits fast_lim vouches for
         int n = 0;
         if (x == 15) { x += (int)(v >> (32 - linbits)); v <<= linbits; n = linbits; }
         if (x != 0) { if ((int32_t)v < 0) x = -x; v <<= 1; n++; }
         if (y == 15) { y += (int)(v >> (32 - linbits)); v <<= linbits; n += linbits; }
         if (y != 0) { if ((int32_t)v < 0) y = -y; n++; }
-        bc.p += n;
+        fw.advance(n);                     // at most 2 * 13 + 2 = 28 bits
         return ((uint32_t)x & 0xffffu) | ((uint32_t)y << 16);
     }
-    bc.p += e >> 10;
+    fw.advance(e >> 10);
     return leaf_pair(e);
 }
 
@@ -499,6 +533,45 @@ MP3_HD void sf_skip_run(BC &bc, int count, int slen) {
     for (int i = 0; i < count; i++) (void)bc.bits(slen);
 }
 
+// MPEG-1, long-type block (maindata.go:233-279), lane-uniform form: 21 scalefactors in four bands (sfb 0-5, 6-10, 11-15,
+// 16-20), slen1 bits each in the first two bands and slen2 in the last two; in gr 1 a band whose scfsi bit is set is copied
+// from what gr 0's parse left in ScalefacL[0][ch] — re-read here from gr 0's bits through the look-back cursor b0, which
+// passes over all of gr 0's values (n0 of them, s1_0 / s2_0 bits each).  Every lane runs the same 21 steps whatever its
+// slen values and scfsi bits are (a width of 0 reads nothing), where the run-by-run form above diverged into a handful of
+// lanes (ncu: 12 % of K1's issue slots at 6 of 32 lanes).  Requires that no read can be refused: the caller checks that
+// both cursors have all their bits in front of the buffer end.
+template <class BC>
+MP3_HD void sf_mpeg1_long_uniform(BC &bc, BC &b0, int scfsi, int slen1, int slen2, int n0, int s1_0, int s2_0, uint32_t *pk) {
+    uint32_t acc[3] = {0u, 0u, 0u};
+    uint32_t w = 0, w0 = 0;
+    int used = 0, used0 = 0;
+#pragma unroll
+    for (int sfb = 0; sfb < 21; sfb++) {
+        if ((sfb & 7) == 0) {  // eight values of at most four bits per window
+            bc.skip(used);
+            b0.skip(used0);
+            used = used0 = 0;
+            w = bc.peek32();
+            w0 = b0.peek32();
+        }
+        const int band = sfb < 6 ? 0 : (sfb < 11 ? 1 : (sfb < 16 ? 2 : 3));
+        const bool copied = ((scfsi >> band) & 1) != 0;
+        const uint32_t s = copied ? 0u : (uint32_t)(sfb < 11 ? slen1 : slen2);
+        const uint32_t s0 = sfb < n0 ? (uint32_t)(sfb < 11 ? s1_0 : s2_0) : 0u;
+        const uint32_t v = hi_bits_mod32(w, s), v0 = hi_bits_mod32(w0, s0);
+        w = shl_mod32(w, s);
+        w0 = shl_mod32(w0, s0);
+        used += (int)s;
+        used0 += (int)s0;
+        acc[sfb >> 3] |= (copied ? v0 : v) << (4 * (sfb & 7));
+    }
+    bc.skip(used);
+    b0.skip(used0);
+    pk[0] = acc[0];
+    pk[1] = acc[1];
+    pk[2] = acc[2];
+}
+
 // Scalefactors of an MPEG-1 unit that reads all of them itself: gr 0, or gr 1 short blocks, or
 // gr 1 with no scfsi band set (maindata.go:204-232 and the read arms of :233-279).
 template <class BC>
@@ -562,11 +635,10 @@ MP3_HD uint32_t huff_pair_at(const HuffRegions &R, int k, BC &bc) {
     return huff_pair(in0 ? R.t0 : (in1 ? R.t1 : R.t2),
                      [&] { return (int)((R.lin >> (in0 ? 0 : (in1 ? 4 : 8))) & 0xf); }, bc);
 }
-template <class BC>
-MP3_HD uint32_t huff_pair_fast_at(const HuffRegions &R, int k, BC &bc) {
+MP3_HD uint32_t huff_pair_fast_at(const HuffRegions &R, int k, FastWindow &fw) {
     const bool in0 = k < R.r1h, in1 = k < R.r2h;
     return huff_pair_fast(in0 ? R.t0 : (in1 ? R.t1 : R.t2),
-                          [&] { return (int)((R.lin >> (in0 ? 0 : (in1 ? 4 : 8))) & 0xf); }, bc);
+                          [&] { return (int)((R.lin >> (in0 ? 0 : (in1 ? 4 : 8))) & 0xf); }, fw);
 }
 
 template <class BC, class MkCursor>
@@ -601,17 +673,18 @@ MP3_HD uint32_t huffman_unit_t(const DeviceTables &T, SmemRef lut, const uint32_
             sf_run(bc, nw, (int)T.sfsize_mpeg2[(n * 6 + d) * 4 + i], num);
         }
         nw.flush();
-    } else if (u_gr(w2) == 0 || (u_winsw(w0) == 1 && u_btype(w0) == 2) || u_scfsi(w2) == 0) {
-        sf_mpeg1_read_all(T, bc, w0, w1, w2, pk);
+    } else if (u_winsw(w0) == 1 && u_btype(w0) == 2) {
+        sf_mpeg1_read_all(T, bc, w0, w1, w2, pk);  // short blocks read everything themselves (maindata.go:206-232)
     } else {
-        // gr 1, long-type block, at least one scfsi band set: those bands copy ScalefacL[0][ch] as gr 0's parse left it
-        // (21 values if gr 0 was a long-type block, sfb 0-7 only if it was mixed, zeros if it was short).  gr 0's
-        // scalefactor bits are re-read by a second cursor, band by band: a band this unit copies is read from it, a
-        // band this unit reads itself is passed over.
+        // Long-type block.  In gr 1 the bands whose scfsi bit is set copy ScalefacL[0][ch] as gr 0's parse left it (21
+        // values if gr 0 was a long-type block, sfb 0-7 only if it was mixed, zeros if it was short).  gr 0's scalefactor
+        // bits are re-read by a second cursor, band by band: a band this unit copies is read from it, a band this unit
+        // reads itself is passed over.
+        const int scfsi = u_gr(w2) == 0 ? 0 : u_scfsi(w2);
         int n0 = 0, s1_0 = 0, s2_0 = 0;
         BC b0;
         mk(b0, 0, 0);
-        if (unit_index >= 2) {  // a submission always starts on a frame boundary; guard against one that does not
+        if (scfsi != 0 && unit_index >= 2) {  // a submission always starts on a frame boundary; guard against one that does not
             const mp3gpu_unit u0 = units[unit_index - 2];
             const bool short0 = u_winsw(u0.w0) == 1 && u_btype(u0.w0) == 2;
             n0 = short0 ? (u_mixed(u0.w2) ? 8 : 0) : 21;
@@ -622,26 +695,29 @@ MP3_HD uint32_t huffman_unit_t(const DeviceTables &T, SmemRef lut, const uint32_
         }
         const int sfc = u_sfcomp(w1) & 15;
         const int slen1 = T.slen_mpeg1[sfc * 2], slen2 = T.slen_mpeg1[sfc * 2 + 1];
-        const int scfsi = u_scfsi(w2);
-        NibWriter nw;
-        nw.init(pk, 0);
+        if (bc.pos() + 11 * slen1 + 10 * slen2 <= bc.lim && (n0 == 0 || b0.pos() + 11 * s1_0 + 10 * s2_0 <= b0.lim)) {
+            sf_mpeg1_long_uniform(bc, b0, scfsi, slen1, slen2, n0, s1_0, s2_0, pk);
+        } else {  // a read could be refused at the buffer end (bits.go:65-68): value by value
+            NibWriter nw;
+            nw.init(pk, 0);
 #pragma unroll 1
-        for (int band = 0; band < 4; band++) {
-            const int first = band == 0 ? 0 : (band == 1 ? 6 : (band == 2 ? 11 : 16));
-            const int len = band == 0 ? 6 : 5;
-            int have0 = n0 - first;  // values of this band that gr 0's parse read (the rest stayed 0)
-            have0 = have0 < 0 ? 0 : (have0 > len ? len : have0);
-            const int s0 = band < 2 ? s1_0 : s2_0;
-            if ((scfsi >> band) & 1) {
-                sf_run(b0, nw, have0, s0);
+            for (int band = 0; band < 4; band++) {
+                const int first = band == 0 ? 0 : (band == 1 ? 6 : (band == 2 ? 11 : 16));
+                const int len = band == 0 ? 6 : 5;
+                int have0 = n0 - first;  // values of this band that gr 0's parse read (the rest stayed 0)
+                have0 = have0 < 0 ? 0 : (have0 > len ? len : have0);
+                const int s0 = band < 2 ? s1_0 : s2_0;
+                if ((scfsi >> band) & 1) {
+                    sf_run(b0, nw, have0, s0);
 #pragma unroll 1
-                for (int i = have0; i < len; i++) nw.put(0);
-            } else {
-                sf_skip_run(b0, have0, s0);
-                sf_run(bc, nw, len, band < 2 ? slen1 : slen2);
+                    for (int i = have0; i < len; i++) nw.put(0);
+                } else {
+                    sf_skip_run(b0, have0, s0);
+                    sf_run(bc, nw, len, band < 2 ? slen1 : slen2);
+                }
             }
+            nw.flush();
         }
-        nw.flush();
     }
 
     // ---- part 3: Huffman (maindata/huffman.go:27-138) ------------------------------------------
@@ -655,13 +731,19 @@ MP3_HD uint32_t huffman_unit_t(const DeviceTables &T, SmemRef lut, const uint32_
         // No bit-budget check (quirk Q4).
         uint4 *dst4 = reinterpret_cast<uint4 *>(is_out);
         const int lim4 = bc.fast_lim - 3 * 47;
-        for (; k + 4 <= R.nbig && bc.p <= lim4; k += 4) {
-            uint4 v;
-            v.x = huff_pair_fast_at(R, k, bc);
-            v.y = huff_pair_fast_at(R, k + 1, bc);
-            v.z = huff_pair_fast_at(R, k + 2, bc);
-            v.w = huff_pair_fast_at(R, k + 3, bc);
-            dst4[k >> 2] = v;
+        if (4 <= R.nbig && bc.p <= lim4) {
+            FastWindow fw;
+            fw.open(bc);
+            do {
+                uint4 v;
+                v.x = huff_pair_fast_at(R, k, fw);
+                v.y = huff_pair_fast_at(R, k + 1, fw);
+                v.z = huff_pair_fast_at(R, k + 2, fw);
+                v.w = huff_pair_fast_at(R, k + 3, fw);
+                dst4[k >> 2] = v;
+                k += 4;
+            } while (k + 4 <= R.nbig && fw.p <= lim4);
+            bc.p = fw.p;
         }
     }
     PairSink sink;
@@ -672,15 +754,20 @@ MP3_HD uint32_t huffman_unit_t(const DeviceTables &T, SmemRef lut, const uint32_
         const uint32_t dq = huff_desc[32 + u_c1tsel(w2)] & 0xffffffu;
         if constexpr (BC::kFast) {
             const int p_end = bc.off0 + bit_pos_end;  // inside the fast range pos() is p - off0
-            while (is_pos <= 572 && bc.p <= p_end && bc.p <= bc.fast_lim) {
-                const uint32_t wd = bc.peek32_fast();
-                const uint32_t e = lut_at(qlut, dq + ((wd >> (32 - kRootBits)) << 2));
-                const uint32_t four = shl_mod32(wd, e >> 16) >> 28;
-                const uint64_t r = quad_signs[((e & 0xf) << 4) | four];
-                bc.p += (int)(e >> 26);
-                sink.put((uint32_t)r);
-                sink.put((uint32_t)(r >> 32));
-                is_pos += 4;
+            if (is_pos <= 572 && bc.p <= p_end && bc.p <= bc.fast_lim) {
+                FastWindow fw;
+                fw.open(bc);
+                do {
+                    const uint32_t wd = fw.peek();
+                    const uint32_t e = lut_at(qlut, dq + ((wd >> (32 - kRootBits)) << 2));
+                    const uint32_t four = shl_mod32(wd, e >> 16) >> 28;
+                    const uint64_t r = quad_signs[((e & 0xf) << 4) | four];
+                    fw.advance((int)(e >> 26));
+                    sink.put((uint32_t)r);
+                    sink.put((uint32_t)(r >> 32));
+                    is_pos += 4;
+                } while (is_pos <= 572 && fw.p <= p_end && fw.p <= bc.fast_lim);
+                bc.p = fw.p;
             }
         }
         while (is_pos <= 572 && bc.pos() <= bit_pos_end) {
