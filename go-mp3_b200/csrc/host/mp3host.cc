@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../../include/mp3host.h"
+#include "lameinfo.h"
 #include "stream_parser.h"
 
 using namespace mp3host;
@@ -37,6 +38,7 @@ struct GpuApi {
     void (*destroy)(mp3gpu_ctx *) = nullptr;
     const char *(*last_error)(const mp3gpu_ctx *) = nullptr;
     int (*decode)(mp3gpu_ctx *, const uint8_t *, size_t, const mp3gpu_unit *, size_t, int16_t *) = nullptr;
+    int (*decode_range)(mp3gpu_ctx *, const uint8_t *, size_t, const mp3gpu_unit *, size_t, size_t, int16_t *) = nullptr;
     void *(*host_alloc)(size_t) = nullptr;
     void (*host_free)(void *) = nullptr;
     int (*last_timings)(mp3gpu_ctx *, mp3gpu_timings *) = nullptr;
@@ -69,6 +71,7 @@ bool load_gpu_api(GpuApi &api, bool exact, std::string &err) {
     SYM(destroy, "mp3gpu_destroy")
     SYM(last_error, "mp3gpu_last_error")
     SYM(decode, "mp3gpu_decode")
+    SYM(decode_range, "mp3gpu_decode_range")
     SYM(host_alloc, "mp3gpu_host_alloc")
     SYM(host_free, "mp3gpu_host_free")
     SYM(last_timings, "mp3gpu_last_timings")
@@ -169,13 +172,28 @@ void gather_batch(const std::vector<ParsedStream> &ps, const BatchLayout &L, uin
 
 }  // namespace
 
+// One device of the engine: its device engine (libmp3gpu context) and the pinned staging arenas of calls that target
+// this device alone (mp3_decode_frames, the streaming Decoder).
+struct DeviceSlot {
+    int device = 0;
+    mp3gpu_ctx *gpu = nullptr;
+    Pinned r_main, r_units;  // frame-range jobs
+    std::mutex mu;           // one call at a time per device engine (the device engine is single-owner)
+};
+
 struct mp3_engine {
     mp3_engine_opts opts{};
     GpuApi api;
-    mp3gpu_ctx *gpu = nullptr;
+    std::vector<DeviceSlot *> devs;
+    mp3gpu_ctx *gpu = nullptr;  // devs[0]->gpu
     std::string err;
-    Pinned a_main, a_units, a_pcm;
+    std::mutex err_mu;
+    Pinned a_main, a_units, a_pcm;  // DecodeBatch / stream-split arenas, shared by the devices (each works in its own region)
 
+    void set_err(const std::string &m) {
+        std::lock_guard<std::mutex> lk(err_mu);
+        err = m;
+    }
     int ensure(Pinned &a, size_t bytes) {
         if (a.cap >= bytes) return MP3_OK;
         if (a.p) api.host_free(a.p);
@@ -184,7 +202,7 @@ struct mp3_engine {
         size_t want = bytes + bytes / 16 + 4096;
         a.p = api.host_alloc(want);
         if (!a.p) {
-            err = "pinned host allocation of " + std::to_string(want) + " bytes failed";
+            set_err("pinned host allocation of " + std::to_string(want) + " bytes failed");
             return MP3_ERR_DEVICE;
         }
         a.cap = want;
@@ -197,6 +215,10 @@ extern "C" int mp3_engine_create(const mp3_engine_opts *opts, mp3_engine **out) 
     *out = nullptr;
     mp3_engine *e = new mp3_engine();
     if (opts) e->opts = *opts;
+    if (e->opts.n_devices < 0 || e->opts.n_devices > MP3_MAX_DEVICES) {
+        delete e;
+        return MP3_ERR_INVALID;
+    }
     if (!load_gpu_api(e->api, e->opts.use_exact_library != 0, e->err)) {
         fprintf(stderr, "mp3_engine_create: %s\n", e->err.c_str());
         delete e;
@@ -206,13 +228,21 @@ extern "C" int mp3_engine_create(const mp3_engine_opts *opts, mp3_engine **out) 
     go.abi_version = MP3GPU_ABI_VERSION;
     go.wave_granules = e->opts.wave_granules;
     go.keep_intermediates = e->opts.keep_intermediates;
-    int rc = e->api.create(e->opts.device, &go, &e->gpu);
-    if (rc != MP3GPU_OK) {
-        fprintf(stderr, "mp3_engine_create: mp3gpu_create failed (%d): no CUDA device, and there is no CPU decode path\n", rc);
-        dlclose(e->api.handle);
-        delete e;
-        return MP3_ERR_DEVICE;
+    const int n = e->opts.n_devices > 0 ? e->opts.n_devices : 1;
+    for (int i = 0; i < n; i++) {
+        DeviceSlot *d = new DeviceSlot();
+        d->device = e->opts.n_devices > 0 ? e->opts.devices[i] : e->opts.device;
+        int rc = e->api.create(d->device, &go, &d->gpu);
+        if (rc != MP3GPU_OK) {
+            fprintf(stderr, "mp3_engine_create: mp3gpu_create on device %d failed (%d): no such CUDA device, and there is no CPU decode path\n",
+                    d->device, rc);
+            delete d;
+            mp3_engine_destroy(e);
+            return MP3_ERR_DEVICE;
+        }
+        e->devs.push_back(d);
     }
+    e->gpu = e->devs[0]->gpu;
     *out = e;
     return MP3_OK;
 }
@@ -222,13 +252,22 @@ extern "C" void mp3_engine_destroy(mp3_engine *e) {
     if (e->a_main.p) e->api.host_free(e->a_main.p);
     if (e->a_units.p) e->api.host_free(e->a_units.p);
     if (e->a_pcm.p) e->api.host_free(e->a_pcm.p);
-    if (e->gpu) e->api.destroy(e->gpu);
+    for (DeviceSlot *d : e->devs) {
+        if (d->r_main.p) e->api.host_free(d->r_main.p);
+        if (d->r_units.p) e->api.host_free(d->r_units.p);
+        if (d->gpu) e->api.destroy(d->gpu);
+        delete d;
+    }
     if (e->api.handle) dlclose(e->api.handle);
     delete e;
 }
 
 extern "C" const char *mp3_engine_last_error(const mp3_engine *e) { return e ? e->err.c_str() : "no engine"; }
 extern "C" mp3gpu_ctx *mp3_engine_gpu(mp3_engine *e) { return e ? e->gpu : nullptr; }
+extern "C" int mp3_engine_device_count(const mp3_engine *e) { return e ? (int)e->devs.size() : 0; }
+extern "C" mp3gpu_ctx *mp3_engine_gpu_at(mp3_engine *e, int slot) {
+    return (e && slot >= 0 && (size_t)slot < e->devs.size()) ? e->devs[(size_t)slot]->gpu : nullptr;
+}
 
 extern "C" const char *mp3_error_string(int code) {
     switch (code) {
@@ -245,11 +284,25 @@ extern "C" const char *mp3_error_string(int code) {
     case MP3_ERR_SEEK_UNSUPPORTED: return "mp3: seek not supported on non-seekable source";
     case MP3_ERR_WHENCE: return "mp3: invalid whence";
     case MP3_ERR_REF_PANIC: return "mp3: input on which the reference decoder panics";
+    case MP3_ERR_NO_XING_HEADER: return "lameinfo: no Xing/Info header found";
     case MP3_ERR_DEVICE: return "mp3: device engine failure";
     case MP3_ERR_INVALID: return "mp3: invalid argument";
     }
     return "mp3: unknown error";
 }
+
+// ---- lameinfo (lameinfo.h) ---------------------------------------------------------------------------
+extern "C" int mp3_lameinfo_parse(const uint8_t *frame, size_t len, mp3_lame_info *out) {
+    if (!out || (!frame && len)) return MP3_ERR_INVALID;
+    return lameinfo_parse(frame, len, out);
+}
+extern "C" int mp3_lameinfo_parse_from_reader(const uint8_t *data, size_t len, mp3_lame_info *out) {
+    if (!out || (!data && len)) return MP3_ERR_INVALID;
+    return lameinfo_parse_from_reader(data, len, out);
+}
+extern "C" int mp3_lameinfo_total_delay(const mp3_lame_info *info) { return info ? lameinfo_total_delay(info) : MP3_LAME_DECODER_DELAY; }
+extern "C" int mp3_lameinfo_total_padding(const mp3_lame_info *info) { return info ? lameinfo_total_padding(info) : 0; }
+extern "C" int mp3_lameinfo_is_lame_version(const uint8_t *s, size_t n) { return is_lame_version(s, n) ? 1 : 0; }
 
 // ---- host-only parse (tests, bench staging) ---------------------------------------------------------
 extern "C" int mp3_parse_streams(const uint8_t *const *data, const size_t *lens, size_t n, int host_threads, mp3_parsed **out) {
@@ -318,108 +371,82 @@ struct DeviceJob {
 // Test hook (tests/test_host_and_emulation.py): the arena bound DecodeBatch relies on.
 extern "C" size_t mp3_debug_unit_slots_upper_bound(const uint8_t *data, size_t len) { return unit_slots_upper_bound(data, len); }
 
-// Large batches are cut into chunks of streams: while the device decodes chunk k (the PCIe-bound part), the host
-// threads parse and gather chunk k+1 straight behind it in the same pinned arenas.
-extern "C" int mp3_decode_batch(mp3_engine *e, const uint8_t *const *data, const size_t *lens, size_t n,
-                                mp3_stream_result *results, const uint8_t **pcm_base, mp3_batch_timings *timings) {
-    if (!e || !results || !pcm_base || (n && (!data || !lens))) return MP3_ERR_INVALID;
-    const double t0 = now_s();
-    const size_t n_chunks = n >= 256 ? std::min<size_t>(8, n / 128) : 1;
-    // ---- arena sizes: main data never exceeds the input bytes; unit slots from a header-only frame walk ----
-    size_t main_ub = 64 * (n_chunks + 1), slots_ub = 0;
-    {
-        std::vector<size_t> ub(n);
-        std::atomic<size_t> next{0};
-        auto work = [&]() {
-            for (;;) {
-                size_t i = next.fetch_add(1);
-                if (i >= n) break;
-                ub[i] = n_chunks > 1 ? unit_slots_upper_bound(data[i], lens[i]) : 0;
-            }
-        };
-        int nt = (int)std::min<size_t>((size_t)hw_threads(e->opts.host_threads), n ? n : 1);
-        if (n_chunks > 1 && nt > 1) {
-            std::vector<std::thread> th;
-            for (int t = 0; t < nt; t++) th.emplace_back(work);
-            for (auto &t : th) t.join();
-        } else {
-            work();
-        }
-        for (size_t i = 0; i < n; i++) {
-            main_ub += (lens[i] + 3) & ~size_t(3);
-            slots_ub += ub[i];
-        }
-    }
+namespace {
+
+// Streams [i0, i1) of a batch on one device, in that device's region of the shared arenas.
+struct Shard {
+    size_t i0 = 0, i1 = 0;
+    size_t m_off = 0, m_cap = 0;  // bytes into a_main
+    size_t u_off = 0, u_cap = 0;  // unit slots into a_units (PCM: slot / 2 * 2304 bytes into a_pcm)
     double parse_s = 0, gather_s = 0, device_s = 0;
-    size_t m_cursor = 0, u_cursor = 0;  // bytes into a_main (64-byte aligned per chunk), unit slots into a_units
+    size_t m_used = 0, u_used = 0;
+    int rc = MP3_OK;
+    std::string err;
+};
+
+size_t shard_chunks(size_t n) { return n >= 256 ? std::min<size_t>(8, n / 128) : 1; }
+
+// Large shards are cut into chunks of streams: while the device decodes chunk k (the PCIe-bound part), the host
+// threads parse and gather chunk k+1 straight behind it in the same pinned arenas.
+void decode_shard(mp3_engine *e, DeviceSlot *dev, const uint8_t *const *data, const size_t *lens, mp3_stream_result *results, Shard &S,
+                  int threads) {
+    const size_t n = S.i1 - S.i0;
+    if (n == 0) return;
+    const size_t n_chunks = shard_chunks(n);
+    size_t m_cursor = S.m_off, u_cursor = S.u_off;
     int dev_rc = MP3GPU_OK;
     std::string dev_err;
-
     std::mutex mu;
     std::condition_variable cv;
     std::deque<DeviceJob> jobs;
     bool closed = false;
-    std::thread worker;
     auto run_job = [&](const DeviceJob &j) {
         if (dev_rc != MP3GPU_OK || j.n_granules == 0) return;
         const double a = now_s();
-        int rc = e->api.decode(e->gpu, j.main_data, j.main_len, j.units, j.n_granules, j.pcm);
-        device_s += now_s() - a;
-        if (rc != MP3GPU_OK) {
-            dev_rc = rc;
-            dev_err = e->api.last_error(e->gpu);
+        int rc;
+        {
+            std::lock_guard<std::mutex> lk(dev->mu);
+            rc = e->api.decode(dev->gpu, j.main_data, j.main_len, j.units, j.n_granules, j.pcm);
+            if (rc != MP3GPU_OK) dev_err = e->api.last_error(dev->gpu);
         }
+        S.device_s += now_s() - a;
+        if (rc != MP3GPU_OK) dev_rc = rc;
     };
-
+    std::thread worker;
+    if (n_chunks > 1)
+        worker = std::thread([&]() {  // one worker owns the device engine for the duration of the shard
+            for (;;) {
+                DeviceJob j;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return closed || !jobs.empty(); });
+                    if (jobs.empty()) return;
+                    j = jobs.front();
+                    jobs.pop_front();
+                }
+                run_job(j);
+            }
+        });
     std::vector<ParsedStream> ps;  // reused by every chunk: the per-stream vectors keep their (already touched) capacity
     for (size_t c = 0; c < n_chunks; c++) {
-        const size_t i0 = n * c / n_chunks, i1 = n * (c + 1) / n_chunks;
+        const size_t i0 = S.i0 + n * c / n_chunks, i1 = S.i0 + n * (c + 1) / n_chunks;
         const double ta = now_s();
-        parse_all(data + i0, lens + i0, i1 - i0, e->opts.host_threads, ps);
+        parse_all(data + i0, lens + i0, i1 - i0, threads, ps);
         const double tb = now_s();
-        parse_s += tb - ta;
+        S.parse_s += tb - ta;
         BatchLayout L = layout_batch(ps);
-        if (n_chunks == 1) {  // sizes are exact here
-            int rc = e->ensure(e->a_main, L.m_total + 64);
-            if (rc == MP3_OK) rc = e->ensure(e->a_units, sizeof(mp3gpu_unit) * L.u_total + 64);
-            if (rc == MP3_OK) rc = e->ensure(e->a_pcm, (L.u_total / 2) * MP3GPU_PCM_BYTES_PER_GRANULE + 64);
-            if (rc != MP3_OK) return rc;
-        } else if (c == 0) {  // before the worker exists: growing an arena moves it
-            int rc = e->ensure(e->a_main, main_ub);
-            if (rc == MP3_OK) rc = e->ensure(e->a_units, sizeof(mp3gpu_unit) * slots_ub + 64);
-            if (rc == MP3_OK) rc = e->ensure(e->a_pcm, (slots_ub / 2) * MP3GPU_PCM_BYTES_PER_GRANULE + 64);
-            if (rc != MP3_OK) return rc;
-            worker = std::thread([&]() {
-                for (;;) {
-                    DeviceJob j;
-                    {
-                        std::unique_lock<std::mutex> lk(mu);
-                        cv.wait(lk, [&] { return closed || !jobs.empty(); });
-                        if (jobs.empty()) return;
-                        j = jobs.front();
-                        jobs.pop_front();
-                    }
-                    run_job(j);
-                }
-            });
-        }
-        if (n_chunks > 1 && (m_cursor + L.m_total + 64 > e->a_main.cap || u_cursor + L.u_total > slots_ub)) {
-            // cannot happen (the bounds are bounds); refuse rather than overrun
-            {
-                std::lock_guard<std::mutex> lk(mu);
-                closed = true;
-            }
-            cv.notify_all();
-            worker.join();
-            e->err = "DecodeBatch arena bound exceeded";
-            return MP3_ERR_INVALID;
+        if (m_cursor + L.m_total + 64 > S.m_off + S.m_cap || u_cursor + L.u_total > S.u_off + S.u_cap) {
+            // cannot happen (the bounds are bounds: tests/test_host_and_emulation.py); refuse rather than overrun
+            S.rc = MP3_ERR_INVALID;
+            S.err = "DecodeBatch arena bound exceeded";
+            break;
         }
         uint8_t *m_dst = (uint8_t *)e->a_main.p + m_cursor;
         mp3gpu_unit *u_dst = (mp3gpu_unit *)e->a_units.p + u_cursor;
-        gather_batch(ps, L, m_dst, u_dst, results + i0, e->opts.host_threads);
+        gather_batch(ps, L, m_dst, u_dst, results + i0, threads);
         const int64_t pcm_off = (int64_t)(u_cursor / 2) * MP3GPU_PCM_BYTES_PER_GRANULE;
         for (size_t i = i0; i < i1; i++) results[i].pcm_offset += pcm_off;
-        gather_s += now_s() - tb;
+        S.gather_s += now_s() - tb;
         DeviceJob j{m_dst, L.m_total, u_dst, L.u_total / 2, (int16_t *)((uint8_t *)e->a_pcm.p + pcm_off)};
         if (n_chunks == 1) {
             run_job(j);
@@ -441,20 +468,125 @@ extern "C" int mp3_decode_batch(mp3_engine *e, const uint8_t *const *data, const
         cv.notify_all();
         worker.join();
     }
-    const double t3 = now_s();
-    if (dev_rc != MP3GPU_OK) {
-        e->err = dev_err;
-        return MP3_ERR_DEVICE;
+    S.m_used = m_cursor - S.m_off;
+    S.u_used = u_cursor - S.u_off;
+    if (S.rc == MP3_OK && dev_rc != MP3GPU_OK) {
+        S.rc = MP3_ERR_DEVICE;
+        S.err = dev_err;
     }
+}
+
+// The reference's README example (README.md:110-195): skip TotalDelay() stereo samples at the start and TotalPadding()
+// at the end when the first frame (behind the tags) carries a LAME tag.
+void trim_gapless(const uint8_t *data, size_t len, mp3_stream_result &r) {
+    if (r.pcm_bytes <= 0) return;
+    Source s;
+    s.data = data;
+    s.len = len;
+    if (s.skip_tags() != MP3_OK) return;
+    mp3_lame_info info;
+    if (lameinfo_parse_from_reader(data + s.pos, len - (size_t)s.pos, &info) != MP3_OK || !info.has_lame_info) return;
+    const int64_t skip = (int64_t)lameinfo_total_delay(&info) * 4, trim = (int64_t)lameinfo_total_padding(&info) * 4;
+    if (skip + trim > r.pcm_bytes) return;
+    r.pcm_offset += skip;
+    r.pcm_bytes -= skip + trim;
+}
+
+}  // namespace
+
+// DecodeBatch.  The streams are dealt to the engine's devices in contiguous blocks balanced by input bytes (streams share
+// nothing: no collective); every device runs the chunked parse -> gather -> device pipeline above on its
+// own host thread, with its share of the parsing threads, in its own region of the pinned arenas.
+extern "C" int mp3_decode_batch(mp3_engine *e, const uint8_t *const *data, const size_t *lens, size_t n,
+                                mp3_stream_result *results, const uint8_t **pcm_base, mp3_batch_timings *timings) {
+    if (!e || !results || !pcm_base || (n && (!data || !lens))) return MP3_ERR_INVALID;
+    const double t0 = now_s();
+    const size_t D = e->devs.size();
+    const int threads = hw_threads(e->opts.host_threads);
+    // ---- arena bounds: main data never exceeds the input bytes; unit slots from a header-only frame walk ----
+    std::vector<size_t> ub(n);
+    {
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (;;) {
+                size_t i = next.fetch_add(1);
+                if (i >= n) break;
+                ub[i] = unit_slots_upper_bound(data[i], lens[i]);
+            }
+        };
+        int nt = (int)std::min<size_t>((size_t)threads, n ? n : 1);
+        if (nt > 1 && n >= 64) {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nt; t++) th.emplace_back(work);
+            for (auto &t : th) t.join();
+        } else {
+            work();
+        }
+    }
+    // ---- shards: contiguous blocks of streams, balanced by bytes ----
+    std::vector<Shard> shards(D);
+    {
+        size_t total = 0;
+        for (size_t i = 0; i < n; i++) total += lens[i];
+        size_t i = 0, acc = 0, m_off = 0, u_off = 0;
+        for (size_t d = 0; d < D; d++) {
+            Shard &S = shards[d];
+            S.i0 = i;
+            const size_t target = (size_t)((double)total * (double)(d + 1) / (double)D);
+            while (i < n && (d + 1 == D || acc + lens[i] / 2 < target)) acc += lens[i++];
+            S.i1 = i;
+            size_t mb = 64 * (shard_chunks(S.i1 - S.i0) + 1), us = 0;
+            for (size_t k = S.i0; k < S.i1; k++) {
+                mb += (lens[k] + 3) & ~size_t(3);
+                us += ub[k];
+            }
+            mb = (mb + 63) & ~size_t(63);
+            S.m_off = m_off;
+            S.m_cap = mb;
+            S.u_off = u_off;
+            S.u_cap = us;
+            m_off += mb;
+            u_off += us;
+        }
+        int rc = e->ensure(e->a_main, m_off + 64);
+        if (rc == MP3_OK) rc = e->ensure(e->a_units, sizeof(mp3gpu_unit) * u_off + 64);
+        if (rc == MP3_OK) rc = e->ensure(e->a_pcm, (u_off / 2) * MP3GPU_PCM_BYTES_PER_GRANULE + 64);
+        if (rc != MP3_OK) return rc;
+    }
+    if (D == 1) {
+        decode_shard(e, e->devs[0], data, lens, results, shards[0], threads);
+    } else {
+        const int per = std::max(1, threads / (int)D);
+        std::vector<std::thread> th;
+        for (size_t d = 0; d < D; d++)
+            th.emplace_back([&, d]() { decode_shard(e, e->devs[d], data, lens, results, shards[d], per); });
+        for (auto &t : th) t.join();
+    }
+    const double t3 = now_s();
+    for (size_t d = 0; d < D; d++)
+        if (shards[d].rc != MP3_OK) {
+            e->set_err(shards[d].err);
+            return shards[d].rc;
+        }
+    if (e->opts.trim_gapless)
+        for (size_t i = 0; i < n; i++) trim_gapless(data[i], lens[i], results[i]);
     *pcm_base = (const uint8_t *)e->a_pcm.p;
     if (timings) {
-        timings->parse_s = parse_s;     // summed over the chunks; chunks after the first overlap the device call
-        timings->gather_s = gather_s;
-        timings->device_s = device_s;   // summed device-call time (worker thread)
+        memset(timings, 0, sizeof *timings);
+        size_t granules = 0;
+        for (size_t d = 0; d < D; d++) {  // the devices run side by side: the slowest one's sums
+            timings->parse_s = std::max(timings->parse_s, shards[d].parse_s);   // summed over the chunks; chunks after the first overlap the device call
+            timings->gather_s = std::max(timings->gather_s, shards[d].gather_s);
+            timings->device_s = std::max(timings->device_s, shards[d].device_s);  // summed device-call time (worker thread)
+            timings->main_data_bytes += shards[d].m_used;
+            granules += shards[d].u_used / 2;
+        }
         timings->total_s = t3 - t0;
-        timings->main_data_bytes = m_cursor;
-        timings->n_granules = u_cursor / 2;
-        timings->pcm_bytes = (uint64_t)(u_cursor / 2) * MP3GPU_PCM_BYTES_PER_GRANULE;
+        timings->n_granules = granules;
+        // the span of the PCM buffer that holds results (regions of devices are laid out by their bounds: for well-formed
+        // streams the bound is exact and the span is dense)
+        const Shard &last = shards[D - 1];
+        timings->pcm_bytes = (uint64_t)((last.u_off + last.u_used) / 2) * MP3GPU_PCM_BYTES_PER_GRANULE;
     }
     return MP3_OK;
 }
@@ -466,6 +598,7 @@ extern "C" int mp3_decode_batch(mp3_engine *e, const uint8_t *const *data, const
 // the same source position after Seek-to-end (tracked per buffered frame).
 struct mp3_decoder {
     mp3_engine *eng = nullptr;
+    DeviceSlot *dev = nullptr;
     StreamParser parser;
     bool seekable = false;
     int sample_rate = 0;
@@ -548,12 +681,14 @@ struct mp3_decoder {
             for (auto &u : sub) u.bit_start -= base_bits;
             M.resize(M.size() + 64, 0);  // device reads whole words; keep the tail defined
             pcm_tmp.resize(n_gr * 1152);
-            int grc = eng->api.decode(eng->gpu, M.data(), M.size() - 64, sub.data(), n_gr, pcm_tmp.data());
-            M.resize(M.size() - 64);
-            if (grc != MP3GPU_OK) {
-                eng->err = eng->api.last_error(eng->gpu);
-                return MP3_ERR_DEVICE;
+            int grc;
+            {
+                std::lock_guard<std::mutex> lk(dev->mu);
+                grc = eng->api.decode(dev->gpu, M.data(), M.size() - 64, sub.data(), n_gr, pcm_tmp.data());
+                if (grc != MP3GPU_OK) eng->set_err(eng->api.last_error(dev->gpu));
             }
+            M.resize(M.size() - 64);
+            if (grc != MP3GPU_OK) return MP3_ERR_DEVICE;
             const uint8_t *pcm = reinterpret_cast<const uint8_t *>(pcm_tmp.data()) + (halo_units / 2) * MP3GPU_PCM_BYTES_PER_GRANULE;
             size_t off = 0;
             for (int f = 0; f < got; f++) {
@@ -645,14 +780,19 @@ struct mp3_decoder {
 };
 
 extern "C" mp3_decoder *mp3_new_decoder(mp3_engine *e, const uint8_t *data, size_t len, int seekable, int *err) {
+    return mp3_new_decoder_on(e, 0, data, len, seekable, err);
+}
+
+extern "C" mp3_decoder *mp3_new_decoder_on(mp3_engine *e, int slot, const uint8_t *data, size_t len, int seekable, int *err) {
     int dummy;
     if (!err) err = &dummy;
-    if (!e || (!data && len)) {
+    if (!e || (!data && len) || slot < 0 || (size_t)slot >= e->devs.size()) {
         *err = MP3_ERR_INVALID;
         return nullptr;
     }
     mp3_decoder *d = new mp3_decoder();
     d->eng = e;
+    d->dev = e->devs[(size_t)slot];
     d->seekable = seekable != 0;
     d->parser.src.data = data;
     d->parser.src.len = len;
@@ -837,4 +977,175 @@ extern "C" int mp3_decoder_seek_to_time(mp3_decoder *d, int64_t t) {  // decode.
 }
 extern "C" int mp3_decoder_skip(mp3_decoder *d, int64_t delta) {  // decode.go:313-315
     return mp3_decoder_seek_to_time(d, mp3_decoder_position_ns(d) + delta);
+}
+
+// ---- One long stream: frame index, frame-range decode, split over the devices (BASELINE.json configs[4]) ------------
+struct mp3_stream_index {
+    const uint8_t *data = nullptr;
+    size_t len = 0;
+    int sample_rate = 0;
+    std::vector<int64_t> frame_pos;     // byte offset of every frame header (decode.go:154-216's frameStarts)
+    std::vector<uint32_t> own_bytes;    // main-data bytes the frame owns (frame size - header - CRC - side info)
+    std::vector<int64_t> gran_before;   // granules in front of frame f; one more entry at the end = all granules
+};
+
+extern "C" int mp3_stream_index_create(const uint8_t *data, size_t len, mp3_stream_index **out) {
+    if (!out || (!data && len)) return MP3_ERR_INVALID;
+    *out = nullptr;
+    mp3_stream_index *ix = new mp3_stream_index();
+    ix->data = data;
+    ix->len = len;
+    Source s;
+    s.data = data;
+    s.len = len;
+    int rc = s.skip_tags();
+    if (rc != MP3_OK) {
+        delete ix;
+        return rc;
+    }
+    int64_t gran = 0;
+    for (;;) {
+        Header h;
+        int64_t fpos;
+        rc = read_frame_header(s, &h, &fpos);
+        if (rc != MP3_OK) break;
+        if (h.id() == 0 || h.layer() != 1) break;  // frame.Read refuses these (frame.go:79-84): the linear decode ends here
+        const int fs = h.frame_size();
+        const int own = fs - 4 - h.side_info_size() - (h.protection_bit() == 0 ? 2 : 0);
+        if (fs > 2000 || own < 0 || own > 1500 || s.pos + (fs - 4) > (int64_t)len) break;
+        if (ix->frame_pos.empty()) ix->sample_rate = h.sampling_frequency_value();
+        ix->frame_pos.push_back(fpos);
+        ix->own_bytes.push_back((uint32_t)own);
+        ix->gran_before.push_back(gran);
+        gran += h.granules();
+        s.pos += fs - 4;
+    }
+    ix->gran_before.push_back(gran);
+    *out = ix;
+    return MP3_OK;
+}
+extern "C" void mp3_stream_index_free(mp3_stream_index *ix) { delete ix; }
+extern "C" int64_t mp3_stream_index_frames(const mp3_stream_index *ix) { return ix ? (int64_t)ix->frame_pos.size() : 0; }
+extern "C" int mp3_stream_index_sample_rate(const mp3_stream_index *ix) { return ix ? ix->sample_rate : 0; }
+extern "C" int64_t mp3_stream_index_pcm_bytes(const mp3_stream_index *ix, int64_t f0, int64_t f1) {
+    if (!ix || f0 < 0 || f1 < f0 || f1 > (int64_t)ix->frame_pos.size()) return -1;
+    return (ix->gran_before[(size_t)f1] - ix->gran_before[(size_t)f0]) * MP3GPU_PCM_BYTES_PER_GRANULE;
+}
+
+extern "C" int mp3_decode_frames(mp3_engine *e, int slot, const mp3_stream_index *ix, int64_t f0, int64_t f1, uint8_t *pcm_out,
+                                 int64_t *pcm_bytes) {
+    if (pcm_bytes) *pcm_bytes = 0;
+    if (!e || !ix || slot < 0 || (size_t)slot >= e->devs.size() || f0 < 0 || f1 < f0 || f1 > (int64_t)ix->frame_pos.size() ||
+        (f1 > f0 && !pcm_out))
+        return MP3_ERR_INVALID;
+    if (f1 == f0) return MP3_OK;
+    DeviceSlot *dev = e->devs[(size_t)slot];
+    // Halo: whole frames covering the two granules in front of f0 (PCM of a granule needs the IMDCT overlap of the one
+    // before it and 15 slots of synthesis history, which need the overlap of the one before that: SURVEY.md 8e).
+    int64_t fh = f0;
+    while (fh > 0 && ix->gran_before[(size_t)f0] - ix->gran_before[(size_t)fh] < 2) fh--;
+    // Lead-in: frames parsed (not decoded) so that the reservoir state at fh is the linear decode's.  A frame's logical
+    // buffer reaches at most 511 bytes back (9-bit main_data_begin, maindata.go:290-323); once the frames parsed in front
+    // own that many bytes, window starts and lengths no longer depend on how the parse began (prev == nil ignores
+    // main_data_begin, and an underflow keeps all of prev: both only ever make the window start later than the
+    // linear decode's until 511 bytes are covered).  One more frame for the first frame's own quirk (Q8).
+    int64_t fl = fh;
+    {
+        size_t covered = 0;
+        while (fl > 0 && covered < 512) covered += ix->own_bytes[(size_t)--fl];
+        if (fl > 0) fl--;
+    }
+    StreamParser P;
+    P.src.data = ix->data;
+    P.src.len = ix->len;
+    P.src.pos = ix->frame_pos[(size_t)fl];
+    std::vector<uint8_t> M;
+    std::vector<mp3gpu_unit> units;
+    M.reserve((size_t)(ix->frame_pos[(size_t)f1 - 1] - ix->frame_pos[(size_t)fl]) + 2048);
+    units.reserve((size_t)(ix->gran_before[(size_t)f1] - ix->gran_before[(size_t)fl]) * 2);
+    size_t units_at_fh = 0, units_at_f0 = 0;
+    int rc = MP3_OK;
+    int64_t f = fl;
+    for (; f < f1; f++) {
+        if (f == fh) units_at_fh = units.size();
+        if (f == f0) units_at_f0 = units.size();
+        rc = P.next_frame(M, units, 0);
+        if (rc != MP3_OK) break;
+    }
+    if (f <= f0) {  // nothing of the range itself could be parsed
+        if (rc == MP3_EOF || rc == MP3_ERR_UNEXPECTED_EOF || rc == MP3_ERR_SYNC_LIMIT) rc = MP3_EOF;  // decode.go:48-63
+        return rc;
+    }
+    if (fl > 0 && units_at_fh < units.size()) {
+        // the parse began mid-stream: nothing in front of the halo is decoded, and the halo starts from whatever state
+        // the device has there (its output is dropped) — but never from a zero-state flag the lead-in's first frame got
+        for (size_t k = units_at_fh; k < units.size(); k++) units[k].w2 &= ~MP3GPU_W2_ZERO_STATE;
+    }
+    const size_t n_units = units.size() - units_at_fh, halo_gr = (units_at_f0 - units_at_fh) / 2, n_gr = n_units / 2;
+    int grc;
+    {
+        std::lock_guard<std::mutex> lk(dev->mu);
+        // pinned staging makes the device call's copies asynchronous (it pipelines H2D / kernels / D2H wave by wave)
+        int prc = e->ensure(dev->r_main, M.size() + 64);
+        if (prc == MP3_OK) prc = e->ensure(dev->r_units, n_units * sizeof(mp3gpu_unit) + 64);
+        if (prc != MP3_OK) return prc;
+        memcpy(dev->r_main.p, M.data(), M.size());
+        memset((uint8_t *)dev->r_main.p + M.size(), 0, 64);
+        memcpy(dev->r_units.p, units.data() + units_at_fh, n_units * sizeof(mp3gpu_unit));
+        grc = e->api.decode_range(dev->gpu, (const uint8_t *)dev->r_main.p, M.size(), (const mp3gpu_unit *)dev->r_units.p, n_gr, halo_gr,
+                                  (int16_t *)pcm_out);
+        if (grc != MP3GPU_OK) e->set_err(e->api.last_error(dev->gpu));
+    }
+    if (grc != MP3GPU_OK) return MP3_ERR_DEVICE;
+    if (pcm_bytes) *pcm_bytes = (int64_t)(n_gr - halo_gr) * MP3GPU_PCM_BYTES_PER_GRANULE;
+    if (rc == MP3_EOF || rc == MP3_ERR_UNEXPECTED_EOF || rc == MP3_ERR_SYNC_LIMIT) rc = MP3_OK;  // a clean end of stream inside the range
+    return rc;
+}
+
+extern "C" int mp3_decode_stream_split(mp3_engine *e, const mp3_stream_index *ix, const uint8_t **pcm_base, int64_t *pcm_bytes,
+                                       mp3_batch_timings *timings) {
+    if (!e || !ix || !pcm_base || !pcm_bytes) return MP3_ERR_INVALID;
+    const double t0 = now_s();
+    const int64_t frames = (int64_t)ix->frame_pos.size();
+    const size_t D = e->devs.size();
+    const int64_t total = mp3_stream_index_pcm_bytes(ix, 0, frames);
+    int rc = e->ensure(e->a_pcm, (size_t)total + 64);
+    if (rc != MP3_OK) return rc;
+    std::vector<int> rcs(D, MP3_OK);
+    std::vector<int64_t> got(D, 0), want(D, 0);
+    std::vector<double> secs(D, 0.0);
+    auto run = [&](size_t d) {
+        const int64_t f0 = frames * (int64_t)d / (int64_t)D, f1 = frames * (int64_t)(d + 1) / (int64_t)D;
+        want[d] = mp3_stream_index_pcm_bytes(ix, f0, f1);
+        const double a = now_s();
+        rcs[d] = mp3_decode_frames(e, (int)d, ix, f0, f1, (uint8_t *)e->a_pcm.p + mp3_stream_index_pcm_bytes(ix, 0, f0), &got[d]);
+        secs[d] = now_s() - a;
+    };
+    if (D == 1) {
+        run(0);
+    } else {
+        std::vector<std::thread> th;
+        for (size_t d = 0; d < D; d++) th.emplace_back(run, d);
+        for (auto &t : th) t.join();
+    }
+    // what a linear decode returns: everything up to the first range that ended early
+    int64_t out = 0;
+    int status = MP3_OK;
+    for (size_t d = 0; d < D; d++) {
+        out += got[d];
+        if (rcs[d] != MP3_OK || got[d] != want[d]) {
+            status = rcs[d];
+            break;
+        }
+    }
+    *pcm_base = (const uint8_t *)e->a_pcm.p;
+    *pcm_bytes = out;
+    if (timings) {
+        memset(timings, 0, sizeof *timings);
+        for (size_t d = 0; d < D; d++) timings->device_s = std::max(timings->device_s, secs[d]);  // per range: host parse + device call
+        timings->total_s = now_s() - t0;
+        timings->n_granules = (uint64_t)(out / MP3GPU_PCM_BYTES_PER_GRANULE);
+        timings->pcm_bytes = (uint64_t)out;
+    }
+    return status;
 }

@@ -62,116 +62,152 @@ struct WaveBufs {
     float *hyb;        // [-1..nw)[2][18][32] subband samples (k_hybrid -> k_synth), one look-back granule in front
     float *tap_xr;     // debug tap (opts.keep_intermediates): [nw][2][576] index sb*18+m, else nullptr
     const float *synth_d;  // [512]     frame.go:499-628
-    unsigned int *work_counter;  // dynamic segment scheduler of k_hybrid
+    unsigned int *work_counter;  // dynamic segment scheduler of k_hybrid; work_counter[1]: tile scheduler of k_huffman
 };
 
 // ------------------------------------------------------------------------------------------
 // K1: scalefactors + Huffman.  One thread per unit slot; per-unit logic in unit_logic.h.
 // ------------------------------------------------------------------------------------------
-// The grid is persistent (a few CTAs per SM, each walking tiles of THREADS units with a grid stride), so the 33 KB of
-// code tables are staged into shared memory once per CTA and not once per tile.  Per tile:
+// One persistent CTA per SM; its warps share the code tables (30 KB, staged once) and otherwise never meet: every WARP
+// pulls tiles of UPW (32 or 64) consecutive units from a global counter and handles a tile on its own —
 //  1. Work order.  A unit's decode time is proportional to its number of code words, and the 32 lanes of a warp wait
-//     for the slowest: with units in stream order a warp's lanes were busy 37 % of the time.  The CTA deals the tile's
-//     consecutive units to its threads in order of big_values (a counting sort in shared memory, 8-pair bins, largest
-//     first), so the lanes of a warp get units of similar length while the CTA still reads one contiguous stretch of
-//     main data and writes one contiguous stretch of output.
+//     for the slowest.  With UPW = 64 the warp sorts the tile's units by big_values (counting sort in its private bins)
+//     and decodes the 32 longer ones first, then the 32 shorter ones, so that the lanes of a pass get similar lengths.
 //  2. Staging.  The units of a tile are consecutive in stream order, so the bits they read are one contiguous stretch
-//     of main_data (streams lie back to back).  The CTA copies that stretch into shared memory with coalesced 16-byte
-//     loads, byte-swapped once into big-endian bit order; a unit's cursor is then a plain bit position
-//     (StagedCursor, unit_logic.h) — no register window, no divergent refill.  What lies outside the stretch (a tile
-//     whose stretch exceeds the staging capacity, malformed descriptors) is read from global memory word by word.
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
+//     of main_data (streams lie back to back).  The warp copies that stretch into its private staging area with
+//     coalesced 16-byte loads, byte-swapped once into big-endian bit order; a unit's cursor is then a plain bit position
+//     (StagedCursor / FastWindow, unit_logic.h) — no divergent refill from global memory.  What lies outside the stretch
+//     (a tile whose stretch exceeds the staging capacity, malformed descriptors) is read from global memory word by word.
+// The first version of this design did 1. and 2. per CTA (256-512 units sorted and staged at once).  It sorted better, but
+// its four CTA barriers per tile left the warps with the shorter units and all warps during the staging loads idle: a
+// third of the stall samples sat on the barriers (profiles/r02_k1_history.md); there is no __syncthreads in the loop now.
+template <int UPW>
+__global__ void __launch_bounds__(1024, 1)
 k_huffman(const uint8_t *__restrict__ main_data, unsigned long long main_bits, const mp3gpu_unit *__restrict__ units,
-          long long first_unit, int n_units, DeviceTables T, WaveBufs B, int stage_cap16) {
-    extern __shared__ __align__(16) uint32_t s_dyn32[];  // pair-tree code tables (uint16 entries), then the staged stretch
+          long long first_unit, int n_units, DeviceTables T, WaveBufs B, int stage_cap16, unsigned int *__restrict__ tile_counter) {
+    extern __shared__ __align__(16) uint32_t s_dyn32[];  // pair-tree code tables (uint16 entries), then one block per warp
     __shared__ uint64_t s_quad[256];
     __shared__ uint32_t s_qlut[512];
     __shared__ uint32_t s_desc[34];
-    __shared__ unsigned int s_bin[40];
-    __shared__ unsigned int s_lohi[2];
-    __shared__ uint16_t s_order[THREADS];
+    constexpr int NP = UPW / 32;  // units per lane and tile
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const SmemRef s_lut = SmemRef::of(s_dyn32);
-    uint32_t *const s_stage = s_dyn32 + T.huff_lut_n / 2;  // huff_lut_n is a multiple of 8 entries (tables.cc): 16-byte aligned
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(T.huff_lut);
         uint4 *dst = reinterpret_cast<uint4 *>(s_dyn32);
 #pragma unroll 4
-        for (int i = threadIdx.x; i < T.huff_lut_n / 8; i += THREADS) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < T.huff_lut_n / 8; i += blockDim.x) dst[i] = __ldg(src + i);
     }
-    for (int i = threadIdx.x; i < 512; i += THREADS) s_qlut[i] = T.quad_lut[i];
     if (threadIdx.x < 34) s_desc[threadIdx.x] = T.huff_desc[threadIdx.x];
-    if (threadIdx.x < 256) s_quad[threadIdx.x] = T.quad_signs[threadIdx.x];
-    const int n_tiles = (n_units + THREADS - 1) / THREADS;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_quad[i] = T.quad_signs[i];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_qlut[i] = T.quad_lut[i];
+    __syncthreads();  // the only CTA barrier: the tables are staged
+    // this warp's block: staging area (+ 16 bytes the FastWindow prefetch may touch), sort bins, work order
+    const int warp_words = stage_cap16 * 4 + 4 + 40 + UPW / 4;
+    uint32_t *const s_stage = s_dyn32 + T.huff_lut_n / 2 + warp * warp_words;  // huff_lut_n is a multiple of 8 entries: 16-byte aligned
+    unsigned int *const s_bin = s_stage + stage_cap16 * 4 + 4;
+    uint8_t *const s_order = reinterpret_cast<uint8_t *>(s_bin + 40);
     const uint32_t main16 = (uint32_t)(((main_bits >> 3) + 48) >> 4);  // 16-byte chunks that may be read: main_data is followed by 64 bytes of padding
+    const int n_tiles = (n_units + UPW - 1) / UPW;
 #pragma unroll 1
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        if (threadIdx.x < 40) s_bin[threadIdx.x] = 0;
-        if (threadIdx.x == 0) { s_lohi[0] = 0xffffffffu; s_lohi[1] = 0u; }
-        __syncthreads();  // also: the previous tile's s_order / s_stage reads are done, the tables are staged
-        // ---- work order inside the tile, and the stretch of main data the tile reads ---------------------
-        const int base = tile * THREADS;
-        int key = 38;  // beyond the wave
+    for (;;) {
+        int tile = 0;
+        if (lane == 0) tile = (int)atomicAdd(tile_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= n_tiles) break;
+        const int base = tile * UPW;
+        // ---- the stretch of main data the tile reads, and the work order inside the tile ---------------------
+        int key[NP];
         uint32_t lo16 = 0xffffffffu, hi16 = 0u;
-        {
-            const int ul0 = base + threadIdx.x;
+#pragma unroll
+        for (int j = 0; j < NP; j++) {
+            key[j] = 38;  // beyond the wave
+            const int ul0 = base + j * 32 + lane;
             if (ul0 < n_units) {
                 const mp3gpu_unit u = units[first_unit + ul0];
-                key = 37;
+                key[j] = 37;
                 if (u_valid(u.w2)) {
-                    key = 36 - ((u_p23len(u.w0) == 0 ? 0 : imin(u_bigval(u.w0), 288)) >> 3);
-                    stage_reach(u, main_bits, &lo16, &hi16);
+                    key[j] = 36 - ((u_p23len(u.w0) == 0 ? 0 : imin(u_bigval(u.w0), 288)) >> 3);
+                    uint32_t l, h;
+                    stage_reach(u, main_bits, &l, &h);
+                    lo16 = l < lo16 ? l : lo16;
+                    hi16 = h > hi16 ? h : hi16;
                 }
             }
         }
         lo16 = __reduce_min_sync(0xffffffffu, lo16);
         hi16 = __reduce_max_sync(0xffffffffu, hi16);
-        if ((threadIdx.x & 31) == 0) {
-            atomicMin(&s_lohi[0], lo16);
-            atomicMax(&s_lohi[1], hi16);
-        }
-        const unsigned int rank = atomicAdd(&s_bin[key], 1u);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned int acc = 0;
-            for (int i = 0; i < 39; i++) { const unsigned int c = s_bin[i]; s_bin[i] = acc; acc += c; }
+        if (NP > 1) {
+            s_bin[lane] = 0;
+            if (lane < 8) s_bin[32 + lane] = 0;
+            __syncwarp();
+            unsigned int rank[NP];
+#pragma unroll
+            for (int j = 0; j < NP; j++) rank[j] = atomicAdd(&s_bin[key[j]], 1u);
+            __syncwarp();
+            {   // exclusive scan of the 39 bins: lanes 0..31 hold bins 0..31, lanes 0..6 also bins 32..38
+                const unsigned int c0 = s_bin[lane];
+                unsigned int x = c0;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned int y = __shfl_up_sync(0xffffffffu, x, d);
+                    if (lane >= d) x += y;
+                }
+                const unsigned int total32 = __shfl_sync(0xffffffffu, x, 31);
+                const unsigned int c1 = lane < 7 ? s_bin[32 + lane] : 0u;
+                unsigned int z = c1;
+#pragma unroll
+                for (int d = 1; d < 8; d <<= 1) {
+                    const unsigned int y = __shfl_up_sync(0xffffffffu, z, d);
+                    if (lane >= d) z += y;
+                }
+                __syncwarp();
+                s_bin[lane] = x - c0;
+                if (lane < 7) s_bin[32 + lane] = total32 + z - c1;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < NP; j++) s_order[s_bin[key[j]] + rank[j]] = (uint8_t)(j * 32 + lane);
         }
         StageCtx S;
-        S.sw = s_lut.plus((uint32_t)T.huff_lut_n * 2u);
+        S.sw = SmemRef::of(s_stage);
         S.gw = reinterpret_cast<const uint32_t *>(main_data);
         S.main_bits = main_bits;
         {
-            const uint32_t lo = s_lohi[0];
-            uint32_t hi = s_lohi[1] < main16 ? s_lohi[1] : main16;
-            uint32_t n16 = hi > lo ? hi - lo : 0u;   // no valid unit in the tile: lo = ~0
+            const uint32_t hi = hi16 < main16 ? hi16 : main16;
+            uint32_t n16 = hi > lo16 ? hi - lo16 : 0u;  // no valid unit in the tile: lo = ~0
             if (n16 > (uint32_t)stage_cap16) n16 = (uint32_t)stage_cap16;
             S.n_words = (int)(n16 * 4);
-            S.lo_word = (unsigned long long)lo * 4ull;
-            const uint4 *src = reinterpret_cast<const uint4 *>(main_data) + lo;
+            S.lo_word = (unsigned long long)lo16 * 4ull;
+            const uint4 *src = reinterpret_cast<const uint4 *>(main_data) + lo16;
             uint4 *dst = reinterpret_cast<uint4 *>(s_stage);
 #pragma unroll 4
-            for (uint32_t i = threadIdx.x; i < n16; i += THREADS) {
+            for (uint32_t i = lane; i < n16; i += 32) {
                 uint4 v = __ldg(src + i);
                 v.x = be32(v.x); v.y = be32(v.y); v.z = be32(v.z); v.w = be32(v.w);
                 dst[i] = v;
             }
         }
-        __syncthreads();
-        s_order[s_bin[key] + rank] = (uint16_t)threadIdx.x;
-        __syncthreads();
-        const int ul = base + s_order[threadIdx.x];  // wave-local unit index
-        if (ul >= n_units) continue;
-        if (!u_valid(units[first_unit + ul].w2)) {
-            B.meta[ul] = 0;
-            continue;
+        __syncwarp();
+        // ---- decode: the longer units first -------------------------------------------------------------------
+#pragma unroll 1
+        for (int pass = 0; pass < NP; pass++) {
+            const int ul = base + (NP > 1 ? (int)s_order[pass * 32 + lane] : lane);  // wave-local unit index
+            if (ul < n_units) {
+                if (!u_valid(units[first_unit + ul].w2)) {
+                    B.meta[ul] = 0;
+                } else {
+                    uint32_t pk[8];
+                    uint32_t *out = reinterpret_cast<uint32_t *>(B.is16 + (size_t)ul * 576);
+                    const uint32_t meta = huffman_unit_staged(T, s_lut, s_qlut, s_desc, s_quad, S, units, first_unit + ul, pk, out);
+                    uint4 *dst = reinterpret_cast<uint4 *>(B.sfpack + (size_t)ul * 8);
+                    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    B.meta[ul] = meta;
+                }
+            }
+            __syncwarp();
         }
-        uint32_t pk[8];
-        uint32_t *out = reinterpret_cast<uint32_t *>(B.is16 + (size_t)ul * 576);
-        const uint32_t meta = huffman_unit_staged(T, s_lut, s_qlut, s_desc, s_quad, S, units, first_unit + ul, pk, out);
-        uint4 *dst = reinterpret_cast<uint4 *>(B.sfpack + (size_t)ul * 8);
-        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        B.meta[ul] = meta;
     }
 }
 

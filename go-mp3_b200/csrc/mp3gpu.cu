@@ -23,6 +23,10 @@ static_assert(sizeof(mp3gpu_unit) == 32, "mp3gpu_unit must be 32 bytes");
         cudaError_t e__ = (call);                                                             \
         if (e__ != cudaSuccess) {                                                             \
             ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                   \
+            if (e__ == cudaErrorMemoryAllocation) {                                           \
+                cudaGetLastError(); /* not sticky: the context stays usable */                \
+                return MP3GPU_E_NOMEM;                                                        \
+            }                                                                                 \
             return MP3GPU_E_CUDA;                                                             \
         }                                                                                     \
     } while (0)
@@ -42,8 +46,8 @@ struct mp3gpu_ctx {
     DeviceTables T{};
     int lut_bytes = 0;
     int smem_per_sm = 0, smem_per_cta_max = 0;  // shared-memory budget (bytes) of an SM / of one CTA (opt-in maximum)
-    int huff_static_smem[3] = {0, 0, 0};        // static shared memory of k_huffman<256 / 512 / 1024>
-    int k1_threads_override = 0, k1_stage_kb_override = 0;  // experiments: MP3GPU_K1_THREADS / MP3GPU_K1_STAGE_KB
+    int huff_static_smem = 0;                   // static shared memory of k_huffman
+    int k1_upw_override = 0, k1_warps_override = 0, k1_stage_pct_override = 0;  // experiments: MP3GPU_K1_UPW / _WARPS / _STAGE_PCT
     // workspace for one wave (+1 granule look-back where needed)
     int16_t *d_is16 = nullptr;
     uint32_t *d_meta = nullptr;
@@ -61,6 +65,7 @@ struct mp3gpu_ctx {
     mp3gpu_unit *d_units = nullptr;
     size_t d_units_cap = 0;
     int16_t *d_pcm_ring[3] = {nullptr, nullptr, nullptr};
+    size_t ring_granules = 0;  // granules each ring slot holds
     cudaEvent_t ev_in[3]{}, ev_k[3]{}, ev_out[3]{};
     // timing
     cudaEvent_t ev_t[kTimingSlots][4]{};
@@ -82,7 +87,6 @@ static int ensure_workspace(mp3gpu_ctx *ctx, size_t granules) {
     CK(cudaStreamSynchronize(ctx->s_compute));
     cudaFree(ctx->d_is16); cudaFree(ctx->d_meta); cudaFree(ctx->d_sfpack); cudaFree(ctx->d_hyb); cudaFree(ctx->d_tap_xr);
 
-    for (int i = 0; i < 3; i++) { cudaFree(ctx->d_pcm_ring[i]); ctx->d_pcm_ring[i] = nullptr; }
     ctx->d_is16 = nullptr; ctx->d_meta = nullptr; ctx->d_sfpack = nullptr; ctx->d_hyb = nullptr; ctx->d_tap_xr = nullptr;
     ctx->ws_granules = 0;
     // K1 outputs, with two look-back granules (halo of k_hybrid) in front
@@ -218,6 +222,11 @@ extern "C" int mp3gpu_create(int device, const mp3gpu_opts *opts, mp3gpu_ctx **o
     *out = nullptr;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return MP3GPU_E_NO_DEVICE;
+    if (opts && opts->abi_version != MP3GPU_ABI_VERSION) {
+        fprintf(stderr, "mp3gpu_create: caller was built against ABI version %u, this library is version %u\n", opts->abi_version,
+                (unsigned)MP3GPU_ABI_VERSION);
+        return MP3GPU_E_INVALID;
+    }
     mp3gpu_ctx *ctx = new mp3gpu_ctx();
     ctx->device = device;
     if (opts) ctx->opts = *opts;
@@ -235,7 +244,7 @@ extern "C" int mp3gpu_create(int device, const mp3gpu_opts *opts, mp3gpu_ctx **o
         CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
         int rc = upload_tables(ctx);
         if (rc) return rc;
-        CK(cudaMalloc(&ctx->d_counter, sizeof(unsigned int)));
+        CK(cudaMalloc(&ctx->d_counter, 2 * sizeof(unsigned int)));
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, device));
         ctx->sm_count = prop.multiProcessorCount;
@@ -252,17 +261,13 @@ extern "C" int mp3gpu_create(int device, const mp3gpu_opts *opts, mp3gpu_ctx **o
         ctx->smem_per_cta_max = (int)prop.sharedMemPerBlockOptin;
         {
             cudaFuncAttributes fa;
-            CK(cudaFuncGetAttributes(&fa, k_huffman<256>));
-            ctx->huff_static_smem[0] = (int)fa.sharedSizeBytes;
-            CK(cudaFuncGetAttributes(&fa, k_huffman<512>));
-            ctx->huff_static_smem[1] = (int)fa.sharedSizeBytes;
-            CK(cudaFuncGetAttributes(&fa, k_huffman<1024>));
-            ctx->huff_static_smem[2] = (int)fa.sharedSizeBytes;
-            CK(cudaFuncSetAttribute(k_huffman<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_per_cta_max - ctx->huff_static_smem[0]));
-            CK(cudaFuncSetAttribute(k_huffman<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_per_cta_max - ctx->huff_static_smem[1]));
-            CK(cudaFuncSetAttribute(k_huffman<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_per_cta_max - ctx->huff_static_smem[2]));
-            if (const char *e = getenv("MP3GPU_K1_THREADS")) ctx->k1_threads_override = atoi(e);
-            if (const char *e = getenv("MP3GPU_K1_STAGE_KB")) ctx->k1_stage_kb_override = atoi(e);
+            CK(cudaFuncGetAttributes(&fa, k_huffman<64>));
+            ctx->huff_static_smem = (int)fa.sharedSizeBytes;
+            CK(cudaFuncSetAttribute(k_huffman<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_per_cta_max - ctx->huff_static_smem));
+            CK(cudaFuncSetAttribute(k_huffman<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_per_cta_max - ctx->huff_static_smem));
+            if (const char *e = getenv("MP3GPU_K1_UPW")) ctx->k1_upw_override = atoi(e);
+            if (const char *e = getenv("MP3GPU_K1_WARPS")) ctx->k1_warps_override = atoi(e);
+            if (const char *e = getenv("MP3GPU_K1_STAGE_PCT")) ctx->k1_stage_pct_override = atoi(e);
         }
         CK(cudaFuncSetAttribute(k_hybrid<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHybSmemBytes));
         CK(cudaFuncSetAttribute(k_hybrid<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHybSmemBytes));
@@ -325,38 +330,36 @@ static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, size_t main_len, 
     cudaStream_t s = ctx->s_compute;
     if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][0], s));
     {
-        // k_huffman stages the stretch of main data a tile of units reads in shared memory: the staging area is sized
-        // from the call's average bytes per unit (x 1.25 for tile-to-tile variation; a tile that needs more reads its
-        // tail from global memory), and the CTA size is the one that keeps the most warps resident next to the 33 KB of
-        // code tables each CTA holds.
+        // k_huffman: one persistent CTA per SM whose warps each stage the stretch of main data a tile of 32 or 64 units
+        // reads in their own piece of shared memory.  The piece is sized from the call's average bytes per unit (x 1.6 for
+        // tile-to-tile variation, VBR; a tile that needs more reads its tail from global memory), and the CTA gets as many
+        // warps as fit next to the 30 KB of code tables.  64-unit tiles (sorted, two passes) keep the lanes of a warp
+        // busier; 32-unit tiles allow twice the warps when the bitrate is high.
         const int nu = 2 * n;
         const unsigned long long main_bits = (unsigned long long)main_len * 8ull;
-        int best_t = 256, best_ctas = 1, best_stage = 0;
-        {
-            const double avg = bytes_per_unit > 1.0 ? bytes_per_unit : 1.0;
-            int best_warps = -1;
-            for (int ti = 0; ti < 3; ti++) {
-                const int t = 256 << ti;
-                if (ctx->k1_threads_override && t != ctx->k1_threads_override) continue;
-                const int fixed = ctx->lut_bytes + ctx->huff_static_smem[ti] + 1024 + 16;  // + the per-CTA reservation and the staging pad
-                int stage = (int)(avg * t * 1.25) + 2048;
-                if (ctx->k1_stage_kb_override) stage = ctx->k1_stage_kb_override * 1024;
-                const int cap = ctx->smem_per_cta_max - ctx->huff_static_smem[ti] - ctx->lut_bytes - 16;
-                if (stage > cap) stage = cap;
-                stage &= ~15;
-                int ctas = ctx->smem_per_sm / (fixed + stage);
-                if (ctas < 1) ctas = 1;
-                if (ctas > 1024 / t) ctas = 1024 / t;  // 64 registers per thread: 1,024 threads per SM
-                const int warps = ctas * t / 32;
-                if (warps > best_warps) { best_warps = warps; best_t = t; best_ctas = ctas; best_stage = stage; }
-            }
+        const double avg = bytes_per_unit > 1.0 ? bytes_per_unit : 1.0;
+        const int pct = ctx->k1_stage_pct_override ? ctx->k1_stage_pct_override : 160;
+        const int budget = ctx->smem_per_cta_max - ctx->huff_static_smem - ctx->lut_bytes;
+        int upw = 64, warps = 0, cap16 = 0;
+        for (int pass = 0; pass < 2; pass++) {
+            upw = pass == 0 ? 64 : 32;
+            if (ctx->k1_upw_override) upw = ctx->k1_upw_override == 32 ? 32 : 64;
+            int stage = ((int)(avg * upw * pct / 100.0) + 512 + 15) & ~15;
+            const int max_stage = budget / 8 - (16 + 160 + upw);  // at least eight warps
+            if (stage > max_stage) stage = max_stage & ~15;
+            const int per_warp = stage + 16 + 160 + upw;
+            warps = std::min(32, budget / per_warp);
+            if (ctx->k1_warps_override) warps = std::min(warps, ctx->k1_warps_override);
+            cap16 = stage / 16;
+            if (warps >= 20 || pass == 1 || ctx->k1_upw_override) break;
         }
-        const int tiles = (nu + best_t - 1) / best_t;
-        const int grid = std::min(tiles, ctx->sm_count * best_ctas);
-        const size_t dyn = (size_t)ctx->lut_bytes + (size_t)best_stage + 16;  // + the padding FastWindow's prefetch may touch
-        if (best_t == 256) k_huffman<256><<<grid, 256, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, best_stage / 16);
-        else if (best_t == 512) k_huffman<512><<<grid, 512, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, best_stage / 16);
-        else k_huffman<1024><<<grid, 1024, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, best_stage / 16);
+        if (warps < 1) warps = 1;
+        const int tiles = (nu + upw - 1) / upw;
+        const int grid = std::min((tiles + warps - 1) / warps, ctx->sm_count);
+        const size_t dyn = (size_t)ctx->lut_bytes + (size_t)warps * (size_t)(cap16 * 16 + 16 + 160 + upw);
+        CK(cudaMemsetAsync(ctx->d_counter + 1, 0, sizeof(unsigned int), s));
+        if (upw == 64) k_huffman<64><<<grid, warps * 32, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, cap16, ctx->d_counter + 1);
+        else k_huffman<32><<<grid, warps * 32, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, cap16, ctx->d_counter + 1);
     }
     if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][1], s));
     {
@@ -423,6 +426,16 @@ extern "C" int mp3gpu_decode_device_async(mp3gpu_ctx *ctx, const uint8_t *d_main
     ctx->last_slots = 0;
     ctx->last_collected = true;
     if (n_granules == 0) return MP3GPU_OK;
+    if (!d_main_data || !d_units || !d_pcm_out) {
+        ctx->err = "null device pointer";
+        return MP3GPU_E_INVALID;
+    }
+    if (((uintptr_t)d_main_data & 15) || ((uintptr_t)d_units & 15) || ((uintptr_t)d_pcm_out & 3)) {
+        // the kernels read main_data and the descriptors 16 bytes at a time and write PCM as 32-bit L|R words; a
+        // misaligned access would fault, and a CUDA fault is sticky (it takes the whole context down)
+        ctx->err = "device pointers must be aligned: main_data and units to 16 bytes, pcm to 4 bytes";
+        return MP3GPU_E_INVALID;
+    }
     {
         int rc = ensure_workspace(ctx, n_granules);
         if (rc) return rc;
@@ -478,7 +491,13 @@ static int ensure_cap(mp3gpu_ctx *ctx, T **p, size_t *cap, size_t need) {
 
 extern "C" int mp3gpu_decode(mp3gpu_ctx *ctx, const uint8_t *main_data, size_t main_data_len, const mp3gpu_unit *units,
                              size_t n_granules, int16_t *pcm_out) {
+    return mp3gpu_decode_range(ctx, main_data, main_data_len, units, n_granules, 0, pcm_out);
+}
+
+extern "C" int mp3gpu_decode_range(mp3gpu_ctx *ctx, const uint8_t *main_data, size_t main_data_len, const mp3gpu_unit *units,
+                                   size_t n_granules, size_t first_out, int16_t *pcm_out) {
     if (!ctx) return MP3GPU_E_INVALID;
+    if (first_out > n_granules) return MP3GPU_E_INVALID;
     CK(cudaSetDevice(ctx->device));
     ctx->last = mp3gpu_timings{};
     ctx->last_slots = 0;
@@ -499,8 +518,16 @@ extern "C" int mp3gpu_decode(mp3gpu_ctx *ctx, const uint8_t *main_data, size_t m
     rc = ensure_workspace(ctx, want);
     if (rc) return rc;
     const size_t W = std::min<size_t>(ctx->ws_granules, want);
-    for (int i = 0; i < 3; i++)
-        if (!ctx->d_pcm_ring[i]) CK(cudaMalloc(&ctx->d_pcm_ring[i], ctx->ws_granules * MP3GPU_PCM_BYTES_PER_GRANULE));
+    if (ctx->ring_granules < W) {  // sized by the wave this call uses, not by the (possibly much larger) workspace
+        CK(cudaStreamSynchronize(ctx->s_out));
+        for (int i = 0; i < 3; i++) {
+            cudaFree(ctx->d_pcm_ring[i]);
+            ctx->d_pcm_ring[i] = nullptr;
+        }
+        ctx->ring_granules = 0;
+        for (int i = 0; i < 3; i++) CK(cudaMalloc(&ctx->d_pcm_ring[i], W * MP3GPU_PCM_BYTES_PER_GRANULE));
+        ctx->ring_granules = W;
+    }
 
     // Wave w needs main_data up to the end of its last unit's frame buffer.  Units are in stream
     // order, so the byte ranges are monotonic; each wave uploads only the bytes not yet resident.
@@ -545,8 +572,11 @@ extern "C" int mp3gpu_decode(mp3gpu_ctx *ctx, const uint8_t *main_data, size_t m
         // -- D2H on s_out
         CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[r], 0));
         if (widx == 0) CK(cudaEventRecord(ctx->ev_copy[2], ctx->s_out));
-        CK(cudaMemcpyAsync(pcm_out + first * 1152, ctx->d_pcm_ring[r], (size_t)n * MP3GPU_PCM_BYTES_PER_GRANULE,
-                           cudaMemcpyDeviceToHost, ctx->s_out));
+        if (first + n > first_out) {  // granules in front of first_out (a frame-range job's halo) are decoded but not returned
+            const size_t skip = first_out > first ? first_out - first : 0;
+            CK(cudaMemcpyAsync(pcm_out + (first + skip - first_out) * 1152, ctx->d_pcm_ring[r] + skip * 1152,
+                               ((size_t)n - skip) * MP3GPU_PCM_BYTES_PER_GRANULE, cudaMemcpyDeviceToHost, ctx->s_out));
+        }
         CK(cudaEventRecord(ctx->ev_out[r], ctx->s_out));
         ctx->last.waves++;
     }
@@ -564,7 +594,7 @@ extern "C" int mp3gpu_decode(mp3gpu_ctx *ctx, const uint8_t *main_data, size_t m
 
 extern "C" void *mp3gpu_host_alloc(size_t bytes) {
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {  // portable: every device of a multi-GPU engine copies to / from it
         cudaGetLastError();
         return nullptr;
     }

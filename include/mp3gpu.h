@@ -50,7 +50,7 @@ enum {
     MP3GPU_E_NO_DEVICE = -1,
     MP3GPU_E_CUDA = -2,
     MP3GPU_E_INVALID = -3,
-    MP3GPU_E_NOMEM = -4
+    MP3GPU_E_NOMEM = -4      /* a device or pinned allocation failed (the context stays usable) */
 };
 
 /* One (granule, channel) bit-slice + side info.  32 bytes.
@@ -140,7 +140,16 @@ const char *mp3gpu_last_error(const mp3gpu_ctx *ctx);
 int mp3gpu_decode(mp3gpu_ctx *ctx, const uint8_t *main_data, size_t main_data_len,
                   const mp3gpu_unit *units, size_t n_granules, int16_t *pcm_out);
 
-/* Same, with every pointer DEVICE-resident on the context's device (no copies). */
+/* Same, but pcm_out receives only granules [first_out, n_granules): the granules in front are decoded for the state they
+ * leave behind (the halo of a frame-range job, mp3host.h: mp3_decode_frames) and their PCM is not copied back. */
+int mp3gpu_decode_range(mp3gpu_ctx *ctx, const uint8_t *main_data, size_t main_data_len,
+                        const mp3gpu_unit *units, size_t n_granules, size_t first_out, int16_t *pcm_out);
+
+/* Same, with every pointer DEVICE-resident on the context's device (no copies).
+ * Requirements on the caller's buffers (checked where they can be; MP3GPU_E_INVALID): d_main_data and d_units aligned to
+ * 16 bytes, d_pcm_out to 4 bytes (cudaMalloc and whole torch tensors are; a sliced tensor may not be), and d_main_data
+ * readable for 64 bytes past main_data_len (the kernels read whole 16-byte chunks and one word ahead; the bytes
+ * themselves are never used). */
 int mp3gpu_decode_device(mp3gpu_ctx *ctx, const uint8_t *d_main_data, size_t main_data_len,
                          const mp3gpu_unit *d_units, size_t n_granules, int16_t *d_pcm_out);
 
