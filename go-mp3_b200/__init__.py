@@ -38,6 +38,7 @@ MP3_ERR_ISPOS = -8
 MP3_ERR_SEEK_UNSUPPORTED = -11
 MP3_ERR_WHENCE = -12
 MP3_ERR_REF_PANIC = -14
+MP3_ERR_NO_XING_HEADER = -20
 MP3_ERR_DEVICE = -50
 MP3_ERR_INVALID = -51
 
@@ -78,9 +79,22 @@ class GpuTimings(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved_ms"}
 
 
+MAX_DEVICES = 16
+
+
 class EngineOpts(C.Structure):
+    """mp3_engine_opts (include/mp3host.h)."""
     _fields_ = [("device", C.c_int), ("host_threads", C.c_int), ("wave_granules", C.c_uint32),
-                ("chunk_frames", C.c_uint32), ("keep_intermediates", C.c_uint32), ("use_exact_library", C.c_uint32)]
+                ("chunk_frames", C.c_uint32), ("keep_intermediates", C.c_uint32), ("use_exact_library", C.c_uint32),
+                ("n_devices", C.c_int), ("devices", C.c_int * MAX_DEVICES), ("trim_gapless", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class LameInfoStruct(C.Structure):
+    """mp3_lame_info (include/mp3host.h) = lameinfo.Info (lameinfo/lameinfo.go:20-49)."""
+    _fields_ = [("is_xing", C.c_int32), ("flags", C.c_uint32), ("frame_count", C.c_uint32), ("byte_count", C.c_uint32),
+                ("toc", C.c_uint8 * 100), ("vbr_scale", C.c_uint32), ("has_lame_info", C.c_int32),
+                ("lame_version", C.c_char * 12), ("encoder_delay", C.c_uint16), ("encoder_padding", C.c_uint16)]
 
 
 class StreamResult(C.Structure):
@@ -155,6 +169,36 @@ def host_lib() -> C.CDLL:
     L.mp3_decode_batch.argtypes = [vp, pp_u8, C.POINTER(sz), sz, C.POINTER(StreamResult), C.POINTER(C.c_void_p),
                                    C.POINTER(BatchTimings)]
     L.mp3_decode_batch.restype = C.c_int
+    L.mp3_engine_device_count.argtypes = [vp]
+    L.mp3_engine_device_count.restype = C.c_int
+    L.mp3_engine_gpu_at.argtypes = [vp, C.c_int]
+    L.mp3_engine_gpu_at.restype = vp
+    L.mp3_new_decoder_on.argtypes = [vp, C.c_int, C.c_void_p, sz, C.c_int, C.POINTER(C.c_int)]
+    L.mp3_new_decoder_on.restype = vp
+    L.mp3_stream_index_create.argtypes = [C.c_void_p, sz, C.POINTER(vp)]
+    L.mp3_stream_index_create.restype = C.c_int
+    L.mp3_stream_index_free.argtypes = [vp]
+    L.mp3_stream_index_free.restype = None
+    L.mp3_stream_index_frames.argtypes = [vp]
+    L.mp3_stream_index_frames.restype = i64
+    L.mp3_stream_index_sample_rate.argtypes = [vp]
+    L.mp3_stream_index_sample_rate.restype = C.c_int
+    L.mp3_stream_index_pcm_bytes.argtypes = [vp, i64, i64]
+    L.mp3_stream_index_pcm_bytes.restype = i64
+    L.mp3_decode_frames.argtypes = [vp, C.c_int, vp, i64, i64, C.c_void_p, C.POINTER(i64)]
+    L.mp3_decode_frames.restype = C.c_int
+    L.mp3_decode_stream_split.argtypes = [vp, vp, C.POINTER(C.c_void_p), C.POINTER(i64), C.POINTER(BatchTimings)]
+    L.mp3_decode_stream_split.restype = C.c_int
+    L.mp3_lameinfo_parse.argtypes = [C.c_void_p, sz, C.POINTER(LameInfoStruct)]
+    L.mp3_lameinfo_parse.restype = C.c_int
+    L.mp3_lameinfo_parse_from_reader.argtypes = [C.c_void_p, sz, C.POINTER(LameInfoStruct)]
+    L.mp3_lameinfo_parse_from_reader.restype = C.c_int
+    L.mp3_lameinfo_total_delay.argtypes = [C.POINTER(LameInfoStruct)]
+    L.mp3_lameinfo_total_delay.restype = C.c_int
+    L.mp3_lameinfo_total_padding.argtypes = [C.POINTER(LameInfoStruct)]
+    L.mp3_lameinfo_total_padding.restype = C.c_int
+    L.mp3_lameinfo_is_lame_version.argtypes = [C.c_void_p, sz]
+    L.mp3_lameinfo_is_lame_version.restype = C.c_int
     L.mp3_parse_streams.argtypes = [pp_u8, C.POINTER(sz), sz, C.c_int, C.POINTER(C.POINTER(Parsed))]
     L.mp3_parse_streams.restype = C.c_int
     L.mp3_parsed_free.argtypes = [C.POINTER(Parsed)]
@@ -177,6 +221,8 @@ def gpu_lib(exact: bool = False) -> C.CDLL:
     L.mp3gpu_last_error.restype = C.c_char_p
     L.mp3gpu_decode.argtypes = [vp, vp, sz, vp, sz, vp]
     L.mp3gpu_decode.restype = C.c_int
+    L.mp3gpu_decode_range.argtypes = [vp, vp, sz, vp, sz, sz, vp]
+    L.mp3gpu_decode_range.restype = C.c_int
     L.mp3gpu_decode_device.argtypes = [vp, vp, sz, vp, sz, vp]
     L.mp3gpu_decode_device.restype = C.c_int
     L.mp3gpu_decode_device_async.argtypes = [vp, vp, sz, vp, sz, vp]
@@ -466,11 +512,22 @@ class Engine:
     """One GPU + the host stage.  Mirrors what the Go package holds as package-level state."""
 
     def __init__(self, device: int = 0, host_threads: int = 0, wave_granules: int = 0, chunk_frames: int = 0,
-                 keep_intermediates: bool = False, exact: bool = False):
+                 keep_intermediates: bool = False, exact: bool = False, devices: Optional[Sequence[int]] = None,
+                 trim_gapless: bool = False):
+        """`devices`: CUDA ordinals of a multi-GPU engine (DecodeBatch shards its streams over them, decode_stream_split
+        cuts one stream into a frame range per device); the same ordinal may appear twice (two device engines on one GPU)."""
         self.lib = host_lib()
         self.h = C.c_void_p()
-        opts = EngineOpts(device, host_threads, wave_granules, chunk_frames, 1 if keep_intermediates else 0,
-                          1 if exact else 0)
+        opts = EngineOpts()
+        opts.device, opts.host_threads, opts.wave_granules, opts.chunk_frames = device, host_threads, wave_granules, chunk_frames
+        opts.keep_intermediates, opts.use_exact_library = (1 if keep_intermediates else 0), (1 if exact else 0)
+        if devices:
+            if len(devices) > MAX_DEVICES:
+                raise ValueError("too many devices")
+            opts.n_devices = len(devices)
+            for i, d in enumerate(devices):
+                opts.devices[i] = int(d)
+        opts.trim_gapless = 1 if trim_gapless else 0
         rc = self.lib.mp3_engine_create(C.byref(opts), C.byref(self.h))
         if rc != MP3_OK:
             self.h = None
@@ -486,8 +543,34 @@ class Engine:
     def __del__(self):
         self.close()
 
-    def new_decoder(self, data: bytes, seekable: bool = True) -> "Decoder":
-        return Decoder(self, data, seekable)
+    def new_decoder(self, data: bytes, seekable: bool = True, slot: int = 0) -> "Decoder":
+        return Decoder(self, data, seekable, slot)
+
+    def device_count(self) -> int:
+        return self.lib.mp3_engine_device_count(self.h)
+
+    def decode_frames(self, index: "StreamIndex", f0: int, f1: int, slot: int = 0) -> Tuple[np.ndarray, int]:
+        """PCM bytes of frames [f0, f1) of an indexed stream, identical to that stretch of the linear decode
+        (mp3_decode_frames).  Returns (uint8 array, status)."""
+        want = index.pcm_bytes(f0, f1)
+        out = np.empty(max(want, 0), dtype=np.uint8)
+        got = C.c_int64(0)
+        rc = self.lib.mp3_decode_frames(self.h, slot, index.h, f0, f1, out.ctypes.data, C.byref(got))
+        if rc == MP3_ERR_DEVICE or rc == MP3_ERR_INVALID:
+            raise Mp3Error(rc, self.lib.mp3_engine_last_error(self.h).decode() or error_string(rc))
+        return out[:got.value], rc
+
+    def decode_stream_split(self, index: "StreamIndex") -> Tuple[np.ndarray, int, dict]:
+        """One stream cut into a frame range per device, ranges decoded concurrently (mp3_decode_stream_split).
+        Returns (PCM bytes view valid until the next batch/split call, status, timings)."""
+        base = C.c_void_p()
+        n = C.c_int64(0)
+        tm = BatchTimings()
+        rc = self.lib.mp3_decode_stream_split(self.h, index.h, C.byref(base), C.byref(n), C.byref(tm))
+        if rc == MP3_ERR_DEVICE or rc == MP3_ERR_INVALID:
+            raise Mp3Error(rc, self.lib.mp3_engine_last_error(self.h).decode() or error_string(rc))
+        pcm = np.ctypeslib.as_array(C.cast(base, C.POINTER(C.c_uint8)), shape=(n.value,)) if n.value else np.zeros(0, np.uint8)
+        return pcm, rc, tm.as_dict()
 
     def decode_batch(self, streams: Sequence[bytes]) -> Tuple[List[dict], np.ndarray, dict]:
         """DecodeBatch: returns (per-stream results, PCM bytes view (valid until the next call), timings)."""
@@ -509,12 +592,12 @@ class Engine:
 class Decoder:
     """Drop-in mirror of *mp3.Decoder (decode.go): Read/Seek/SampleRate/Length/... over in-memory data."""
 
-    def __init__(self, engine: Engine, data: bytes, seekable: bool = True):
+    def __init__(self, engine: Engine, data: bytes, seekable: bool = True, slot: int = 0):
         self.engine = engine
         self.lib = engine.lib
         self._data = bytes(data)  # must outlive the decoder
         err = C.c_int(0)
-        self.h = self.lib.mp3_new_decoder(engine.h, self._data, len(self._data), 1 if seekable else 0, C.byref(err))
+        self.h = self.lib.mp3_new_decoder_on(engine.h, slot, self._data, len(self._data), 1 if seekable else 0, C.byref(err))
         if not self.h:
             raise Mp3Error(err.value, "NewDecoder: " + error_string(err.value))
 
@@ -568,3 +651,103 @@ class Decoder:
     def seek_to_sample(self, s: int): self._chk(self.lib.mp3_decoder_seek_to_sample(self.h, s))
     def skip(self, delta_ns: int): self._chk(self.lib.mp3_decoder_skip(self.h, delta_ns))
     def seek_to_time(self, t_ns: int): self._chk(self.lib.mp3_decoder_seek_to_time(self.h, t_ns))
+
+
+class StreamIndex:
+    """Frame index of one stream (mp3_stream_index): what frame-range decode and the split over devices work from."""
+
+    def __init__(self, data):
+        self.lib = host_lib()
+        if isinstance(data, np.ndarray):
+            self._data = np.ascontiguousarray(data, dtype=np.uint8)
+            ptr, n = self._data.ctypes.data, self._data.size
+        else:
+            self._data = bytes(data)
+            ptr, n = C.cast(C.c_char_p(self._data), C.c_void_p), len(self._data)
+        self.h = C.c_void_p()
+        rc = self.lib.mp3_stream_index_create(ptr, n, C.byref(self.h))
+        if rc != MP3_OK:
+            self.h = None
+            raise Mp3Error(rc, "mp3_stream_index_create: " + error_string(rc))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mp3_stream_index_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def frames(self) -> int: return self.lib.mp3_stream_index_frames(self.h)
+    def sample_rate(self) -> int: return self.lib.mp3_stream_index_sample_rate(self.h)
+    def pcm_bytes(self, f0: int, f1: int) -> int: return self.lib.mp3_stream_index_pcm_bytes(self.h, f0, f1)
+
+
+# --------------------------------------------------------------------------------------------------
+# lameinfo (mirror of package lameinfo, lameinfo/lameinfo.go)
+# --------------------------------------------------------------------------------------------------
+LAME_FLAG_FRAME_COUNT, LAME_FLAG_BYTE_COUNT, LAME_FLAG_TOC, LAME_FLAG_VBR_SCALE = 1, 2, 4, 8
+LAME_DECODER_DELAY = 529
+
+
+class NoXingHeader(Mp3Error):
+    """lameinfo.ErrNoXingHeader."""
+
+
+class LameInfo:
+    """lameinfo.Info with its helper methods (lameinfo.go:20-108)."""
+
+    def __init__(self, raw: Optional[LameInfoStruct] = None, **kw):
+        self._raw = raw if raw is not None else LameInfoStruct()
+        for k, v in kw.items():  # tests build Info values directly, like the reference's do
+            if k == "lame_version":
+                self._raw.lame_version = v if isinstance(v, bytes) else v.encode()
+                self._raw.has_lame_info = 1 if v else 0
+            else:
+                setattr(self._raw, k, v)
+
+    is_xing = property(lambda s: bool(s._raw.is_xing))
+    flags = property(lambda s: s._raw.flags)
+    frame_count = property(lambda s: s._raw.frame_count)
+    byte_count = property(lambda s: s._raw.byte_count)
+    toc = property(lambda s: bytes(s._raw.toc))
+    vbr_scale = property(lambda s: s._raw.vbr_scale)
+    encoder_delay = property(lambda s: s._raw.encoder_delay)
+    encoder_padding = property(lambda s: s._raw.encoder_padding)
+
+    @property
+    def lame_version(self) -> bytes:
+        """The 9 bytes of the version field (b"" if there is no LAME tag); may end in NULs (e.g. b"LAME3.99\x00")."""
+        return C.string_at(C.addressof(self._raw) + LameInfoStruct.lame_version.offset, 9) if self._raw.has_lame_info else b""
+
+    def has_frame_count(self): return bool(self.flags & LAME_FLAG_FRAME_COUNT)
+    def has_byte_count(self): return bool(self.flags & LAME_FLAG_BYTE_COUNT)
+    def has_toc(self): return bool(self.flags & LAME_FLAG_TOC)
+    def has_vbr_scale(self): return bool(self.flags & LAME_FLAG_VBR_SCALE)
+    def has_lame_info(self): return bool(self._raw.has_lame_info)
+    def total_delay(self) -> int: return host_lib().mp3_lameinfo_total_delay(C.byref(self._raw))
+    def total_padding(self) -> int: return host_lib().mp3_lameinfo_total_padding(C.byref(self._raw))
+
+
+def _lame_result(rc: int, raw: LameInfoStruct) -> LameInfo:
+    if rc == MP3_ERR_NO_XING_HEADER:
+        raise NoXingHeader(rc, error_string(rc))
+    if rc != MP3_OK:
+        raise Mp3Error(rc, "EOF" if rc == MP3_EOF else error_string(rc))
+    return LameInfo(raw)
+
+
+def lameinfo_parse(frame: bytes) -> LameInfo:
+    """lameinfo.Parse (lameinfo.go:139-270)."""
+    raw = LameInfoStruct()
+    return _lame_result(host_lib().mp3_lameinfo_parse(bytes(frame), len(frame), C.byref(raw)), raw)
+
+
+def lameinfo_parse_from_reader(data: bytes) -> LameInfo:
+    """lameinfo.ParseFromReader (lameinfo.go:288-328) over bytes positioned at the first frame."""
+    raw = LameInfoStruct()
+    return _lame_result(host_lib().mp3_lameinfo_parse_from_reader(bytes(data), len(data), C.byref(raw)), raw)
+
+
+def is_lame_version(s: bytes) -> bool:
+    return bool(host_lib().mp3_lameinfo_is_lame_version(bytes(s), len(s)))

@@ -55,9 +55,9 @@ def stream_cases():
 
 def check_staged_cursor(pb, is16, meta, sf):
     """k_huffman's staged cursor (tiles of units, the stretch they read staged big-endian; positions outside the stretch
-    read from main_data) decodes exactly what the register-window cursor does — with the whole stretch staged, with a
-    staging area far too small (most reads take the fallback) and with odd tile sizes."""
-    for tile, cap16 in ((256, 1 << 20), (512, 1 << 20), (64, 3), (100, 40), (256, 0)):
+    read from main_data) decodes exactly what the register-window cursor does — one piece per unit as k_huffman stages
+    them, whole stretches of many units, staging areas far too small (most reads take the fallback), odd tile sizes."""
+    for tile, cap16 in ((1, 1 << 20), (1, 6), (256, 1 << 20), (64, 3), (100, 40), (256, 0)):  # tile 1 = k_huffman's per-unit pieces
         a, b, c = hostemu_lib.huffman_staged(pb.main_data, pb.units, tile, cap16)
         assert np.array_equal(a, is16) and np.array_equal(b, meta) and np.array_equal(c, sf), (tile, cap16)
 
@@ -252,7 +252,7 @@ def test_unit_logic_sweep_vs_oracle(pkg):
         is16, meta, sf = hostemu_lib.huffman(pb.main_data, pb.units)
         assert np.array_equal(is16, o["is_"]) and np.array_equal(meta & 0x3FF, o["count1"])
         assert np.array_equal(sf[:, :22], o["scalefac_l"]) and np.array_equal(sf[:, 22:61], o["scalefac_s"])
-        a, b, c = hostemu_lib.huffman_staged(pb.main_data, pb.units, 256, 1 << 20)
+        a, b, c = hostemu_lib.huffman_staged(pb.main_data, pb.units, 1, 1 << 20)
         assert np.array_equal(a, is16) and np.array_equal(b, meta) and np.array_equal(c, sf)
         a, b, c = hostemu_lib.huffman_staged(pb.main_data, pb.units, 96, 24)
         assert np.array_equal(a, is16) and np.array_equal(b, meta) and np.array_equal(c, sf)
