@@ -5,21 +5,32 @@
     python bench.py --impl reference --gpus N --steps K --warmup W
 
 A "step" is one pass of the hot path (k_huffman: scalefactors + Huffman; k_hybrid: requantise/stereo/alias + IMDCT;
-k_synth: polyphase synthesis + int16 store) over one batch of synthetic streams.  Workload (BASELINE.json configs[2]):
-4,096 synthetic 30 s MPEG-1 Layer III 128 kbps CBR stereo streams, long blocks only, per GPU (weak scaling:
-every rank decodes its own 4,096 streams; streams are independent, so there is no data-path collective).
+k_synth: polyphase synthesis + int16 store) over one batch of synthetic streams.
 
-`value`  : whole-job stereo samples/s with main data + unit descriptors already resident in HBM and PCM left in
-           HBM; timed with CUDA events on the engine's compute stream around K back-to-back passes, max over ranks.
-`e2e`    : the same metric through the C-ABI call with HOST buffers (mp3gpu_decode, include/mp3gpu.h): pinned host
-           main data + descriptors -> device, PCM -> pinned host, all inside the timed region.
+Headline workload (`value`, BASELINE.json configs[2]): 4,096 synthetic 30 s MPEG-1 Layer III 128 kbps CBR stereo streams,
+long blocks only, per GPU (weak scaling: every rank decodes its own 4,096 streams; streams are independent, so there is
+no data-path collective).
+
+`value`   : whole-job stereo samples/s with main data + unit descriptors already resident in HBM and PCM left in
+            HBM; timed with CUDA events on the engine's compute stream around K back-to-back passes, max over ranks.
+`e2e`     : the same metric through the product entry point, mp3_decode_batch (include/mp3host.h): raw .mp3 bytes in
+            host memory -> host parse (tags, headers, side info, reservoir) -> pinned arenas -> H2D -> kernels -> D2H ->
+            PCM in pinned host memory, everything inside the timed region.  At N > 1 it is ONE process (rank 0) driving
+            one multi-device engine over all N GPUs (streams dealt to devices by bytes), the same streams per GPU at
+            every N; `frac_of_copy_ceiling` compares it with plain concurrent cudaMemcpyAsync D2H of the same PCM bytes.
 `roofline`: the dominant kernel against its bound (FP32 FMA issue or HBM), see DESIGN.md for the per-unit figures.
 `cpu_baseline`: the oracle (C restatement of go-mp3; no Go toolchain in the image) on all host cores, bounded sample.
-Inputs (2 GB main data + 0.6 GB descriptors) and outputs (21.7 GB PCM) per pass are far larger than the 126 MB L2,
-so no explicit L2 flush is needed between timed iterations.
+`cfg4`    : BASELINE.json configs[3] — 8,192 synthetic VBR streams per GPU (N = 8: the 65,536-stream batch) with
+            long/short/mixed blocks, MS + intensity stereo, deep reservoir, 5 % LSF: its own value, per-kernel times,
+            parity against the oracle, same-box CPU baseline and e2e.
+`cfg5`    : BASELINE.json configs[4] — one 413,438-frame 320 kbps stream cut into N frame ranges decoded concurrently on
+            the N GPUs (mp3_decode_stream_split), PCM SHA-256 equal to the single-device linear decode, and 1,000 seeded
+            SeekToTime + Read on the drop-in Decoder, each compared with the oracle Decoder doing the same seek.
+Inputs and outputs per pass are far larger than the 126 MB L2, so no explicit L2 flush is needed between iterations.
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -46,6 +57,7 @@ UNIT = "Msamples/s"
 #   picks, per kernel, whichever of HBM and FP32 it sits closer to.
 FLOPS_REFERENCE = {"k1_huffman": 0.0, "k_hybrid": 2472.0 + 43200.0, "k_synth": 92160.0}
 FLOPS = {"k1_huffman": 0.0, "k_hybrid": 2472.0 + 32 * 258.0, "k_synth": 18 * (289.0 + 1024.0 + 2.0)}
+FULL_WAVE_UNITS = 2 * 2097152  # granule-channels of one full kernel wave (default wave_granules)
 
 
 def kernel_bytes(main_bytes_per_unit):
@@ -73,7 +85,6 @@ class ClockSampler:
         self.gpu_id = gpu_id
         self.rows = []
         self.stamps = []
-        self.stop_flag = False
         self.proc = None
 
     def start(self):
@@ -135,6 +146,34 @@ def make_workload(synth, first_stream, n_streams, n_frames, threads, kind):
     return synth.batch(cfgs, threads)
 
 
+def make_long_stream(synth, n_frames, threads):
+    """BASELINE.json configs[4]: ONE 320 kbps stream of n_frames frames.  Synthesised as segments on all host threads and
+    joined: every segment is a valid stream that starts with main_data_begin = 0, so the join is a valid stream whose
+    reservoir restarts at the seams (as a real encoder's does after a flush)."""
+    parts = max(1, min(threads, 32, n_frames // 2048))
+    cuts = [n_frames * i // parts for i in range(parts + 1)]
+    cfgs = []
+    for i in range(parts):
+        c = synth.cfg5(cuts[i + 1] - cuts[i])
+        c.seed += 7919 * i
+        cfgs.append(c)
+    buf, offs, lens = synth.batch(cfgs, threads)
+    out = np.empty(sum(lens), dtype=np.uint8)
+    o = 0
+    for a, n in zip(offs, lens):
+        out[o:o + n] = buf[a:a + n]
+        o += n
+    return out
+
+
+def workload_name(kind, streams, frames):
+    if kind == "cfg3":
+        return (f"{streams} synthetic 30 s MPEG-1 L3 128 kbps CBR stereo streams per GPU, long blocks only "
+                f"(BASELINE.json configs[2]; {frames} frames each)")
+    return (f"{streams} synthetic VBR streams per GPU with long/short/mixed blocks, MS+intensity stereo, deep "
+            f"reservoir, 5% LSF (BASELINE.json configs[3]; {frames} frames each)")
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle (port of the reference's algorithm; Go is not installed) on all host cores."""
     if rank != 0:
@@ -157,20 +196,175 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_tot / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "streams_per_gpu": args.streams, "frames_per_stream": args.frames,
-                       "sample": sample},
+            "config": {"workload": workload_name(args.workload, args.streams, args.frames), "streams_per_gpu": args.streams,
+                       "frames_per_stream": args.frames, "sample": sample},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def workload_name(args):
-    if args.workload == "cfg3":
-        return (f"{args.streams} synthetic 30 s MPEG-1 L3 128 kbps CBR stereo streams per GPU, long blocks only "
-                f"(BASELINE.json configs[2]; {args.frames} frames each)")
-    return (f"{args.streams} synthetic VBR streams per GPU with long/short/mixed blocks, MS+intensity stereo, deep "
-            f"reservoir, 5% LSF (BASELINE.json configs[3]; {args.frames} frames each)")
+# ------------------------------------------------------------------------------------------------------------------
+# One batch workload, device-resident: K timed passes, per-kernel times, parity against the oracle, CPU baseline
+# ------------------------------------------------------------------------------------------------------------------
+class Dist:
+    def __init__(self, world, dev):
+        self.world, self.dev = world, dev
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
+    def max(self, x):
+        if self.world == 1:
+            return x
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([x], dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def measure_resident(pkg, synth, D, eng, kind, streams, frames, first_stream, threads, steps, warmup, rank, parity_streams,
+                     cpu_baseline_streams, sampler=None):
+    """Synthesise + host-parse + stage in HBM, then time `steps` passes.  Returns (result dict, StreamBuffer)."""
+    import torch
+    t0 = time.time()
+    buf, offs, lens = make_workload(synth, first_stream, streams, frames, threads, kind)
+    sb = pkg.StreamBuffer(buf, offs, lens)
+    t1 = time.time()
+    pb = pkg.parse_streams(sb, threads)
+    t2 = time.time()
+    assert all(s["status"] == 0 and s["frames"] == frames for s in pb.streams), "synthetic stream failed to parse"
+    n_gr = pb.n_granules
+    n_units_valid = int(((pb.units["w2"] >> 25) & 1).sum())
+    samples_per_step = n_gr * 576  # stereo samples
+    d_main = torch.from_numpy(pb.main_data).to(D.dev)
+    d_units = torch.from_numpy(pb.units.view(np.uint8)).to(D.dev)
+    d_pcm = torch.empty(n_gr * 1152, dtype=torch.int16, device=D.dev)
+    torch.cuda.synchronize()
+
+    def one_pass(sync):
+        eng.decode_device(d_main.data_ptr(), pb.main_data_len, d_units.data_ptr(), n_gr, d_pcm.data_ptr(), sync=sync)
+
+    for _ in range(max(warmup, 3)):
+        one_pass(True)
+    # ---- timed region: K passes, CUDA events on the compute stream ------------------------------------------------
+    D.barrier()
+    torch.cuda.synchronize()
+    eng.synchronize()
+    t_timed0 = time.time()
+    eng.event_record(0)
+    for _ in range(steps):
+        one_pass(False)
+    eng.event_record(1)
+    total_ms = eng.event_elapsed_ms(0, 1)
+    eng.synchronize()
+    torch.cuda.synchronize()
+    # per-kernel event times: K more passes, read back after each (kept outside the event pair above so that the
+    # read-back synchronisation never sits inside the headline number)
+    ksum = {"k1_huffman": 0.0, "k_hybrid": 0.0, "k_synth": 0.0}
+    launches = 0
+    for _ in range(steps):
+        one_pass(True)
+        t = eng.timings()
+        for k in ksum:
+            ksum[k] += t[k + "_ms"]
+        launches = t["launches"]
+    if sampler is not None:
+        # the clock samples must come from the loaded GPU: keep decoding (outside the event pair) until nvidia-smi has
+        # delivered a few rows since the timed region began
+        while sampler.proc is not None and sampler.samples_since(t_timed0) < 3 and time.time() - t_timed0 < 4.0:
+            one_pass(True)
+            eng.synchronize()
+        sampler.keep_since(t_timed0)
+    D.barrier()
+    total_ms = D.max(total_ms)
+    ms_per_step = total_ms / steps
+    res = {"value": samples_per_step * D.world / (ms_per_step * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_per_step, "steps": steps,
+           "streams_per_gpu": streams, "frames_per_stream": frames, "granules_per_gpu": int(n_gr),
+           "granule_channels_per_gpu": n_units_valid, "main_data_bytes_per_gpu": int(pb.main_data_len),
+           "pcm_bytes_per_gpu": int(n_gr * 2304), "gpu_launches": int(launches * steps),
+           "setup_s": {"synthesise": t1 - t0, "host_parse": t2 - t1}}
+    res["_ksum"], res["_launches"], res["_n_units_valid"] = ksum, launches, n_units_valid
+    res["_main_bytes_per_unit"] = pb.main_data_len / max(n_units_valid, 1)
+
+    # ---- parity against the oracle on a few streams of this rank (checker only) -----------------------------------
+    if rank == 0:
+        import oracle
+        worst, fracs, checked = 0, [], []
+        for i in parity_streams:
+            st = pb.streams[i]
+            ref, err = oracle.OracleDecoder(sb.stream(i)).read_all()
+            ref = np.frombuffer(ref, dtype=np.int16)
+            o = st["pcm_offset"] // 2
+            assert st["pcm_bytes"] == ref.size * 2, "PCM length differs from the oracle's"
+            got = d_pcm[o:o + ref.size].cpu().numpy()
+            diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+            worst = max(worst, int(diff.max()))
+            fracs.append(float((diff == 0).mean()))
+            checked.append(int(i))
+        res["parity"] = {"streams_checked": checked, "max_abs_diff_lsb": worst, "exact_fraction": min(fracs), "tolerance_lsb": 1,
+                         "oracle": "oracle/mp3_oracle.c (parity unpinned: the reference holds no PCM vectors and cannot be run here)"}
+        if cpu_baseline_streams:
+            cores = os.cpu_count() or 1
+            n_s = min(streams, cpu_baseline_streams)
+            ss = [sb.stream(i) for i in range(n_s)]
+            secs, pcm_bytes, _ = oracle.decode_streams_mt(ss, cores)
+            res["cpu_baseline"] = {"value": sum(pcm_bytes) / 4 / secs / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"first {n_s} of the {streams} streams ({frames} frames each), one thread per "
+                                             f"stream on {cores} threads, {secs:.1f} s wall"}
+    del d_main, d_units, d_pcm
+    torch.cuda.empty_cache()
+    return res, sb
+
+
+def kernel_table(res, hbm_peak, fp32_peak):
+    ksum, launches, n_units, steps = res.pop("_ksum"), res.pop("_launches"), res.pop("_n_units_valid"), res["steps"]
+    kb = kernel_bytes(res.pop("_main_bytes_per_unit"))
+    step_kernel_ms = sum(ksum.values()) / steps
+    kernels = {}
+    for k, ms_sum in ksum.items():
+        ms = ms_sum / steps                          # all waves of one pass
+        gbs = kb[k] * n_units / (ms * 1e-3) / 1e9
+        tfs = FLOPS[k] * n_units / (ms * 1e-3) / 1e12
+        kernels[k] = {"ms_per_step": ms, "launches_per_step": launches // 3, "share": ms / step_kernel_ms,
+                      "alg_bytes_per_unit": kb[k], "alg_flops_per_unit": FLOPS[k],
+                      "reference_direct_form_flops_per_unit": FLOPS_REFERENCE[k], "hbm_gbs": gbs,
+                      "hbm_frac": gbs / hbm_peak, "fp32_tflops": tfs, "fp32_frac": tfs / fp32_peak}
+    return kernels
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# e2e: the product entry point, one process, one engine over all N devices
+# ------------------------------------------------------------------------------------------------------------------
+def measure_e2e(pkg, heng, sb, n_streams_total, steps, ceiling):
+    sub = pkg.StreamBuffer(sb.buf, sb.offsets[:n_streams_total], sb.lens[:n_streams_total])
+    heng.decode_batch(sub)  # first call allocates the pinned arenas
+    heng.decode_batch(sub)
+    tot, last = 0.0, None
+    for _ in range(steps):
+        res, pcm, tm = heng.decode_batch(sub)
+        tot += tm["total_s"]
+        last = (res, pcm, tm)
+    res, pcm, tm = last
+    assert all(r["status"] == 0 for r in res)
+    pcm_bytes = sum(r["pcm_bytes"] for r in res)
+    s = tot / steps
+    n_dev = heng.device_count()
+    out = {"value": pcm_bytes / 4 / s / 1e6, "unit": UNIT, "ms_per_step": s * 1e3, "steps": steps,
+           "streams_per_gpu": n_streams_total // n_dev, "devices": n_dev,
+           "h2d_bytes_per_step": int(tm["main_data_bytes"] + tm["n_granules"] * 64), "d2h_bytes_per_step": int(pcm_bytes),
+           "input_bytes_per_step": int(sum(sub.lens)),
+           "api": "mp3_decode_batch (include/mp3host.h): raw .mp3 bytes in host memory -> PCM in pinned host memory; one "
+                  "process, one engine, streams dealt to the devices by bytes",
+           "last_call": {"parse_s": tm["parse_s"], "gather_s": tm["gather_s"], "device_s": tm["device_s"], "total_s": tm["total_s"]}}
+    if ceiling:
+        out["copy_ceiling"] = ceiling
+        out["d2h_gbs"] = pcm_bytes / s / 1e9
+        out["frac_of_copy_ceiling"] = (pcm_bytes / s / 1e9) / ceiling["aggregate_gbs"]
+    return out, (res, pcm)
 
 
 def run_ours(args, rank, world, local_rank):
@@ -185,179 +379,66 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    D = Dist(world, dev)
     cores = os.cpu_count() or 1
     threads = max(1, cores // world)
-
-    # ---- workload: synthesise, host-parse (tags/headers/side info/reservoir), stage in HBM -------------------------
-    t0 = time.time()
-    buf, offs, lens = make_workload(synth, rank * args.streams, args.streams, args.frames, threads, args.workload)
-    sb = pkg.StreamBuffer(buf, offs, lens)
-    t1 = time.time()
-    pb = pkg.parse_streams(sb, threads)
-    t2 = time.time()
-    assert all(s["status"] == 0 and s["frames"] == args.frames for s in pb.streams), "synthetic stream failed to parse"
-    n_gr = pb.n_granules
-    n_units_valid = int(((pb.units["w2"] >> 25) & 1).sum())
-    samples_per_step = n_gr * 576  # stereo samples
-    d_main = torch.from_numpy(pb.main_data).to(dev)
-    d_units = torch.from_numpy(pb.units.view(np.uint8)).to(dev)
-    d_pcm = torch.empty(n_gr * 1152, dtype=torch.int16, device=dev)
-    torch.cuda.synchronize()
     eng = pkg.GpuEngine(local_rank, wave_granules=args.wave)
     info = eng.device_info()
-
-    def one_pass(sync):
-        eng.decode_device(d_main.data_ptr(), pb.main_data_len, d_units.data_ptr(), n_gr, d_pcm.data_ptr(), sync=sync)
-
     uuid = str(torch.cuda.get_device_properties(dev).uuid)
     sampler = ClockSampler(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
     sampler.start()  # started here: nvidia-smi takes about a second to deliver its first row; rows before the timed region are dropped
-    for _ in range(max(args.warmup, 3)):
-        one_pass(True)
+
+    # ---- headline: configs[2] (or --workload cfg4), device-resident ------------------------------------------------
+    main, sb_main = measure_resident(pkg, synth, D, eng, args.workload, args.streams, args.frames, rank * args.streams, threads,
+                                     args.steps, args.warmup, rank, sorted({0, args.streams // 2, args.streams - 1}),
+                                     0 if args.no_cpu_baseline else max(cores * 4, 16), sampler)
+    clocks = sampler.stop()
     fp32_peak = eng.fp32_peak_tflops()
 
-    # ---- timed region: K passes, CUDA events on the compute stream ------------------------------------------------
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    eng.synchronize()
-    t_timed0 = time.time()
-    ksum = {"k1_huffman": 0.0, "k_hybrid": 0.0, "k_synth": 0.0}
-    launches = 0
-    eng.event_record(0)
-    for _ in range(args.steps):
-        one_pass(False)
-    eng.event_record(1)
-    total_ms = eng.event_elapsed_ms(0, 1)
-    eng.synchronize()
-    torch.cuda.synchronize()
-    # per-kernel event times: K more passes, read back after each (kept outside the event pair above so that the
-    # read-back synchronisation never sits inside the headline number)
-    for _ in range(args.steps):
-        one_pass(True)
-        t = eng.timings()
-        for k in ksum:
-            ksum[k] += t[k + "_ms"]
-        launches = t["launches"]
-    # the clock samples must come from the loaded GPU: keep decoding (outside the event pair) until nvidia-smi has
-    # delivered a few rows since the timed region began
-    while sampler.proc is not None and sampler.samples_since(t_timed0) < 3 and time.time() - t_timed0 < 4.0:
-        one_pass(True)
-        eng.synchronize()
-    sampler.keep_since(t_timed0)
-    clocks = sampler.stop()
-    if world > 1:
-        dist.barrier()
-        tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_ms = float(tt.item())
-    ms_per_step = total_ms / args.steps
-    value = samples_per_step * world / (ms_per_step * 1e-3) / 1e6
+    # ---- configs[3]: 8,192 VBR mixed-feature streams per GPU -------------------------------------------------------
+    cfg4, sb_cfg4 = None, None
+    if not args.no_cfg4 and args.workload == "cfg3":
+        # streams 19 + 20 k are LSF (k % 3 == 1: mono); every non-LSF stream has short, mixed and long blocks and joint stereo
+        par = sorted({0, 3, 19, 39, args.cfg4_streams - 1} & set(range(args.cfg4_streams)))
+        cfg4, sb_cfg4 = measure_resident(pkg, synth, D, eng, "cfg4", args.cfg4_streams, args.frames, rank * args.cfg4_streams, threads,
+                                         max(3, args.steps // 2), 3, rank, par, 0 if args.no_cpu_baseline else max(cores * 4, 16))
+    eng.close()
+    D.barrier()
 
-    # ---- parity spot check against the oracle on the first stream of this rank (checker only) ---------------------
-    parity = None
+    # ---- rank 0 alone from here on: the product API (one process, one engine over all N devices) -------------------
+    e2e = e2e_cfg4 = cfg5 = None
     if rank == 0:
-        import oracle
-        worst, fracs, checked = 0, [], []
-        for i in sorted({0, args.streams // 2, args.streams - 1}):
-            st = pb.streams[i]
-            ref, err = oracle.OracleDecoder(sb.stream(i)).read_all()
-            ref = np.frombuffer(ref, dtype=np.int16)
-            o = st["pcm_offset"] // 2
-            got = d_pcm[o:o + ref.size].cpu().numpy()
-            diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
-            worst = max(worst, int(diff.max()))
-            fracs.append(float((diff == 0).mean()))
-            checked.append(i)
-        ref0, _ = oracle.OracleDecoder(sb.stream(0)).read_all()
-        ref = np.frombuffer(ref0, dtype=np.int16)
-        parity = {"streams_checked": checked, "max_abs_diff_lsb": worst, "exact_fraction": min(fracs),
-                  "tolerance_lsb": 1}
-
-    # ---- e2e: host buffers through the C ABI (pinned; H2D + kernels + D2H inside the timed region) ----------------
-    e2e = None
-    # Pinned host memory is bounded to ~48 GB over all ranks of the node: at N = 1 and 2 every rank runs its whole batch
-    # through the host API; beyond that a stream-ordered prefix of the batch (per-GPU e2e is PCIe-bound and does not depend
-    # on the batch size).  The prefix is a whole number of streams, so it is a self-contained submission.
-    e2e_streams = args.streams
-    per_stream_pcm = (n_gr * 2304) // max(args.streams, 1)
-    budget = int(48e9) // world
-    if per_stream_pcm * e2e_streams > budget:
-        e2e_streams = max(1, budget // max(per_stream_pcm, 1))
-    e2e_gr = sum(s["pcm_bytes"] for s in pb.streams[:e2e_streams]) // 2304
-    full_gr, full_main_len = n_gr, pb.main_data_len
-    if e2e_streams < args.streams:
-        u = pb.units[: e2e_gr * 2]
-        valid = (u["w2"] >> 25) & 1 == 1
-        main_end = int(((u["bit_start"][valid].astype(np.int64) + u["buf_end_rel"][valid]).max() + 7) // 8)
-        n_gr, main_len_e2e = e2e_gr, min(main_end, pb.main_data_len)
-    else:
-        main_len_e2e = pb.main_data_len
-    h2d = main_len_e2e + n_gr * 2 * 32
-    d2h = n_gr * 2304
-    del d_pcm
-    torch.cuda.empty_cache()
-    numa_node = eng.bind_host_to_gpu_numa_node() if world > 1 else None  # keep each rank's pinned buffers next to its GPU
-    try:
-        p_main = eng.host_alloc(main_len_e2e + 64)
-        p_units = eng.host_alloc(n_gr * 2 * 32)
-        p_pcm = eng.host_alloc(d2h)
-        C.memset(p_main, 0, main_len_e2e + 64)
-        C.memmove(p_main, pb.main_data.ctypes.data, main_len_e2e)
-        C.memmove(p_units, pb.units.ctypes.data, n_gr * 2 * 32)
-        e2e_steps = max(1, min(args.steps, 3))
-        eng.decode_host(p_main, main_len_e2e, p_units, n_gr, p_pcm)  # warm-up (allocates the staging ring)
-        if world > 1:
-            dist.barrier()
-        tw = time.perf_counter()
-        for _ in range(e2e_steps):
-            eng.decode_host(p_main, main_len_e2e, p_units, n_gr, p_pcm)
-        e2e_s = (time.perf_counter() - tw) / e2e_steps
-        e2e_t = eng.timings()
-        if world > 1:
-            tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e_s = float(tt.item())
-        if rank == 0 and parity is not None:
-            got = np.ctypeslib.as_array(C.cast(p_pcm, C.POINTER(C.c_int16)), shape=(ref.size,))
-            parity["e2e_max_abs_diff_lsb"] = int(np.abs(got.astype(np.int32) - ref.astype(np.int32)).max())
-        e2e = {"value": n_gr * 576 * world / e2e_s / 1e6, "unit": UNIT, "streams_per_gpu": int(e2e_streams), "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-               "api": "mp3gpu_decode (include/mp3gpu.h), pinned host buffers", "numa_node": numa_node,
-               "h2d_ms": e2e_t["h2d_ms"], "d2h_ms": e2e_t["d2h_ms"]}
-        for p in (p_main, p_units, p_pcm):
-            eng.host_free(p)
-    except MemoryError as ex:
-        e2e = {"value": None, "unit": UNIT, "error": str(ex)}
-    n_gr = full_gr
-
-    # ---- informational: DecodeBatch from raw .mp3 bytes (host parse + gather + device), rank 0 at N = 1 ------------
-    decode_batch = None
-    if rank == 0 and world == 1 and not args.no_decode_batch:
+        e2e_streams = min(args.e2e_streams, args.streams)
+        heng = pkg.Engine(devices=list(range(world)), host_threads=cores)
+        # every rank synthesised its own streams; rank 0's are re-used for all devices (stream content does not matter to
+        # the copy-bound path, and per-stream results are compared with rank 0's device-resident PCM parity above)
+        def replicate(sb, n_per_dev):
+            offs = list(sb.offsets[:n_per_dev]) * world
+            lens = list(sb.lens[:n_per_dev]) * world
+            return pkg.StreamBuffer(sb.buf, offs, lens)
         try:
-            heng = pkg.Engine(local_rank, host_threads=cores)
-            n_b = min(args.streams, 1024)  # bounded: the first 1,024 streams
-            sub = pkg.StreamBuffer(buf, offs[:n_b], lens[:n_b])
-            heng.decode_batch(sub)            # first call allocates the pinned arenas
-            res_b, pcm_b, tm = heng.decode_batch(sub)
-            decode_batch = {"streams": n_b, "value": tm["pcm_bytes"] / 4 / tm["total_s"] / 1e6, "unit": UNIT,
-                            "parse_s": tm["parse_s"], "gather_s": tm["gather_s"], "device_s": tm["device_s"],
-                            "host_threads": cores, "api": "mp3_decode_batch (include/mp3host.h): raw .mp3 bytes in, PCM out"}
-            heng.close()
-        except Exception as ex:  # informational only
-            decode_batch = {"error": str(ex)}
-
-    # ---- CPU baseline (rank 0, N = 1): oracle on all host cores over a bounded sample -----------------------------
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        import oracle
-        n_s = min(args.streams, max(cores * 4, 16))
-        streams = [sb.stream(i) for i in range(n_s)]
-        secs, pcm_bytes, _ = oracle.decode_streams_mt(streams, cores)
-        cpu_baseline = {"value": sum(pcm_bytes) / 4 / secs / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"first {n_s} of the {args.streams} streams ({args.frames} frames each), one thread per "
-                                  f"stream on {cores} threads, {secs:.1f} s wall"}
-
+            per_dev_pcm = sum(sb_main.lens[:e2e_streams]) * 11  # PCM is about 11 x the mp3 bytes at 128 kbps
+            ceiling = heng.measure_d2h_ceiling(min(per_dev_pcm, 4 << 30), 3)
+            e2e, (res_e, pcm_e) = measure_e2e(pkg, heng, replicate(sb_main, e2e_streams), e2e_streams * world, args.steps, ceiling)
+            import oracle
+            ref, err = oracle.OracleDecoder(sb_main.stream(0)).read_all()
+            got = pcm_e[res_e[0]["pcm_offset"]:res_e[0]["pcm_offset"] + res_e[0]["pcm_bytes"]].view(np.int16)
+            e2e["parity_stream0_max_abs_diff_lsb"] = int(np.abs(got.astype(np.int32) - np.frombuffer(ref, np.int16).astype(np.int32)).max())
+            if world > 1:  # T6: a stream decodes to the same PCM on whichever device it lands
+                d0 = hashlib.sha256(pcm_e[res_e[0]["pcm_offset"]:res_e[0]["pcm_offset"] + res_e[0]["pcm_bytes"]].tobytes()).hexdigest()
+                k = e2e_streams * (world - 1)
+                dk = hashlib.sha256(pcm_e[res_e[k]["pcm_offset"]:res_e[k]["pcm_offset"] + res_e[k]["pcm_bytes"]].tobytes()).hexdigest()
+                e2e["same_stream_same_pcm_on_first_and_last_device"] = d0 == dk
+            if cfg4 is not None:
+                n4 = min(args.e2e_streams, args.cfg4_streams)
+                e2e_cfg4, _ = measure_e2e(pkg, heng, replicate(sb_cfg4, n4), n4 * world, max(3, args.steps // 2), ceiling)
+        except MemoryError as ex:
+            e2e = {"value": None, "unit": UNIT, "error": str(ex)}
+        # ---- configs[4]: one long stream, N frame ranges, SeekToTime ------------------------------------------------
+        if not args.no_cfg5:
+            cfg5 = run_cfg5(pkg, synth, heng, args, cores, world)
+        heng.close()
+    D.barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -372,27 +453,20 @@ def run_ours(args, rank, world, local_rank):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    kb = kernel_bytes(pb.main_data_len / max(n_units_valid, 1))
     traffic = {}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             traffic = json.load(f)
     except OSError:
         pass
-    kernels = {}
-    step_kernel_ms = sum(ksum.values()) / args.steps
-    for k, ms_sum in ksum.items():
-        ms = ms_sum / args.steps                     # all waves of one pass
-        per_launch_ms = ms / max(launches // 3, 1)   # one launch = one wave of this kernel
-        gbs = kb[k] * n_units_valid / (ms * 1e-3) / 1e9
-        tfs = FLOPS[k] * n_units_valid / (ms * 1e-3) / 1e12
-        kernels[k] = {"ms_per_step": ms, "ms_per_launch": per_launch_ms, "share": ms / step_kernel_ms,
-                      "alg_bytes_per_unit": kb[k], "alg_flops_per_unit": FLOPS[k],
-                      "reference_direct_form_flops_per_unit": FLOPS_REFERENCE[k], "hbm_gbs": gbs,
-                      "hbm_frac": gbs / hbm_peak, "fp32_tflops": tfs, "fp32_frac": tfs / fp32_peak}
+    n_units_main = main["granule_channels_per_gpu"]
+    kernels = kernel_table(main, hbm_peak, fp32_peak)
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
     kd = kernels[dom]
-    units_per_launch = n_units_valid / max(launches // 3, 1)
+    # per LAUNCH, like `traffic`: one full wave of 2,097,152 granules (the last wave of a pass is partial; the pass time is
+    # apportioned by units, which is exact for kernels whose time is proportional to the units they process)
+    units_per_launch = min(FULL_WAVE_UNITS, n_units_main)
+    ms_per_launch = kd["ms_per_step"] * units_per_launch / n_units_main
     if kd["fp32_frac"] >= kd["hbm_frac"]:
         roofline = {"kernel": dom, "bound": "fp32", "achieved": kd["fp32_tflops"], "peak": fp32_peak, "unit": "TFLOP/s",
                     "frac": kd["fp32_frac"],
@@ -403,31 +477,132 @@ def run_ours(args, rank, world, local_rank):
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kd["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s",
                     "frac": kd["hbm_frac"], "peak_source": hbm_src}
     roofline["units_per_launch"] = units_per_launch
-    roofline["traffic"] = traffic.get(dom)
+    roofline["ms_per_launch"] = ms_per_launch
+    roofline["algorithmic_bytes_per_launch"] = kd["alg_bytes_per_unit"] * units_per_launch
+    tr = traffic.get(dom)
+    roofline["traffic"] = tr["bytes"] if isinstance(tr, dict) else tr
+    roofline["traffic_source"] = (tr.get("source") if isinstance(tr, dict) else
+                                  "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one full-wave launch (ncu --set full)")
     roofline["also"] = {"hbm_frac": kd["hbm_frac"], "fp32_frac": kd["fp32_frac"], "hbm_peak_gbs": hbm_peak,
                         "fp32_peak_tflops": fp32_peak}
     # whole-pipeline view: algorithmic bytes of the fused minimum (bits + descriptor in, PCM out) and all flops
-    pipe_bytes = (pb.main_data_len + n_gr * 2 * 32 + n_gr * 2304)
-    pipe_flops = sum(FLOPS.values()) * n_units_valid
-    pipeline = {"hbm_gbs_fused_minimum": pipe_bytes / (ms_per_step * 1e-3) / 1e9,
-                "fp32_tflops": pipe_flops / (ms_per_step * 1e-3) / 1e12,
-                "fp32_frac": pipe_flops / (ms_per_step * 1e-3) / 1e12 / fp32_peak}
+    pipe_bytes = main["main_data_bytes_per_gpu"] + main["granules_per_gpu"] * 2 * 32 + main["pcm_bytes_per_gpu"]
+    pipe_flops = sum(FLOPS.values()) * n_units_main
+    pipeline = {"hbm_gbs_fused_minimum": pipe_bytes / (main["ms_per_step"] * 1e-3) / 1e9,
+                "fp32_tflops": pipe_flops / (main["ms_per_step"] * 1e-3) / 1e12,
+                "fp32_frac": pipe_flops / (main["ms_per_step"] * 1e-3) / 1e12 / fp32_peak}
+    if cfg4 is not None:
+        cfg4["kernels"] = kernel_table(cfg4, hbm_peak, fp32_peak)
+        cfg4["workload"] = workload_name("cfg4", args.cfg4_streams, args.frames)
+        cfg4["e2e"] = e2e_cfg4
+        if cfg4.get("cpu_baseline"):
+            cfg4["x_cpu_baseline_device_resident"] = cfg4["value"] / cfg4["cpu_baseline"]["value"]
+            if e2e_cfg4 and e2e_cfg4.get("value"):
+                cfg4["x_cpu_baseline_e2e"] = e2e_cfg4["value"] / cfg4["cpu_baseline"]["value"]
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+    line = {"metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(args), "streams_per_gpu": args.streams, "frames_per_stream": args.frames,
-                       "granules_per_gpu": int(n_gr), "granule_channels_per_gpu": n_units_valid,
-                       "main_data_bytes_per_gpu": int(pb.main_data_len), "pcm_bytes_per_gpu": int(n_gr * 2304),
+            "config": {"workload": workload_name(args.workload, args.streams, args.frames), "streams_per_gpu": args.streams,
+                       "frames_per_stream": args.frames, "granules_per_gpu": main["granules_per_gpu"],
+                       "granule_channels_per_gpu": n_units_main, "main_data_bytes_per_gpu": main["main_data_bytes_per_gpu"],
+                       "pcm_bytes_per_gpu": main["pcm_bytes_per_gpu"],
                        "l2": "inputs (main data + descriptors) and outputs per pass are >> 126 MB L2; no explicit flush",
                        "parallelism": f"streams sharded over {world} GPU(s), no collective", "wave_granules": args.wave or 2097152,
-                       "device": info, "setup_s": {"synthesise": t1 - t0, "host_parse": t2 - t1}},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches * args.steps), "roofline": roofline,
-            "kernels": kernels, "pipeline": pipeline, "cpu_baseline": cpu_baseline, "parity": parity,
-            "decode_batch_from_mp3_bytes": decode_batch}
+                       "device": info, "setup_s": main["setup_s"]},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": main["gpu_launches"], "roofline": roofline,
+            "kernels": kernels, "pipeline": pipeline, "cpu_baseline": main.get("cpu_baseline"), "parity": main.get("parity"),
+            "cfg4": cfg4, "cfg5": cfg5}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_cfg5(pkg, synth, heng, args, cores, world):
+    """BASELINE.json configs[4]: one long 320 kbps stream split at frame boundaries over the engine's devices, plus random
+    access through the drop-in Decoder (SeekToTime, decode.go:320-341)."""
+    import oracle
+    t0 = time.time()
+    data = make_long_stream(synth, args.cfg5_frames, cores)
+    t1 = time.time()
+    ix = pkg.StreamIndex(data)
+    t2 = time.time()
+    frames = ix.frames()
+    out = {"workload": f"one synthetic {frames}-frame 320 kbps joint-stereo stream with long/short/mixed blocks and deep reservoir "
+                       f"(BASELINE.json configs[4]), cut into {world} frame range(s), one per GPU",
+           "frames": int(frames), "mp3_bytes": int(data.size), "setup_s": {"synthesise": t1 - t0, "index": t2 - t1}}
+    # -- linear decode on one device = the reference result of the split
+    one = pkg.Engine(device=0, host_threads=cores) if world > 1 else heng
+    pcm, rc, tm = one.decode_stream_split(ix)
+    assert rc == 0 and len(pcm) == frames * 4608, (rc, len(pcm))
+    sha_linear = hashlib.sha256(pcm).hexdigest()
+    lin_s = []
+    for _ in range(2):
+        pcm, rc, tm = one.decode_stream_split(ix)
+        lin_s.append(tm["total_s"])
+    # oracle parity on three stretches of the stream (the oracle needs ~45 s for the whole of it): a sub-stream starting 40
+    # frames earlier converges to the linear decode's state (reservoir <= 511 bytes back, overlap/V history two granules)
+    worst, fracs = 0, []
+    for f0 in (0, frames // 2, frames - 260):
+        lead = min(f0, 40)
+        a = ix_frame_offset(pkg, data, ix, f0 - lead)
+        b = ix_frame_offset(pkg, data, ix, f0 + 256)
+        ref, err = oracle.OracleDecoder(data[a:b].tobytes()).read_all()
+        ref = np.frombuffer(ref, np.int16)[lead * 2304:]
+        got = np.frombuffer(pcm[f0 * 4608:(f0 + 256) * 4608].tobytes(), np.int16)
+        d = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+        worst = max(worst, int(d.max()))
+        fracs.append(float((d == 0).mean()))
+    out["parity"] = {"frames_checked": 3 * 256, "max_abs_diff_lsb": worst, "exact_fraction": min(fracs), "tolerance_lsb": 1}
+    if world > 1:
+        one.close()
+        pcm, rc, tm = heng.decode_stream_split(ix)  # warm-up: arenas
+        split_s = []
+        for _ in range(3):
+            pcm, rc, tm = heng.decode_stream_split(ix)
+            split_s.append(tm["total_s"])
+        assert rc == 0
+        out["split_sha256_equals_linear"] = hashlib.sha256(pcm).hexdigest() == sha_linear
+    else:
+        split_s = lin_s
+        out["split_sha256_equals_linear"] = True
+    s = min(split_s)
+    out.update({"pcm_sha256": sha_linear, "value": frames * 1152 / s / 1e6, "unit": UNIT, "ms_per_decode": s * 1e3,
+                "linear_one_device_ms": min(lin_s) * 1e3, "devices": world,
+                "api": "mp3_decode_stream_split (include/mp3host.h): per range host parse (lead-in + halo) -> device -> pinned host"})
+    # -- 1,000 seeded SeekToTime + Read(4608) on the drop-in Decoder, decoders spread over the device slots
+    raw = data.tobytes()
+    decs = [heng.new_decoder(raw, slot=k) for k in range(world)]
+    ref_dec = oracle.OracleDecoder(raw)
+    dur = decs[0].duration_ns()
+    rng = np.random.default_rng(7)
+    targets = rng.integers(0, dur, args.cfg5_seeks)
+    t_seek, worst, n_exact, n_bytes = 0.0, 0, 0, 0
+    for k, t in enumerate(targets):
+        d = decs[k % world]
+        ta = time.perf_counter()
+        d.seek_to_time(int(t))
+        got, err = d.read(4608)
+        t_seek += time.perf_counter() - ta
+        ref_dec.seek_to_time(int(t))
+        want, err2 = ref_dec.read(4608)
+        assert len(got) == len(want) and d.position_ns() == ref_dec.position_ns(), (k, len(got), len(want))
+        dd = np.abs(np.frombuffer(got, np.int16).astype(np.int32) - np.frombuffer(want, np.int16).astype(np.int32))
+        worst = max(worst, int(dd.max()) if dd.size else 0)
+        n_exact += int((dd == 0).sum())
+        n_bytes += dd.size
+    for d in decs:
+        d.close()
+    out["seek_to_time"] = {"seeks": int(args.cfg5_seeks), "seed": 7, "ms_per_seek_and_read": t_seek / max(args.cfg5_seeks, 1) * 1e3,
+                           "checked_against": "the oracle Decoder performing the same SeekToTime + Read (decode.go:320-341, quirk Q9)",
+                           "max_abs_diff_lsb": worst, "exact_fraction": n_exact / max(n_bytes, 1)}
+    return out
+
+
+def ix_frame_offset(pkg, data, ix, f):
+    """Byte offset of frame f's header (the end of the data for f = number of frames)."""
+    f = max(0, f)
+    return int(data.size) if f >= ix.frames() else int(ix.frame_pos(f))
 
 
 def main():
@@ -440,8 +615,13 @@ def main():
     ap.add_argument("--streams", type=int, default=4096, help="streams per GPU")
     ap.add_argument("--frames", type=int, default=1149, help="frames per stream (1149 = 30 s at 44.1 kHz)")
     ap.add_argument("--wave", type=int, default=0, help="granules per kernel wave (0 = engine default)")
+    ap.add_argument("--e2e-streams", type=int, default=1024, help="streams per GPU of the end-to-end (host buffers) measurement")
+    ap.add_argument("--cfg4-streams", type=int, default=8192, help="streams per GPU of the configs[3] section")
+    ap.add_argument("--cfg5-frames", type=int, default=413438, help="frames of the configs[4] long stream (3 h at 320 kbps)")
+    ap.add_argument("--cfg5-seeks", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-decode-batch", action="store_true")
+    ap.add_argument("--no-cfg4", action="store_true")
+    ap.add_argument("--no-cfg5", action="store_true")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":

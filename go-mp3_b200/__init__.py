@@ -183,6 +183,8 @@ def host_lib() -> C.CDLL:
     L.mp3_stream_index_frames.restype = i64
     L.mp3_stream_index_sample_rate.argtypes = [vp]
     L.mp3_stream_index_sample_rate.restype = C.c_int
+    L.mp3_stream_index_frame_pos.argtypes = [vp, i64]
+    L.mp3_stream_index_frame_pos.restype = i64
     L.mp3_stream_index_pcm_bytes.argtypes = [vp, i64, i64]
     L.mp3_stream_index_pcm_bytes.restype = i64
     L.mp3_decode_frames.argtypes = [vp, C.c_int, vp, i64, i64, C.c_void_p, C.POINTER(i64)]
@@ -253,6 +255,8 @@ def gpu_lib(exact: bool = False) -> C.CDLL:
     L.mp3gpu_device_info.restype = C.c_int
     L.mp3gpu_device_pci_bus_id.argtypes = [vp, C.c_char_p, sz]
     L.mp3gpu_device_pci_bus_id.restype = C.c_int
+    L.mp3gpu_measure_d2h.argtypes = [vp, vp, sz, C.c_int, C.POINTER(C.c_double)]
+    L.mp3gpu_measure_d2h.restype = C.c_int
     L.mp3gpu_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.mp3gpu_measure_fp32_peak.restype = C.c_int
     _gpu[exact] = L
@@ -549,6 +553,39 @@ class Engine:
     def device_count(self) -> int:
         return self.lib.mp3_engine_device_count(self.h)
 
+    def measure_d2h_ceiling(self, bytes_per_device: int, reps: int = 3) -> dict:
+        """Plain cudaMemcpyAsync device -> pinned host on every device of the engine AT THE SAME TIME (one thread per
+        device): the copy ceiling the end-to-end path is measured against.  Returns aggregate and per-device GB/s."""
+        import threading
+        g = gpu_lib(getattr(self, "exact", False))
+        n = self.device_count()
+        bufs = [g.mp3gpu_host_alloc(bytes_per_device) for _ in range(n)]
+        if not all(bufs):
+            for b in bufs:
+                if b:
+                    g.mp3gpu_host_free(b)
+            raise MemoryError("pinned allocation for the copy ceiling failed")
+        secs = [C.c_double(0) for _ in range(n)]
+        rcs = [0] * n
+        start = threading.Barrier(n)
+
+        def run(i):
+            ctx = self.lib.mp3_engine_gpu_at(self.h, i)
+            start.wait()
+            rcs[i] = g.mp3gpu_measure_d2h(ctx, bufs[i], bytes_per_device, reps, C.byref(secs[i]))
+
+        th = [threading.Thread(target=run, args=(i,)) for i in range(n)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        for b in bufs:
+            g.mp3gpu_host_free(b)
+        if any(rcs):
+            raise Mp3Error(-2, "mp3gpu_measure_d2h failed")
+        per = [bytes_per_device * reps / s.value / 1e9 for s in secs]
+        return {"aggregate_gbs": bytes_per_device * reps * n / max(s.value for s in secs) / 1e9, "per_device_gbs": per}
+
     def decode_frames(self, index: "StreamIndex", f0: int, f1: int, slot: int = 0) -> Tuple[np.ndarray, int]:
         """PCM bytes of frames [f0, f1) of an indexed stream, identical to that stretch of the linear decode
         (mp3_decode_frames).  Returns (uint8 array, status)."""
@@ -681,6 +718,7 @@ class StreamIndex:
     def frames(self) -> int: return self.lib.mp3_stream_index_frames(self.h)
     def sample_rate(self) -> int: return self.lib.mp3_stream_index_sample_rate(self.h)
     def pcm_bytes(self, f0: int, f1: int) -> int: return self.lib.mp3_stream_index_pcm_bytes(self.h, f0, f1)
+    def frame_pos(self, f: int) -> int: return self.lib.mp3_stream_index_frame_pos(self.h, f)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -1027,6 +1027,9 @@ extern "C" int mp3_stream_index_create(const uint8_t *data, size_t len, mp3_stre
 extern "C" void mp3_stream_index_free(mp3_stream_index *ix) { delete ix; }
 extern "C" int64_t mp3_stream_index_frames(const mp3_stream_index *ix) { return ix ? (int64_t)ix->frame_pos.size() : 0; }
 extern "C" int mp3_stream_index_sample_rate(const mp3_stream_index *ix) { return ix ? ix->sample_rate : 0; }
+extern "C" int64_t mp3_stream_index_frame_pos(const mp3_stream_index *ix, int64_t f) {
+    return (ix && f >= 0 && f < (int64_t)ix->frame_pos.size()) ? ix->frame_pos[(size_t)f] : -1;
+}
 extern "C" int64_t mp3_stream_index_pcm_bytes(const mp3_stream_index *ix, int64_t f0, int64_t f1) {
     if (!ix || f0 < 0 || f1 < f0 || f1 > (int64_t)ix->frame_pos.size()) return -1;
     return (ix->gran_before[(size_t)f1] - ix->gran_before[(size_t)f0]) * MP3GPU_PCM_BYTES_PER_GRANULE;

@@ -69,23 +69,19 @@ struct WaveBufs {
 // K1: scalefactors + Huffman.  One thread per unit slot; per-unit logic in unit_logic.h.
 // ------------------------------------------------------------------------------------------
 // One persistent CTA per SM; its warps share the code tables (30 KB, staged once) and otherwise never meet: every WARP
-// pulls windows of WIN (128) consecutive units from a global counter and handles a window on its own —
+// pulls tiles of UPW (32 or 64) consecutive units from a global counter and handles a tile on its own —
 //  1. Work order.  A unit's decode time is proportional to its number of code words, and the 32 lanes of a warp wait
-//     for the slowest (with units in stream order the lanes of a warp are busy half of the time).  The warp sorts the
-//     window's units by big_values (counting sort in its private bins, 8-pair bins) and decodes them in batches of 32,
-//     longest first, so that the lanes of a batch get units of similar length.
-//  2. Staging.  Every lane copies the bits its unit reads (part2_3_length bits, never beyond the frame's buffer end) from
-//     main_data into its own piece of the warp's staging area, 16 bytes at a time, byte-swapped once into big-endian bit
-//     order; the pieces are packed by a warp prefix sum of their sizes.  A unit's cursor is then a plain bit position
-//     into shared memory (StagedCursor / FastWindow, unit_logic.h) — no divergent refill from global memory.  What does
-//     not fit (a batch larger than the staging area, a unit that runs past its part 3, the scfsi look-back into gr 0's
-//     scalefactor bits) is read from global memory word by word.
-// Earlier versions of this design sorted and staged per CTA (256-512 units, one contiguous stretch): better sorting, but the
-// four CTA barriers per tile left a third of the stall samples on barriers; and per warp with one contiguous stretch per
-// 32 / 64 consecutive units: no barriers, but too few units to sort (profiles/r02_k1_history.md).  There is no
-// __syncthreads in the loop now, and the staging area holds only the 32 units in flight, so the window can be sorted
-// as widely as one likes.
-constexpr int kHuffWin = 128;
+//     for the slowest.  With UPW = 64 the warp sorts the tile's units by big_values (counting sort in its private bins)
+//     and decodes the 32 longer ones first, then the 32 shorter ones, so that the lanes of a pass get similar lengths.
+//  2. Staging.  The units of a tile are consecutive in stream order, so the bits they read are one contiguous stretch
+//     of main_data (streams lie back to back).  The warp copies that stretch into its private staging area with
+//     coalesced 16-byte loads, byte-swapped once into big-endian bit order; a unit's cursor is then a plain bit position
+//     (StagedCursor / FastWindow, unit_logic.h) — no divergent refill from global memory.  What lies outside the stretch
+//     (a tile whose stretch exceeds the staging capacity, malformed descriptors) is read from global memory word by word.
+// The first version of this design did 1. and 2. per CTA (256-512 units sorted and staged at once).  It sorted better, but
+// its four CTA barriers per tile left the warps with the shorter units and all warps during the staging loads idle: a
+// third of the stall samples sat on the barriers (profiles/r02_k1_history.md); there is no __syncthreads in the loop now.
+template <int UPW>
 __global__ void __launch_bounds__(1024, 1)
 k_huffman(const uint8_t *__restrict__ main_data, unsigned long long main_bits, const mp3gpu_unit *__restrict__ units,
           long long first_unit, int n_units, DeviceTables T, WaveBufs B, int stage_cap16, unsigned int *__restrict__ tile_counter) {
@@ -93,7 +89,7 @@ k_huffman(const uint8_t *__restrict__ main_data, unsigned long long main_bits, c
     __shared__ uint64_t s_quad[256];
     __shared__ uint32_t s_qlut[512];
     __shared__ uint32_t s_desc[34];
-    constexpr int NP = kHuffWin / 32;  // units per lane and window
+    constexpr int NP = UPW / 32;  // units per lane and tile
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const SmemRef s_lut = SmemRef::of(s_dyn32);
     {
@@ -107,32 +103,41 @@ k_huffman(const uint8_t *__restrict__ main_data, unsigned long long main_bits, c
     for (int i = threadIdx.x; i < 512; i += blockDim.x) s_qlut[i] = T.quad_lut[i];
     __syncthreads();  // the only CTA barrier: the tables are staged
     // this warp's block: staging area (+ 16 bytes the FastWindow prefetch may touch), sort bins, work order
-    const int warp_words = stage_cap16 * 4 + 4 + 40 + kHuffWin / 4;
+    const int warp_words = stage_cap16 * 4 + 4 + 40 + UPW / 4;
     uint32_t *const s_stage = s_dyn32 + T.huff_lut_n / 2 + warp * warp_words;  // huff_lut_n is a multiple of 8 entries: 16-byte aligned
     unsigned int *const s_bin = s_stage + stage_cap16 * 4 + 4;
     uint8_t *const s_order = reinterpret_cast<uint8_t *>(s_bin + 40);
     const uint32_t main16 = (uint32_t)(((main_bits >> 3) + 48) >> 4);  // 16-byte chunks that may be read: main_data is followed by 64 bytes of padding
-    const int n_windows = (n_units + kHuffWin - 1) / kHuffWin;
+    const int n_tiles = (n_units + UPW - 1) / UPW;
 #pragma unroll 1
     for (;;) {
-        int win = 0;
-        if (lane == 0) win = (int)atomicAdd(tile_counter, 1u);
-        win = __shfl_sync(0xffffffffu, win, 0);
-        if (win >= n_windows) break;
-        const int base = win * kHuffWin;
-        // ---- work order inside the window -----------------------------------------------------------------------
-        {
-            int key[NP];
+        int tile = 0;
+        if (lane == 0) tile = (int)atomicAdd(tile_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= n_tiles) break;
+        const int base = tile * UPW;
+        // ---- the stretch of main data the tile reads, and the work order inside the tile ---------------------
+        int key[NP];
+        uint32_t lo16 = 0xffffffffu, hi16 = 0u;
 #pragma unroll
-            for (int j = 0; j < NP; j++) {
-                key[j] = 38;  // beyond the wave
-                const int ul0 = base + j * 32 + lane;
-                if (ul0 < n_units) {
-                    const mp3gpu_unit *u = units + first_unit + ul0;
-                    const uint32_t w0 = __ldg(&u->w0), w2 = __ldg(&u->w2);
-                    key[j] = !u_valid(w2) ? 37 : 36 - ((u_p23len(w0) == 0 ? 0 : imin(u_bigval(w0), 288)) >> 3);
+        for (int j = 0; j < NP; j++) {
+            key[j] = 38;  // beyond the wave
+            const int ul0 = base + j * 32 + lane;
+            if (ul0 < n_units) {
+                const mp3gpu_unit u = units[first_unit + ul0];
+                key[j] = 37;
+                if (u_valid(u.w2)) {
+                    key[j] = 36 - ((u_p23len(u.w0) == 0 ? 0 : imin(u_bigval(u.w0), 288)) >> 3);
+                    uint32_t l, h;
+                    stage_reach(u, main_bits, &l, &h);
+                    lo16 = l < lo16 ? l : lo16;
+                    hi16 = h > hi16 ? h : hi16;
                 }
             }
+        }
+        lo16 = __reduce_min_sync(0xffffffffu, lo16);
+        hi16 = __reduce_max_sync(0xffffffffu, hi16);
+        if (NP > 1) {
             s_bin[lane] = 0;
             if (lane < 8) s_bin[32 + lane] = 0;
             __syncwarp();
@@ -163,51 +168,35 @@ k_huffman(const uint8_t *__restrict__ main_data, unsigned long long main_bits, c
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < NP; j++) s_order[s_bin[key[j]] + rank[j]] = (uint8_t)(j * 32 + lane);
-            __syncwarp();
         }
-        // ---- batches of 32 units, the longest first ----------------------------------------------------------------
-#pragma unroll 1
-        for (int batch = 0; batch < NP; batch++) {
-            const int ul = base + (int)s_order[batch * 32 + lane];  // wave-local unit index
-            const bool live = ul < n_units && u_valid(__ldg(&units[first_unit + (ul < n_units ? ul : 0)].w2));
-            // the lane's piece of the staging area
-            uint32_t lo16 = 0, n16 = 0;
-            if (live) {
-                uint32_t hi16;
-                stage_reach(units[first_unit + ul], main_bits, &lo16, &hi16);
-                hi16 = hi16 < main16 ? hi16 : main16;
-                n16 = hi16 > lo16 ? hi16 - lo16 : 0u;
-            }
-            uint32_t off16 = n16;  // inclusive scan ...
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, off16, d);
-                if (lane >= d) off16 += y;
-            }
-            off16 -= n16;          // ... made exclusive
-            if (off16 >= (uint32_t)stage_cap16) n16 = 0;                                              // the batch is larger than the staging area:
-            else if (off16 + n16 > (uint32_t)stage_cap16) n16 = (uint32_t)stage_cap16 - off16;        // the rest is read from global memory
-            {
-                const uint4 *src = reinterpret_cast<const uint4 *>(main_data) + lo16;
-                uint4 *dst = reinterpret_cast<uint4 *>(s_stage) + off16;
+        StageCtx S;
+        S.sw = SmemRef::of(s_stage);
+        S.gw = reinterpret_cast<const uint32_t *>(main_data);
+        S.main_bits = main_bits;
+        {
+            const uint32_t hi = hi16 < main16 ? hi16 : main16;
+            uint32_t n16 = hi > lo16 ? hi - lo16 : 0u;  // no valid unit in the tile: lo = ~0
+            if (n16 > (uint32_t)stage_cap16) n16 = (uint32_t)stage_cap16;
+            S.n_words = (int)(n16 * 4);
+            S.lo_word = (unsigned long long)lo16 * 4ull;
+            const uint4 *src = reinterpret_cast<const uint4 *>(main_data) + lo16;
+            uint4 *dst = reinterpret_cast<uint4 *>(s_stage);
 #pragma unroll 4
-                for (uint32_t i = 0; i < n16; i++) {
-                    uint4 v = __ldg(src + i);
-                    v.x = be32(v.x); v.y = be32(v.y); v.z = be32(v.z); v.w = be32(v.w);
-                    dst[i] = v;
-                }
+            for (uint32_t i = lane; i < n16; i += 32) {
+                uint4 v = __ldg(src + i);
+                v.x = be32(v.x); v.y = be32(v.y); v.z = be32(v.z); v.w = be32(v.w);
+                dst[i] = v;
             }
-            // no barrier: a lane reads its own piece only (and the four padding words behind it, whoever they belong to)
+        }
+        __syncwarp();
+        // ---- decode: the longer units first -------------------------------------------------------------------
+#pragma unroll 1
+        for (int pass = 0; pass < NP; pass++) {
+            const int ul = base + (NP > 1 ? (int)s_order[pass * 32 + lane] : lane);  // wave-local unit index
             if (ul < n_units) {
-                if (!live) {
+                if (!u_valid(units[first_unit + ul].w2)) {
                     B.meta[ul] = 0;
                 } else {
-                    StageCtx S;
-                    S.sw = SmemRef::of(s_stage + off16 * 4);
-                    S.n_words = (int)(n16 * 4);
-                    S.lo_word = (unsigned long long)lo16 * 4ull;
-                    S.gw = reinterpret_cast<const uint32_t *>(main_data);
-                    S.main_bits = main_bits;
                     uint32_t pk[8];
                     uint32_t *out = reinterpret_cast<uint32_t *>(B.is16 + (size_t)ul * 576);
                     const uint32_t meta = huffman_unit_staged(T, s_lut, s_qlut, s_desc, s_quad, S, units, first_unit + ul, pk, out);
@@ -217,7 +206,7 @@ k_huffman(const uint8_t *__restrict__ main_data, unsigned long long main_bits, c
                     B.meta[ul] = meta;
                 }
             }
-            __syncwarp();  // the next batch overwrites the staging area
+            __syncwarp();
         }
     }
 }

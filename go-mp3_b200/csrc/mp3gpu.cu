@@ -47,7 +47,7 @@ struct mp3gpu_ctx {
     int lut_bytes = 0;
     int smem_per_sm = 0, smem_per_cta_max = 0;  // shared-memory budget (bytes) of an SM / of one CTA (opt-in maximum)
     int huff_static_smem = 0;                   // static shared memory of k_huffman
-    int k1_warps_override = 0, k1_stage_pct_override = 0;  // experiments: MP3GPU_K1_WARPS / MP3GPU_K1_STAGE_PCT
+    int k1_upw_override = 0, k1_warps_override = 0, k1_stage_pct_override = 0;  // experiments: MP3GPU_K1_UPW / _WARPS / _STAGE_PCT
     // workspace for one wave (+1 granule look-back where needed)
     int16_t *d_is16 = nullptr;
     uint32_t *d_meta = nullptr;
@@ -261,9 +261,11 @@ extern "C" int mp3gpu_create(int device, const mp3gpu_opts *opts, mp3gpu_ctx **o
         ctx->smem_per_cta_max = (int)prop.sharedMemPerBlockOptin;
         {
             cudaFuncAttributes fa;
-            CK(cudaFuncGetAttributes(&fa, k_huffman));
+            CK(cudaFuncGetAttributes(&fa, k_huffman<64>));
             ctx->huff_static_smem = (int)fa.sharedSizeBytes;
-            CK(cudaFuncSetAttribute(k_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_per_cta_max - ctx->huff_static_smem));
+            CK(cudaFuncSetAttribute(k_huffman<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_per_cta_max - ctx->huff_static_smem));
+            CK(cudaFuncSetAttribute(k_huffman<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_per_cta_max - ctx->huff_static_smem));
+            if (const char *e = getenv("MP3GPU_K1_UPW")) ctx->k1_upw_override = atoi(e);
             if (const char *e = getenv("MP3GPU_K1_WARPS")) ctx->k1_warps_override = atoi(e);
             if (const char *e = getenv("MP3GPU_K1_STAGE_PCT")) ctx->k1_stage_pct_override = atoi(e);
         }
@@ -328,26 +330,36 @@ static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, size_t main_len, 
     cudaStream_t s = ctx->s_compute;
     if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][0], s));
     {
-        // k_huffman: one persistent CTA per SM.  Each warp stages the bits of the 32 units it has in flight in its own piece
-        // of shared memory, sized from the call's average bytes per unit (x 2: a batch holds units of similar, and for the
-        // first batches above-average, length; what does not fit is read from global memory); the CTA gets as many warps
-        // as fit next to the 30 KB of code tables.
+        // k_huffman: one persistent CTA per SM whose warps each stage the stretch of main data a tile of 32 or 64 units
+        // reads in their own piece of shared memory.  The piece is sized from the call's average bytes per unit (x 1.25 for
+        // tile-to-tile variation, VBR; a tile that needs more reads its tail from global memory), and the CTA gets as many
+        // warps as fit next to the 30 KB of code tables.  64-unit tiles (sorted, two passes) keep the lanes of a warp
+        // busier; 32-unit tiles allow twice the warps when the bitrate is high.
         const int nu = 2 * n;
         const unsigned long long main_bits = (unsigned long long)main_len * 8ull;
         const double avg = bytes_per_unit > 1.0 ? bytes_per_unit : 1.0;
-        const int pct = ctx->k1_stage_pct_override ? ctx->k1_stage_pct_override : 200;
+        const int pct = ctx->k1_stage_pct_override ? ctx->k1_stage_pct_override : 125;
         const int budget = ctx->smem_per_cta_max - ctx->huff_static_smem - ctx->lut_bytes;
-        const int fixed = 16 + 160 + kHuffWin;  // per warp: FastWindow padding, sort bins, work order
-        int stage = (int)((avg + 24.0) * 32.0 * pct / 100.0);  // + 24: a unit's piece starts and ends on 16-byte chunks and reads 64 bits ahead
-        stage = std::max(1024, std::min(stage, budget / 8 - fixed)) & ~15;  // at least eight warps
-        int warps = std::min(32, budget / (stage + fixed));
-        if (ctx->k1_warps_override) warps = std::min(warps, ctx->k1_warps_override);
+        int upw = 64, warps = 0, cap16 = 0;
+        for (int pass = 0; pass < 2; pass++) {
+            upw = pass == 0 ? 64 : 32;
+            if (ctx->k1_upw_override) upw = ctx->k1_upw_override == 32 ? 32 : 64;
+            int stage = ((int)(avg * upw * pct / 100.0) + 512 + 15) & ~15;
+            const int max_stage = budget / 8 - (16 + 160 + upw);  // at least eight warps
+            if (stage > max_stage) stage = max_stage & ~15;
+            const int per_warp = stage + 16 + 160 + upw;
+            warps = std::min(32, budget / per_warp);
+            if (ctx->k1_warps_override) warps = std::min(warps, ctx->k1_warps_override);
+            cap16 = stage / 16;
+            if (warps >= 20 || pass == 1 || ctx->k1_upw_override) break;
+        }
         if (warps < 1) warps = 1;
-        const int windows = (nu + kHuffWin - 1) / kHuffWin;
-        const int grid = std::min((windows + warps - 1) / warps, ctx->sm_count);
-        const size_t dyn = (size_t)ctx->lut_bytes + (size_t)warps * (size_t)(stage + fixed);
+        const int tiles = (nu + upw - 1) / upw;
+        const int grid = std::min((tiles + warps - 1) / warps, ctx->sm_count);
+        const size_t dyn = (size_t)ctx->lut_bytes + (size_t)warps * (size_t)(cap16 * 16 + 16 + 160 + upw);
         CK(cudaMemsetAsync(ctx->d_counter + 1, 0, sizeof(unsigned int), s));
-        k_huffman<<<grid, warps * 32, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, stage / 16, ctx->d_counter + 1);
+        if (upw == 64) k_huffman<64><<<grid, warps * 32, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, cap16, ctx->d_counter + 1);
+        else k_huffman<32><<<grid, warps * 32, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, cap16, ctx->d_counter + 1);
     }
     if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][1], s));
     {
@@ -722,6 +734,30 @@ extern "C" int mp3gpu_device_info(mp3gpu_ctx *ctx, char *name, size_t name_len, 
 extern "C" int mp3gpu_device_pci_bus_id(mp3gpu_ctx *ctx, char *out, size_t out_len) {
     if (!ctx || !out || out_len < 16) return MP3GPU_E_INVALID;
     CK(cudaDeviceGetPCIBusId(out, (int)out_len, ctx->device));
+    return MP3GPU_OK;
+}
+
+extern "C" int mp3gpu_measure_d2h(mp3gpu_ctx *ctx, void *host_dst, size_t bytes, int reps, double *seconds) {
+    if (!ctx || !host_dst || !seconds || bytes == 0 || reps < 1) return MP3GPU_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    void *d = nullptr;
+    CK(cudaMalloc(&d, bytes));
+    CK(cudaMemsetAsync(d, 0x5a, bytes, ctx->s_out));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    CK(cudaMemcpyAsync(host_dst, d, bytes, cudaMemcpyDeviceToHost, ctx->s_out));  // warm-up: first touch of the host pages
+    CK(cudaStreamSynchronize(ctx->s_out));
+    CK(cudaEventRecord(a, ctx->s_out));
+    for (int r = 0; r < reps; r++) CK(cudaMemcpyAsync(host_dst, d, bytes, cudaMemcpyDeviceToHost, ctx->s_out));
+    CK(cudaEventRecord(b, ctx->s_out));
+    CK(cudaEventSynchronize(b));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    *seconds = (double)ms * 1e-3;
     return MP3GPU_OK;
 }
 

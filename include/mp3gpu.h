@@ -193,6 +193,11 @@ int mp3gpu_device_info(mp3gpu_ctx *ctx, char *name, size_t name_len, int *sm_cou
  * GPU's NUMA node (/sys/bus/pci/devices/<id>/numa_node). */
 int mp3gpu_device_pci_bus_id(mp3gpu_ctx *ctx, char *out, size_t out_len);
 
+/* Copies `bytes` from a device scratch buffer to host_dst (pinned host memory) `reps` times with plain cudaMemcpyAsync
+ * on the context's output stream and returns the device-timed seconds: the ceiling of the end-to-end path, whose cost
+ * is the PCM going home over PCIe (4 bytes per stereo sample).  bench.py runs it on all devices of an engine at once. */
+int mp3gpu_measure_d2h(mp3gpu_ctx *ctx, void *host_dst, size_t bytes, int reps, double *seconds);
+
 /* Measures the FP32 FMA issue peak of the device with a register-resident FFMA loop (TFLOP/s).
  * Used by bench.py as the fp32 roofline denominator (MEASURED_PEAKS.json has no fp32 entry). */
 int mp3gpu_measure_fp32_peak(mp3gpu_ctx *ctx, double *tflops);

@@ -129,6 +129,7 @@ void mp3_stream_index_free(mp3_stream_index *idx);
 int64_t mp3_stream_index_frames(const mp3_stream_index *idx);
 int mp3_stream_index_sample_rate(const mp3_stream_index *idx);
 int64_t mp3_stream_index_pcm_bytes(const mp3_stream_index *idx, int64_t f0, int64_t f1); /* PCM bytes of frames [f0, f1) */
+int64_t mp3_stream_index_frame_pos(const mp3_stream_index *idx, int64_t f); /* byte offset of frame f's header; -1 if out of range */
 
 /* PCM of frames [f0, f1) of the stream, byte-identical to that stretch of a linear decode of the whole stream, decoded
  * on their own on device slot `slot`.  The library re-creates the state a linear decode has at f0: it parses a lead-in of
