@@ -209,11 +209,12 @@ def host_lib() -> C.CDLL:
     return L
 
 
-def gpu_lib(exact: bool = False) -> C.CDLL:
-    """libmp3gpu.so (or the no-contraction build libmp3gpu_exact.so) with prototypes set."""
+def gpu_lib(exact=False) -> C.CDLL:
+    """libmp3gpu.so (False), the no-contraction build libmp3gpu_exact.so (True) or the bounds-checked build
+    libmp3gpu_checked.so ("checked"), with prototypes set."""
     if exact in _gpu:
         return _gpu[exact]
-    L = C.CDLL(_lib_path("libmp3gpu_exact.so" if exact else "libmp3gpu.so"))
+    L = C.CDLL(_lib_path({False: "libmp3gpu.so", True: "libmp3gpu_exact.so", "checked": "libmp3gpu_checked.so"}[exact]))
     vp, sz = C.c_void_p, C.c_size_t
     L.mp3gpu_create.argtypes = [C.c_int, C.POINTER(GpuOpts), C.POINTER(vp)]
     L.mp3gpu_create.restype = C.c_int
@@ -255,6 +256,8 @@ def gpu_lib(exact: bool = False) -> C.CDLL:
     L.mp3gpu_device_info.restype = C.c_int
     L.mp3gpu_device_pci_bus_id.argtypes = [vp, C.c_char_p, sz]
     L.mp3gpu_device_pci_bus_id.restype = C.c_int
+    L.mp3gpu_pcm_to_f32_planar.argtypes = [vp, vp, sz, vp, vp]
+    L.mp3gpu_pcm_to_f32_planar.restype = C.c_int
     L.mp3gpu_measure_d2h.argtypes = [vp, vp, sz, C.c_int, C.POINTER(C.c_double)]
     L.mp3gpu_measure_d2h.restype = C.c_int
     L.mp3gpu_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double)]
@@ -391,8 +394,9 @@ def parse_streams(streams: Sequence[bytes], host_threads: int = 0) -> ParsedBatc
 # Device engine (mp3gpu.h) — used directly by bench.py and the stage-level parity tests
 # --------------------------------------------------------------------------------------------------
 class GpuEngine:
-    def __init__(self, device: int = 0, wave_granules: int = 0, keep_intermediates: bool = False, exact: bool = False):
-        self.lib = gpu_lib(exact)
+    def __init__(self, device: int = 0, wave_granules: int = 0, keep_intermediates: bool = False, exact: bool = False,
+                 checked: bool = False):
+        self.lib = gpu_lib("checked" if checked else exact)
         self.ctx = C.c_void_p()
         opts = GpuOpts(1, wave_granules, 1 if keep_intermediates else 0, 0)
         rc = self.lib.mp3gpu_create(device, C.byref(opts), C.byref(self.ctx))
@@ -428,6 +432,10 @@ class GpuEngine:
         """Device-resident decode (raw device pointers, e.g. torch tensors' data_ptr())."""
         f = self.lib.mp3gpu_decode_device if sync else self.lib.mp3gpu_decode_device_async
         self._check(f(self.ctx, d_main, main_len, d_units, n_granules, d_pcm))
+
+    def pcm_to_f32_planar(self, d_pcm: int, n_samples: int, d_left: int, d_right: int):
+        """Output side: device-resident s16 interleaved PCM -> two float32 planes (x 1/32768), queued behind the decode."""
+        self._check(self.lib.mp3gpu_pcm_to_f32_planar(self.ctx, d_pcm, n_samples, d_left, d_right))
 
     def decode_host(self, p_main: int, main_len: int, p_units: int, n_granules: int, p_pcm: int):
         """Host-buffer decode with raw host pointers (pinned buffers from host_alloc make the copies asynchronous)."""
@@ -517,14 +525,14 @@ class Engine:
 
     def __init__(self, device: int = 0, host_threads: int = 0, wave_granules: int = 0, chunk_frames: int = 0,
                  keep_intermediates: bool = False, exact: bool = False, devices: Optional[Sequence[int]] = None,
-                 trim_gapless: bool = False):
+                 trim_gapless: bool = False, checked: bool = False):
         """`devices`: CUDA ordinals of a multi-GPU engine (DecodeBatch shards its streams over them, decode_stream_split
         cuts one stream into a frame range per device); the same ordinal may appear twice (two device engines on one GPU)."""
         self.lib = host_lib()
         self.h = C.c_void_p()
         opts = EngineOpts()
         opts.device, opts.host_threads, opts.wave_granules, opts.chunk_frames = device, host_threads, wave_granules, chunk_frames
-        opts.keep_intermediates, opts.use_exact_library = (1 if keep_intermediates else 0), (1 if exact else 0)
+        opts.keep_intermediates, opts.use_exact_library = (1 if keep_intermediates else 0), (2 if checked else (1 if exact else 0))
         if devices:
             if len(devices) > MAX_DEVICES:
                 raise ValueError("too many devices")
@@ -537,7 +545,7 @@ class Engine:
             self.h = None
             raise Mp3Error(rc, "mp3_engine_create failed: a CUDA device and libmp3gpu.so are required; "
                                "there is no CPU decode path")
-        self.exact = exact
+        self.exact = "checked" if checked else exact
 
     def close(self):
         if getattr(self, "h", None):

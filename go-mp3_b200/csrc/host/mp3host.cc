@@ -54,8 +54,8 @@ std::string self_dir() {
     return ".";
 }
 
-bool load_gpu_api(GpuApi &api, bool exact, std::string &err) {
-    std::string path = self_dir() + (exact ? "/libmp3gpu_exact.so" : "/libmp3gpu.so");
+bool load_gpu_api(GpuApi &api, unsigned which, std::string &err) {
+    std::string path = self_dir() + (which == 1 ? "/libmp3gpu_exact.so" : (which == 2 ? "/libmp3gpu_checked.so" : "/libmp3gpu.so"));
     api.handle = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
     if (!api.handle) {
         err = std::string("dlopen ") + path + ": " + dlerror();
@@ -177,8 +177,11 @@ void gather_batch(const std::vector<ParsedStream> &ps, const BatchLayout &L, uin
 struct DeviceSlot {
     int device = 0;
     mp3gpu_ctx *gpu = nullptr;
+    mp3gpu_ctx *gpu_b = nullptr;  // second device engine of the same GPU, created by the first chunked DecodeBatch: two calls in
+                                  // flight hide each call's exposed head (first wave's upload + kernels) and tail (last wave's
+                                  // download) behind the other's copies
     Pinned r_main, r_units;  // frame-range jobs
-    std::mutex mu;           // one call at a time per device engine (the device engine is single-owner)
+    std::mutex mu, mu_b;     // one call at a time per device engine (a device engine is single-owner)
 };
 
 struct mp3_engine {
@@ -219,7 +222,7 @@ extern "C" int mp3_engine_create(const mp3_engine_opts *opts, mp3_engine **out) 
         delete e;
         return MP3_ERR_INVALID;
     }
-    if (!load_gpu_api(e->api, e->opts.use_exact_library != 0, e->err)) {
+    if (!load_gpu_api(e->api, e->opts.use_exact_library, e->err)) {
         fprintf(stderr, "mp3_engine_create: %s\n", e->err.c_str());
         delete e;
         return MP3_ERR_DEVICE;
@@ -256,6 +259,7 @@ extern "C" void mp3_engine_destroy(mp3_engine *e) {
         if (d->r_main.p) e->api.host_free(d->r_main.p);
         if (d->r_units.p) e->api.host_free(d->r_units.p);
         if (d->gpu) e->api.destroy(d->gpu);
+        if (d->gpu_b) e->api.destroy(d->gpu_b);
         delete d;
     }
     if (e->api.handle) dlclose(e->api.handle);
@@ -384,7 +388,11 @@ struct Shard {
     std::string err;
 };
 
-size_t shard_chunks(size_t n) { return n >= 256 ? std::min<size_t>(8, n / 128) : 1; }
+size_t shard_chunks(size_t n) {
+    static const int forced = [] { const char *e = getenv("MP3HOST_CHUNKS"); return e ? atoi(e) : 0; }();  // experiments
+    if (forced > 0) return std::min<size_t>((size_t)forced, n ? n : 1);
+    return n >= 256 ? std::min<size_t>(8, n / 128) : 1;
+}
 
 // Large shards are cut into chunks of streams: while the device decodes chunk k (the PCIe-bound part), the host
 // threads parse and gather chunk k+1 straight behind it in the same pinned arenas.
@@ -400,33 +408,51 @@ void decode_shard(mp3_engine *e, DeviceSlot *dev, const uint8_t *const *data, co
     std::condition_variable cv;
     std::deque<DeviceJob> jobs;
     bool closed = false;
-    auto run_job = [&](const DeviceJob &j) {
-        if (dev_rc != MP3GPU_OK || j.n_granules == 0) return;
+    if (n_chunks > 1 && !dev->gpu_b && !e->opts.keep_intermediates) {
+        mp3gpu_opts go{};
+        go.abi_version = MP3GPU_ABI_VERSION;
+        go.wave_granules = e->opts.wave_granules;
+        if (e->api.create(dev->device, &go, &dev->gpu_b) != MP3GPU_OK) dev->gpu_b = nullptr;  // one engine still works
+    }
+    std::mutex rc_mu;
+    auto run_job = [&](const DeviceJob &j, int which) {
+        if (j.n_granules == 0) return;
+        {
+            std::lock_guard<std::mutex> lk(rc_mu);
+            if (dev_rc != MP3GPU_OK) return;
+        }
+        mp3gpu_ctx *ctx = which ? dev->gpu_b : dev->gpu;
         const double a = now_s();
         int rc;
+        std::string msg;
         {
-            std::lock_guard<std::mutex> lk(dev->mu);
-            rc = e->api.decode(dev->gpu, j.main_data, j.main_len, j.units, j.n_granules, j.pcm);
-            if (rc != MP3GPU_OK) dev_err = e->api.last_error(dev->gpu);
+            std::lock_guard<std::mutex> lk(which ? dev->mu_b : dev->mu);
+            rc = e->api.decode(ctx, j.main_data, j.main_len, j.units, j.n_granules, j.pcm);
+            if (rc != MP3GPU_OK) msg = e->api.last_error(ctx);
         }
+        std::lock_guard<std::mutex> lk(rc_mu);
         S.device_s += now_s() - a;
-        if (rc != MP3GPU_OK) dev_rc = rc;
+        if (rc != MP3GPU_OK && dev_rc == MP3GPU_OK) {
+            dev_rc = rc;
+            dev_err = msg;
+        }
     };
-    std::thread worker;
+    std::vector<std::thread> workers;
     if (n_chunks > 1)
-        worker = std::thread([&]() {  // one worker owns the device engine for the duration of the shard
-            for (;;) {
-                DeviceJob j;
-                {
-                    std::unique_lock<std::mutex> lk(mu);
-                    cv.wait(lk, [&] { return closed || !jobs.empty(); });
-                    if (jobs.empty()) return;
-                    j = jobs.front();
-                    jobs.pop_front();
+        for (int w = 0; w < (dev->gpu_b ? 2 : 1); w++)
+            workers.emplace_back([&, w]() {  // a worker owns one device engine for the duration of the shard
+                for (;;) {
+                    DeviceJob j;
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [&] { return closed || !jobs.empty(); });
+                        if (jobs.empty()) return;
+                        j = jobs.front();
+                        jobs.pop_front();
+                    }
+                    run_job(j, w);
                 }
-                run_job(j);
-            }
-        });
+            });
     std::vector<ParsedStream> ps;  // reused by every chunk: the per-stream vectors keep their (already touched) capacity
     for (size_t c = 0; c < n_chunks; c++) {
         const size_t i0 = S.i0 + n * c / n_chunks, i1 = S.i0 + n * (c + 1) / n_chunks;
@@ -449,7 +475,7 @@ void decode_shard(mp3_engine *e, DeviceSlot *dev, const uint8_t *const *data, co
         S.gather_s += now_s() - tb;
         DeviceJob j{m_dst, L.m_total, u_dst, L.u_total / 2, (int16_t *)((uint8_t *)e->a_pcm.p + pcm_off)};
         if (n_chunks == 1) {
-            run_job(j);
+            run_job(j, 0);
         } else {
             {
                 std::lock_guard<std::mutex> lk(mu);
@@ -460,13 +486,13 @@ void decode_shard(mp3_engine *e, DeviceSlot *dev, const uint8_t *const *data, co
         m_cursor += (L.m_total + 64 + 63) & ~size_t(63);
         u_cursor += L.u_total;
     }
-    if (worker.joinable()) {
+    if (!workers.empty()) {
         {
             std::lock_guard<std::mutex> lk(mu);
             closed = true;
         }
         cv.notify_all();
-        worker.join();
+        for (auto &t : workers) t.join();
     }
     S.m_used = m_cursor - S.m_off;
     S.u_used = u_cursor - S.u_off;

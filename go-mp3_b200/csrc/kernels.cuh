@@ -63,6 +63,9 @@ struct WaveBufs {
     float *tap_xr;     // debug tap (opts.keep_intermediates): [nw][2][576] index sb*18+m, else nullptr
     const float *synth_d;  // [512]     frame.go:499-628
     unsigned int *work_counter;  // dynamic segment scheduler of k_hybrid; work_counter[1]: tile scheduler of k_huffman
+    // extents, read by the guards of the checked build only (MP3_CHECK, unit_logic.h)
+    long long units_total;       // unit slots of the whole submission (2 per granule)
+    int n_gran;                  // granules of this wave: is16 / meta / sfpack hold granules [-2, n_gran), hyb [-1, n_gran)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -124,6 +127,7 @@ k_huffman(const uint8_t *__restrict__ main_data, unsigned long long main_bits, c
             key[j] = 38;  // beyond the wave
             const int ul0 = base + j * 32 + lane;
             if (ul0 < n_units) {
+                if (!MP3_CHECK(first_unit + ul0 >= 0 && first_unit + ul0 < B.units_total, first_unit + ul0)) continue;
                 const mp3gpu_unit u = units[first_unit + ul0];
                 key[j] = 37;
                 if (u_valid(u.w2)) {
@@ -183,6 +187,7 @@ k_huffman(const uint8_t *__restrict__ main_data, unsigned long long main_bits, c
             uint4 *dst = reinterpret_cast<uint4 *>(s_stage);
 #pragma unroll 4
             for (uint32_t i = lane; i < n16; i += 32) {
+                if (!MP3_CHECK(lo16 + i < main16, lo16 + i)) continue;
                 uint4 v = __ldg(src + i);
                 v.x = be32(v.x); v.y = be32(v.y); v.z = be32(v.z); v.w = be32(v.w);
                 dst[i] = v;
@@ -193,7 +198,7 @@ k_huffman(const uint8_t *__restrict__ main_data, unsigned long long main_bits, c
 #pragma unroll 1
         for (int pass = 0; pass < NP; pass++) {
             const int ul = base + (NP > 1 ? (int)s_order[pass * 32 + lane] : lane);  // wave-local unit index
-            if (ul < n_units) {
+            if (ul < n_units && MP3_CHECK(ul >= 0 && ul < 2 * B.n_gran && first_unit + ul < B.units_total, ul)) {
                 if (!u_valid(units[first_unit + ul].w2)) {
                     B.meta[ul] = 0;
                 } else {
@@ -419,6 +424,10 @@ __device__ __forceinline__ void prefetch_granule(GranulePre &P, const mp3gpu_uni
         P.w2a = 0;
         return;
     }
+    if (!MP3_CHECK(G * 2 + 1 < B.units_total && g >= -2 && g < B.n_gran, G)) {
+        P.w2a = 0;
+        return;
+    }
     const mp3gpu_unit *ug = units + G * 2;
     P.w0a = __ldg(&ug[0].w0); P.w1a = __ldg(&ug[0].w1); P.w2a = __ldg(&ug[0].w2);
     P.w0b = __ldg(&ug[1].w0); P.w1b = __ldg(&ug[1].w1); P.w2b = __ldg(&ug[1].w2);
@@ -597,7 +606,8 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
                     if (ch == 1 && !valid_b) break;
                     const GranuleChan &c = ch ? c1 : c0;
                     const uint32_t *is2 = reinterpret_cast<const uint32_t *>(B.is16 + ((long long)g * 2 + ch) * 576);
-                    const int npair = c.cnt1 >> 1;  // count1 is even: big_values pairs + count1 quadruples
+                    int npair = c.cnt1 >> 1;  // count1 is even: big_values pairs + count1 quadruples
+                    if (!MP3_CHECK(g >= -2 && g < B.n_gran && npair <= 288, g)) npair = 0;
                     float *xs = s_x[ch];
     #pragma unroll 3
                     for (int p = lane; p < 288; p += 32) {
@@ -681,6 +691,7 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
 #pragma unroll
                     for (int m = 0; m < 18; m++) in[m] = s_x[ch][lane * kXrStride + m];
                 }
+                if (!MP3_CHECK(!need_first || (g >= 0 && g < B.n_gran), g)) continue;  // hyb / tap stores below
                 if (TAPS && need_first && B.tap_xr) {
                     float *o = B.tap_xr + ((long long)g * 2 + ch) * 576 + lane * 18;
 #pragma unroll
@@ -870,7 +881,7 @@ __device__ __forceinline__ void synth_window_slot(const float *U0, const float *
     } else {
         pr = pl;  // mono: both output channels carry channel 0 (frame.go:671-678)
     }
-    if (!WARMUP && (f & 1) && (FAST || sigma < n_slots)) pcm32[sigma * 32 + lane] = pl | (pr << 16);
+    if (!WARMUP && (f & 1) && (FAST || sigma < n_slots) && MP3_CHECK(sigma >= 0 && sigma < n_slots, sigma)) pcm32[sigma * 32 + lane] = pl | (pr << 16);
 }
 
 // 15 consecutive rows starting at `rb` (circular positions 0..14).
@@ -886,10 +897,11 @@ __device__ __forceinline__ void synth_window_block(const float *U0, const float 
 // Slot flags of wave-local slot sigma: bit 0 / 1 = channel 0 / 1 present, bit 2 = first slot of a ZERO_STATE granule;
 // 0 outside the submission.  Split in two so that the descriptor loads can be issued a block ahead of their use:
 // synth_flag_words() only loads (bit 31 of the result: slot inside the submission), synth_flags_of() decodes.
-__device__ __forceinline__ uint2 synth_flag_words(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_slots, int sigma) {
+__device__ __forceinline__ uint2 synth_flag_words(const mp3gpu_unit *__restrict__ units, long long units_total, long long first_granule, int n_slots, int sigma) {
     if (sigma < -18 || sigma >= n_slots || first_granule * 18 + sigma < 0) return make_uint2(0u, 0u);
     const int g = (sigma + 18) / 18 - 1;
     const mp3gpu_unit *ug = units + (first_granule + g) * 2;
+    if (!MP3_CHECK(first_granule + g >= 0 && (first_granule + g) * 2 + 1 < units_total, first_granule + g)) return make_uint2(0u, 0u);
     return make_uint2(__ldg(&ug[0].w2), __ldg(&ug[1].w2));
 }
 __device__ __forceinline__ int synth_flags_of(uint2 w, int sigma) {
@@ -918,7 +930,7 @@ __device__ __forceinline__ void synth_stage_block(const WaveBufs &B, long long f
         const int rem = c - ch * 8 * kSynBlock;
         const int row = rem >> 3, q = rem & 7;
         const int sigma = sigma0 + row;
-        if (sigma < n_slots && first_granule * 18 + sigma >= 0)
+        if (sigma < n_slots && first_granule * 18 + sigma >= 0 && MP3_CHECK(sigma >= -18, sigma))
             cp_async16(S + (ch * kSynBlock + row) * kURow + q * 4, synth_slot_src(B, sigma, ch) + q * 4);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -959,7 +971,7 @@ k_synth(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_gr
     // warm-up: the 15 slots in front of the segment (slot seg_first - 15 + p sits at circular position p), straight
     // from global memory
     {
-        const int f = lane < 15 ? synth_flags_of(synth_flag_words(units, first_granule, n_slots, seg_first - 15 + lane), seg_first - 15 + lane) : 0;
+        const int f = lane < 15 ? synth_flags_of(synth_flag_words(units, B.units_total, first_granule, n_slots, seg_first - 15 + lane), seg_first - 15 + lane) : 0;
 #pragma unroll 1
         for (int ch = 0; ch < 2; ch++)
             if (f & (1 << ch)) {
@@ -974,7 +986,7 @@ k_synth(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_gr
         else synth_window_block<false, true>(U0, U1, flags, 0, L, h, pcm32, seg_first - 15, n_slots, lane);
         __syncwarp();
     }
-    uint2 fw_next = synth_flag_words(units, first_granule, n_slots, lane < kSynBlock ? seg_first + lane : n_slots);
+    uint2 fw_next = synth_flag_words(units, B.units_total, first_granule, n_slots, lane < kSynBlock ? seg_first + lane : n_slots);
 #pragma unroll 1
     for (int blk = 0; blk < kSynSegSlots / kSynBlock; blk++) {
         const int sigma0 = seg_first + blk * kSynBlock;
@@ -1001,7 +1013,7 @@ k_synth(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_gr
         const bool more = blk + 1 < kSynSegSlots / kSynBlock && sigma0 + kSynBlock < n_slots;
         if (more) {
             synth_stage_block(B, first_granule, n_slots, S, sigma0 + kSynBlock, lane);
-            fw_next = synth_flag_words(units, first_granule, n_slots, lane < kSynBlock ? sigma0 + kSynBlock + lane : n_slots);
+            fw_next = synth_flag_words(units, B.units_total, first_granule, n_slots, lane < kSynBlock ? sigma0 + kSynBlock + lane : n_slots);
         }
         // ---- phase B ----
 #pragma unroll 1
@@ -1012,6 +1024,36 @@ k_synth(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_gr
             else synth_window_block<false, false>(U0, U1, flags, rb, L, h, pcm32, sigma0 + rb, n_slots, lane);
         }
         __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Output side: PCM for a consumer on the same GPU.  The reference's only consumer takes s16le
+// stereo (example/main.go:40-52) and so does Decoder.Read; a GPU audio pipeline (resampler, feature extractor, model
+// front end) takes float planes.  k_pcm_to_f32_planar converts device-resident interleaved int16 to two float32 planes
+// scaled by 1/32768 without the PCM ever crossing PCIe (the ceiling of the end-to-end path).  Pure streaming: 4 bytes
+// in and 8 bytes out per stereo sample, 16-byte loads and stores, grid-stride over a few CTAs per SM.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_pcm_to_f32_planar(const uint4 *__restrict__ pcm4 /* 4 stereo samples per element */, size_t n4, float4 *__restrict__ left4,
+                    float4 *__restrict__ right4, const int16_t *__restrict__ pcm, size_t n, float *__restrict__ left, float *__restrict__ right) {
+    const float k = 1.0f / 32768.0f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(pcm4 + i);
+        float4 l, r;
+        l.x = (float)(int16_t)(v.x & 0xffffu) * k; r.x = (float)(int16_t)(v.x >> 16) * k;
+        l.y = (float)(int16_t)(v.y & 0xffffu) * k; r.y = (float)(int16_t)(v.y >> 16) * k;
+        l.z = (float)(int16_t)(v.z & 0xffffu) * k; r.z = (float)(int16_t)(v.z >> 16) * k;
+        l.w = (float)(int16_t)(v.w & 0xffffu) * k; r.w = (float)(int16_t)(v.w >> 16) * k;
+        left4[i] = l;
+        right4[i] = r;
+    }
+    // the last n % 4 samples
+    const size_t tail0 = n4 * 4;
+    if (blockIdx.x == 0 && threadIdx.x < n - tail0) {
+        const size_t j = tail0 + threadIdx.x;
+        left[j] = (float)pcm[2 * j] * k;
+        right[j] = (float)pcm[2 * j + 1] * k;
     }
 }
 

@@ -266,6 +266,7 @@ extern "C" int mp3gpu_create(int device, const mp3gpu_opts *opts, mp3gpu_ctx **o
             CK(cudaFuncSetAttribute(k_huffman<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_per_cta_max - ctx->huff_static_smem));
             CK(cudaFuncSetAttribute(k_huffman<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_per_cta_max - ctx->huff_static_smem));
             if (const char *e = getenv("MP3GPU_K1_UPW")) ctx->k1_upw_override = atoi(e);
+            if (const char *e = getenv("MP3GPU_SEG_LEN")) ctx->seg_len = std::max(2, atoi(e));  // experiments: k_hybrid segment length
             if (const char *e = getenv("MP3GPU_K1_WARPS")) ctx->k1_warps_override = atoi(e);
             if (const char *e = getenv("MP3GPU_K1_STAGE_PCT")) ctx->k1_stage_pct_override = atoi(e);
         }
@@ -318,7 +319,7 @@ extern "C" const char *mp3gpu_last_error(const mp3gpu_ctx *ctx) { return ctx ? c
 // Launch the four kernels for granules [first, first+n) of the submission on s_compute.
 // d_pcm_wave points at the PCM of granule `first`.  `slot` selects the timing events (or -1).
 static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, size_t main_len, const mp3gpu_unit *d_units, long long first, int n,
-                       int16_t *d_pcm_wave, int slot, double bytes_per_unit) {
+                       int16_t *d_pcm_wave, int slot, double bytes_per_unit, size_t n_granules_total) {
     WaveBufs B;
     B.is16 = ctx->d_is16 + 2 * 2 * 576;  // granules -2, -1 live in front
     B.meta = ctx->d_meta + 2 * 2;
@@ -327,6 +328,8 @@ static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, size_t main_len, 
     B.tap_xr = ctx->d_tap_xr;
     B.synth_d = ctx->d_synth;
     B.work_counter = ctx->d_counter;
+    B.units_total = (long long)n_granules_total * 2;
+    B.n_gran = n;
     cudaStream_t s = ctx->s_compute;
     if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][0], s));
     {
@@ -399,6 +402,24 @@ static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, size_t main_len, 
     return MP3GPU_OK;
 }
 
+// Checked build: a guard that failed in a kernel (MP3_CHECK, unit_logic.h) becomes an error of the call that ran it.
+static int check_faults(mp3gpu_ctx *ctx) {
+#if MP3GPU_CHECKED
+    unsigned int f[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyFromSymbol(f, g_fault, sizeof f));
+    if (f[0]) {
+        const unsigned int zero[4] = {0, 0, 0, 0};
+        cudaMemcpyToSymbol(g_fault, zero, sizeof zero);
+        ctx->err = "checked build: " + std::to_string(f[0]) + " out-of-range access(es) stopped; first at source line " + std::to_string(f[1]) +
+                   ", index " + std::to_string((long long)(((unsigned long long)f[3] << 32) | f[2]));
+        return MP3GPU_E_CUDA;
+    }
+#else
+    (void)ctx;
+#endif
+    return MP3GPU_OK;
+}
+
 static int collect_timings(mp3gpu_ctx *ctx, int nslots) {
     float k[3] = {0, 0, 0};
     for (int i = 0; i < nslots; i++)
@@ -444,7 +465,7 @@ extern "C" int mp3gpu_decode_device_async(mp3gpu_ctx *ctx, const uint8_t *d_main
     for (size_t first = 0; first < n_granules; first += ctx->ws_granules) {
         int n = (int)std::min<size_t>(ctx->ws_granules, n_granules - first);
         int rc = launch_wave(ctx, d_main_data, main_data_len, d_units, (long long)first, n, d_pcm_out + first * 1152,
-                             slot < kTimingSlots ? slot : -1, (double)main_data_len / (2.0 * (double)n_granules));
+                             slot < kTimingSlots ? slot : -1, (double)main_data_len / (2.0 * (double)n_granules), n_granules);
         if (rc) return rc;
         if (slot < kTimingSlots) slot++;
         ctx->last.waves++;
@@ -459,7 +480,7 @@ extern "C" int mp3gpu_decode_device(mp3gpu_ctx *ctx, const uint8_t *d_main_data,
     int rc = mp3gpu_decode_device_async(ctx, d_main_data, main_data_len, d_units, n_granules, d_pcm_out);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->s_compute));
-    return MP3GPU_OK;
+    return check_faults(ctx);
 }
 
 extern "C" int mp3gpu_event_record(mp3gpu_ctx *ctx, int which) {
@@ -565,7 +586,7 @@ extern "C" int mp3gpu_decode_range(mp3gpu_ctx *ctx, const uint8_t *main_data, si
         CK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_in[r], 0));
         if (widx >= 3) CK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_out[r], 0));
         rc = launch_wave(ctx, ctx->d_main, main_data_len, ctx->d_units, (long long)first, n, ctx->d_pcm_ring[r],
-                         slot < kTimingSlots ? slot : -1, (double)main_data_len / (2.0 * (double)n_granules));
+                         slot < kTimingSlots ? slot : -1, (double)main_data_len / (2.0 * (double)n_granules), n_granules);
         if (rc) return rc;
         if (slot < kTimingSlots) slot++;
         CK(cudaEventRecord(ctx->ev_k[r], ctx->s_compute));
@@ -589,7 +610,7 @@ extern "C" int mp3gpu_decode_range(mp3gpu_ctx *ctx, const uint8_t *main_data, si
     ctx->last_collected = false;
     CK(cudaEventElapsedTime(&ctx->last.h2d_ms, ctx->ev_copy[0], ctx->ev_copy[1]));
     CK(cudaEventElapsedTime(&ctx->last.d2h_ms, ctx->ev_copy[2], ctx->ev_copy[3]));
-    return MP3GPU_OK;
+    return check_faults(ctx);
 }
 
 extern "C" void *mp3gpu_host_alloc(size_t bytes) {
@@ -637,7 +658,7 @@ extern "C" int mp3gpu_synchronize(mp3gpu_ctx *ctx) {
     if (!ctx) return MP3GPU_E_INVALID;
     CK(cudaSetDevice(ctx->device));
     CK(cudaDeviceSynchronize());
-    return MP3GPU_OK;
+    return check_faults(ctx);
 }
 
 extern "C" int mp3gpu_last_timings(mp3gpu_ctx *ctx, mp3gpu_timings *out) {
@@ -734,6 +755,22 @@ extern "C" int mp3gpu_device_info(mp3gpu_ctx *ctx, char *name, size_t name_len, 
 extern "C" int mp3gpu_device_pci_bus_id(mp3gpu_ctx *ctx, char *out, size_t out_len) {
     if (!ctx || !out || out_len < 16) return MP3GPU_E_INVALID;
     CK(cudaDeviceGetPCIBusId(out, (int)out_len, ctx->device));
+    return MP3GPU_OK;
+}
+
+extern "C" int mp3gpu_pcm_to_f32_planar(mp3gpu_ctx *ctx, const int16_t *d_pcm, size_t n_samples, float *d_left, float *d_right) {
+    if (!ctx) return MP3GPU_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (n_samples == 0) return MP3GPU_OK;
+    if (!d_pcm || !d_left || !d_right || ((uintptr_t)d_pcm & 15) || ((uintptr_t)d_left & 15) || ((uintptr_t)d_right & 15)) {
+        ctx->err = "pcm_to_f32_planar: device pointers must be non-null and 16-byte aligned";
+        return MP3GPU_E_INVALID;
+    }
+    const size_t n4 = n_samples / 4;
+    const int grid = (int)std::min<size_t>((n4 + 255) / 256 + 1, (size_t)ctx->sm_count * 8);
+    k_pcm_to_f32_planar<<<grid, 256, 0, ctx->s_compute>>>(reinterpret_cast<const uint4 *>(d_pcm), n4, reinterpret_cast<float4 *>(d_left),
+                                                          reinterpret_cast<float4 *>(d_right), d_pcm, n_samples, d_left, d_right);
+    CK(cudaGetLastError());
     return MP3GPU_OK;
 }
 

@@ -22,6 +22,36 @@
 struct alignas(16) uint4 { uint32_t x, y, z, w; };  // host-emulation build only (tests/hostemu)
 #endif
 
+// ---- checked build (-DMP3GPU_CHECKED=1) -------------------------------------------------------------------------
+// compute-sanitizer is closed on the GPU pool this was developed on, so memory safety has its own build: every global
+// load / store whose index depends on the input is guarded by MP3_CHECK(condition, index).  In the checked build a failed
+// guard records the source line and the index (first fault wins) and the access is skipped; the host side turns a
+// recorded fault into an error after the call (mp3gpu.cu).  In the product build the guard compiles to `true`.
+#ifndef MP3GPU_CHECKED
+#define MP3GPU_CHECKED 0
+#endif
+#if MP3GPU_CHECKED && defined(__CUDACC__)
+namespace mp3gpu {
+__device__ unsigned int g_fault[4];  // [0] faults, [1] source line of the first, [2..3] its index
+__host__ __device__ __forceinline__ bool check_fail(int line, long long idx) {
+#if defined(__CUDA_ARCH__)
+    if (atomicAdd(&g_fault[0], 1u) == 0u) {
+        g_fault[1] = (unsigned int)line;
+        g_fault[2] = (unsigned int)(unsigned long long)idx;
+        g_fault[3] = (unsigned int)((unsigned long long)idx >> 32);
+    }
+#else
+    (void)line;
+    (void)idx;
+#endif
+    return false;
+}
+}  // namespace mp3gpu
+#define MP3_CHECK(cond, idx) ((cond) ? true : ::mp3gpu::check_fail(__LINE__, (long long)(idx)))
+#else
+#define MP3_CHECK(cond, idx) (true)
+#endif
+
 namespace mp3gpu {
 
 // Tables indexed per lane (divergent): global memory on the device, plain memory in hostemu.
@@ -229,6 +259,8 @@ struct StageCtx {
     const uint32_t *gw;           // main_data as words (fallback)
     unsigned long long main_bits;
 };
+// words of main_data (+ its 64 bytes of tail padding) a cursor may load
+MP3_HD unsigned long long stage_readable_words(unsigned long long main_bits) { return ((main_bits >> 3) + 64) >> 2; }
 // Stretch of main data one unit may touch, in 16-byte chunks [lo16, hi16): from its first part2 bit to the end of
 // part 3 (a part2_3_length of 0 still reads its scalefactors, quirk Q1), never beyond the frame's buffer end.  A unit
 // that runs past that (big_values never checks the bit budget, quirk Q4) leaves the stretch and takes the fallback.
@@ -254,6 +286,10 @@ struct StagedCursor {
     int lim;                // max(buf_end_rel, 0): the logical position never advances past it
     int fast_lim;           // p <= fast_lim: the 64 bits from p on lie inside the stretch and before the buffer end, so
                             // peek32_fast() is exact there, pos() needs no clamp and no Bits(n) <= 32 can be refused
+#if MP3GPU_CHECKED
+    unsigned long long gword0, gwords;  // index of the word at gbase, and the words that may be loaded
+    int staged_words_left;              // staged words from the word at sw on
+#endif
 
     MP3_HD void init(const StageCtx &S, unsigned long long bit_start, int buf_end_rel) {
         if (bit_start > S.main_bits) bit_start = S.main_bits;  // same clipping as BitCursor::init
@@ -269,6 +305,11 @@ struct StagedCursor {
         p = off0;
         end = off0 + buf_end_rel;
         lim = buf_end_rel > 0 ? buf_end_rel : 0;
+#if MP3GPU_CHECKED
+        gword0 = word;
+        gwords = stage_readable_words(S.main_bits);
+        staged_words_left = sidx0 >= 0 ? S.n_words - sidx0 : 0;
+#endif
         fast_lim = -(1 << 30);
         if (sidx0 >= 0) {
             const int staged_end = (S.n_words - sidx0) * 32;  // p of the first bit behind the staged words
@@ -276,8 +317,11 @@ struct StagedCursor {
         }
     }
     MP3_HD uint32_t peek32_fast() const {  // requires p <= fast_lim
-        uint32_t w0, w1;
-        sw.ld32x2((uint32_t)(p >> 5) * 4u, w0, w1);
+        uint32_t w0 = 0, w1 = 0;
+#if MP3GPU_CHECKED
+        if (MP3_CHECK(p >= 0 && (p >> 5) + 1 < staged_words_left, p))
+#endif
+            sw.ld32x2((uint32_t)(p >> 5) * 4u, w0, w1);
         return funnel_l(w0, w1, p);
     }
     MP3_HD uint32_t peek32() const {  // next 32 bits, MSB first
@@ -286,8 +330,10 @@ struct StagedCursor {
         if ((uint32_t)si < (uint32_t)n_words_m1) {
             sw.ld32x2((uint32_t)idx * 4u, w0, w1);
         } else if (p < end) {  // outside the stretch: the two words straight from main_data (a word holding a bit below the buffer end lies inside main_data; the next one inside its tail padding)
-            w0 = be32(load_raw32(gbase + idx));
-            w1 = be32(load_raw32(gbase + idx + 1));
+            if (MP3_CHECK(idx >= 0 && gword0 + (unsigned long long)idx + 1 < gwords, gword0 + (unsigned long long)idx)) {
+                w0 = be32(load_raw32(gbase + idx));
+                w1 = be32(load_raw32(gbase + idx + 1));
+            }
         }
         const int rem = end - p;  // bits left before the buffer end
         return funnel_l(w0, w1, p) & ~ones_shr_clamp(rem > 0 ? rem : 0);
@@ -319,8 +365,15 @@ struct FastWindow {
     SmemRef next;  // the word after w2
     int off;       // cursor inside w0
     int p;         // the StagedCursor's p, kept alongside for the loop bounds
+#if MP3GPU_CHECKED
+    int words_left;  // staged words + padding from `next` on
+#endif
     MP3_HD void open(const StagedCursor &bc) {
         const uint32_t byte = (uint32_t)(bc.p >> 5) * 4u;
+#if MP3GPU_CHECKED
+        words_left = bc.staged_words_left + 4 - (bc.p >> 5) - 3;
+        if (!MP3_CHECK(bc.p >= 0 && words_left >= 0, bc.p)) { w0 = w1 = w2 = 0; next = bc.sw; off = 0; p = bc.p; words_left = 0; return; }
+#endif
         bc.sw.ld32x2(byte, w0, w1);
         w2 = bc.sw.ld32(byte + 8u);
         next = bc.sw.plus(byte + 12u);
@@ -335,6 +388,10 @@ struct FastWindow {
             off -= 32;
             w0 = w1;
             w1 = w2;
+#if MP3GPU_CHECKED
+            if (!MP3_CHECK(words_left > 0, p)) return;
+            words_left--;
+#endif
             w2 = next.ld32(0u);
             next = next.plus(4u);
         }
@@ -463,7 +520,7 @@ struct PairSink {
         n++;
         if ((n & 3) == 0) {
             uint4 v; v.x = a0; v.y = a1; v.z = a2; v.w = a3;
-            dst[(n >> 2) - 1] = v;
+            if (MP3_CHECK((n >> 2) - 1 < 72, n)) dst[(n >> 2) - 1] = v;  // 576 lines = 288 pairs = 72 stores per unit
         }
     }
     MP3_HD void flush() {  // pad with zero pairs up to the next multiple of four (they lie above count1)
@@ -644,7 +701,7 @@ MP3_HD uint32_t huff_pair_fast_at(const HuffRegions &R, int k, FastWindow &fw) {
 template <class BC, class MkCursor>
 MP3_HD uint32_t huffman_unit_t(const DeviceTables &T, SmemRef lut, const uint32_t *qlut, const uint32_t *huff_desc, const uint64_t *quad_signs,
                                const mp3gpu_unit *units, long long unit_index, MkCursor mk, uint32_t *pk, uint32_t *is_out) {
-    const mp3gpu_unit u = units[unit_index];
+    const mp3gpu_unit u = units[unit_index];  // the caller vouches for unit_index (kernels.cuh checks it against the submission)
     const uint32_t w0 = u.w0, w1 = u.w1, w2 = u.w2;
     BC bc;
     mk(bc, u.bit_start, u.buf_end_rel);
@@ -740,7 +797,7 @@ MP3_HD uint32_t huffman_unit_t(const DeviceTables &T, SmemRef lut, const uint32_
                 v.y = huff_pair_fast_at(R, k + 1, fw);
                 v.z = huff_pair_fast_at(R, k + 2, fw);
                 v.w = huff_pair_fast_at(R, k + 3, fw);
-                dst4[k >> 2] = v;
+                if (MP3_CHECK((k >> 2) < 72, k)) dst4[k >> 2] = v;  // 288 pairs = 72 stores per unit
                 k += 4;
             } while (k + 4 <= R.nbig && fw.p <= lim4);
             bc.p = fw.p;

@@ -193,6 +193,12 @@ int mp3gpu_device_info(mp3gpu_ctx *ctx, char *name, size_t name_len, int *sm_cou
  * GPU's NUMA node (/sys/bus/pci/devices/<id>/numa_node). */
 int mp3gpu_device_pci_bus_id(mp3gpu_ctx *ctx, char *out, size_t out_len);
 
+/* Output side: hands decoded PCM to a consumer on the same GPU without crossing PCIe.  Converts n_samples stereo samples of
+ * device-resident s16le interleaved PCM (what mp3gpu_decode_device leaves in HBM; the contract of Decoder.Read,
+ * decode.go:356-360) into two float32 planes scaled by 1/32768, queued on the context's compute stream behind the decode
+ * (no synchronise; use mp3gpu_synchronize or the event calls).  All three pointers 16-byte aligned. */
+int mp3gpu_pcm_to_f32_planar(mp3gpu_ctx *ctx, const int16_t *d_pcm, size_t n_samples, float *d_left, float *d_right);
+
 /* Copies `bytes` from a device scratch buffer to host_dst (pinned host memory) `reps` times with plain cudaMemcpyAsync
  * on the context's output stream and returns the device-timed seconds: the ceiling of the end-to-end path, whose cost
  * is the PCM going home over PCIe (4 bytes per stereo sample).  bench.py runs it on all devices of an engine at once. */

@@ -59,7 +59,8 @@ typedef struct mp3_engine_opts {
     uint32_t wave_granules;  /* passed to mp3gpu_opts (0 = default) */
     uint32_t chunk_frames;   /* Decoder decode-ahead per GPU call (0 = default 256) */
     uint32_t keep_intermediates; /* passed to mp3gpu_opts */
-    uint32_t use_exact_library;  /* 1: load libmp3gpu_exact.so (no FMA contraction) instead of libmp3gpu.so */
+    uint32_t use_exact_library;  /* 1: load libmp3gpu_exact.so (no FMA contraction), 2: libmp3gpu_checked.so (every input-dependent
+                                    global access guarded; for tests) instead of libmp3gpu.so */
     /* Multi-GPU: work is partitioned by stream (DecodeBatch) or by frame range of one stream
      * (mp3_decode_stream_split); streams share nothing, so there is no collective — each device gets its own device
      * engine, worker thread and region of the pinned arenas.  n_devices == 0 means the single device `device`. */

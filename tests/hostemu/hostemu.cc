@@ -209,6 +209,11 @@ const float *emu_table(int which, int *n) {
     *n = 0;
     return nullptr;
 }
+const float *emu_powq4(int *n) {
+    ensure();
+    *n = (int)g_h->powq4.size();
+    return g_h->powq4.data();
+}
 const double *emu_powtab34(int *n) {
     ensure();
     *n = (int)g_h->powtab34.size();

@@ -170,3 +170,25 @@ def test_device_api_rejects_misaligned_and_null_pointers(pkg):
     import ctypes as C
     ctx = C.c_void_p()
     assert g.lib.mp3gpu_create(0, C.byref(pkg.GpuOpts(99, 0, 0, 0)), C.byref(ctx)) == -3
+
+
+def test_output_side_f32_planar(pkg):
+    """mp3gpu_pcm_to_f32_planar: the PCM a decode leaves in HBM, as float planes for a consumer on the same GPU."""
+    import torch
+    data = synth.stream(synth.cfg4(3, 61))
+    pb = pkg.parse_streams([data])
+    g = pkg.GpuEngine(0)
+    dev = torch.device("cuda", 0)
+    d_main = torch.from_numpy(pb.main_data).to(dev)
+    d_units = torch.from_numpy(pb.units.view(np.uint8)).to(dev)
+    for n in (pb.n_granules * 576, pb.n_granules * 576 - 3, 5, 0):
+        d_pcm = torch.zeros(pb.n_granules * 1152, dtype=torch.int16, device=dev)
+        left = torch.full((max(n, 1) + 8,), 7.0, dtype=torch.float32, device=dev)
+        right = torch.full((max(n, 1) + 8,), 7.0, dtype=torch.float32, device=dev)
+        g.decode_device(d_main.data_ptr(), pb.main_data_len, d_units.data_ptr(), pb.n_granules, d_pcm.data_ptr(), sync=False)
+        g.pcm_to_f32_planar(d_pcm.data_ptr(), n, left.data_ptr(), right.data_ptr())
+        g.synchronize()
+        pcm = d_pcm.cpu().numpy().reshape(-1, 2)[:n].astype(np.float32) / 32768.0
+        assert np.array_equal(left[:n].cpu().numpy(), pcm[:, 0]) and np.array_equal(right[:n].cpu().numpy(), pcm[:, 1])
+        assert float(left[n:].min()) == 7.0 and float(right[n:].min()) == 7.0   # nothing written past the end
+    g.close()

@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--frames", type=int, default=1149)
     ap.add_argument("--passes", type=int, default=3)
     ap.add_argument("--workload", default="cfg3")
+    ap.add_argument("--wave", type=int, default=0, help="granules per kernel wave (0 = engine default)")
     args = ap.parse_args()
     import torch
     pkg = load_package()
@@ -27,7 +28,7 @@ def main():
     d_main = torch.from_numpy(pb.main_data).to(dev)
     d_units = torch.from_numpy(pb.units.view(np.uint8)).to(dev)
     d_pcm = torch.empty(pb.n_granules * 1152, dtype=torch.int16, device=dev)
-    eng = pkg.GpuEngine(0)
+    eng = pkg.GpuEngine(0, wave_granules=args.wave)
     for _ in range(args.passes):
         eng.decode_device(d_main.data_ptr(), pb.main_data_len, d_units.data_ptr(), pb.n_granules, d_pcm.data_ptr())
         print(eng.timings())
