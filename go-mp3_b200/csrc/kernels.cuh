@@ -445,7 +445,7 @@ __device__ __forceinline__ void prefetch_granule(GranulePre &P, const mp3gpu_uni
 template <bool TAPS>
 __global__ void __launch_bounds__(kHybWarps * 32, 4)
 k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_granules, int seg_len, int n_segs,
-         DeviceTables T, WaveBufs B) {
+         DeviceTables T, WaveBufs B, int counter_index) {
     extern __shared__ __align__(16) float s_dyn[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *const s_base = s_dyn + warp * kHybSmemWords;
@@ -464,7 +464,7 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
 
     for (;;) {
         int seg = 0;
-        if (lane == 0) seg = (int)atomicAdd(B.work_counter, 1u);
+        if (lane == 0) seg = (int)atomicAdd(B.work_counter + counter_index, 1u);
         seg = __shfl_sync(0xffffffffu, seg, 0);
         if (seg >= n_segs) break;
         const int g0 = seg * seg_len;
@@ -726,7 +726,7 @@ k_hybrid(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_g
 constexpr int kSynWarps = 4;
 constexpr int kSynThreads = kSynWarps * 32;
 constexpr int kSynBlock = 30;                    // slots per block: two periods of the circular history
-constexpr int kSynSegSlots = kSynBlock * 24;     // 720 slots = 40 granules per segment
+constexpr int kSynSegBlocks = 24;                // default segment: 24 blocks = 720 slots = 40 granules
 constexpr int kURow = 36;                        // floats per U row: 16-byte aligned, conflict-free 128-bit stores
 constexpr int kSynWarpWords = 4 * kSynBlock * kURow + 8;  // U[2][30][36], staging S[2][30][36], flags[30] (8 words)
 constexpr int kSynSmemBytes = kSynWarps * kSynWarpWords * 4;
@@ -938,14 +938,14 @@ __device__ __forceinline__ void synth_stage_block(const WaveBufs &B, long long f
 
 __global__ void __launch_bounds__(kSynThreads, 3)
 k_synth(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_granules, WaveBufs B,
-        int16_t *__restrict__ pcm /* wave-local: [n_granules][576][2] */) {
+        int16_t *__restrict__ pcm /* wave-local: [n_granules][576][2] */, int seg_blocks /* blocks of 30 slots per warp segment */) {
     extern __shared__ __align__(16) float s_u[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *U0 = s_u + warp * kSynWarpWords, *U1 = U0 + kSynBlock * kURow;
     float *S = U0 + 2 * kSynBlock * kURow;  // staging rows of the next block, same shape as U
     uint8_t *flags = reinterpret_cast<uint8_t *>(S + 2 * kSynBlock * kURow);
     const int n_slots = n_granules * 18;  // < 2^31: a wave is at most a few million granules
-    const long long seg_ll = ((long long)blockIdx.x * kSynWarps + warp) * kSynSegSlots;
+    const long long seg_ll = ((long long)blockIdx.x * kSynWarps + warp) * (long long)(seg_blocks * kSynBlock);
     if (seg_ll >= n_slots) return;
     const int seg_first = (int)seg_ll;  // wave-local slot
 
@@ -988,7 +988,7 @@ k_synth(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_gr
     }
     uint2 fw_next = synth_flag_words(units, B.units_total, first_granule, n_slots, lane < kSynBlock ? seg_first + lane : n_slots);
 #pragma unroll 1
-    for (int blk = 0; blk < kSynSegSlots / kSynBlock; blk++) {
+    for (int blk = 0; blk < seg_blocks; blk++) {
         const int sigma0 = seg_first + blk * kSynBlock;
         if (sigma0 >= n_slots) break;
         const int f = synth_flags_of(fw_next, sigma0 + lane);
@@ -1010,7 +1010,7 @@ k_synth(const mp3gpu_unit *__restrict__ units, long long first_granule, int n_gr
         if (lane < kSynBlock) flags[lane] = (uint8_t)f;
         __syncwarp();
         // ---- next block: start its copy and its flag loads, both consumed after phase B ----
-        const bool more = blk + 1 < kSynSegSlots / kSynBlock && sigma0 + kSynBlock < n_slots;
+        const bool more = blk + 1 < seg_blocks && sigma0 + kSynBlock < n_slots;
         if (more) {
             synth_stage_block(B, first_granule, n_slots, S, sigma0 + kSynBlock, lane);
             fw_next = synth_flag_words(units, B.units_total, first_granule, n_slots, lane < kSynBlock ? sigma0 + kSynBlock + lane : n_slots);

@@ -32,6 +32,7 @@ static_assert(sizeof(mp3gpu_unit) == 32, "mp3gpu_unit must be 32 bytes");
     } while (0)
 
 namespace {
+constexpr int kMaxSubWaves = 1024;  // dynamic-scheduler counters of k_hybrid in sub-wave mode
 constexpr int kTimingSlots = 64;  // per-kernel event pairs kept per call (waves beyond this are not timed individually)
 }
 
@@ -58,6 +59,9 @@ struct mp3gpu_ctx {
     unsigned int *d_counter = nullptr;
     int sm_count = 0;
     int seg_len = 32;
+    int sub_granules = 0;     // > 0: k_hybrid / k_synth alternate over sub-waves of this many granules (L2-resident hand-off)
+    int sub_seg_len = 8;      // k_hybrid segment length in sub-wave mode
+    int sub_syn_blocks = 6;   // k_synth blocks of 30 slots per warp segment in sub-wave mode
     size_t ws_granules = 0;   // granules the wave workspace currently holds
     // staging for host-buffer calls
     uint8_t *d_main = nullptr;
@@ -244,7 +248,7 @@ extern "C" int mp3gpu_create(int device, const mp3gpu_opts *opts, mp3gpu_ctx **o
         CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
         int rc = upload_tables(ctx);
         if (rc) return rc;
-        CK(cudaMalloc(&ctx->d_counter, 2 * sizeof(unsigned int)));
+        CK(cudaMalloc(&ctx->d_counter, (2 + kMaxSubWaves) * sizeof(unsigned int)));
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, device));
         ctx->sm_count = prop.multiProcessorCount;
@@ -267,6 +271,9 @@ extern "C" int mp3gpu_create(int device, const mp3gpu_opts *opts, mp3gpu_ctx **o
             CK(cudaFuncSetAttribute(k_huffman<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_per_cta_max - ctx->huff_static_smem));
             if (const char *e = getenv("MP3GPU_K1_UPW")) ctx->k1_upw_override = atoi(e);
             if (const char *e = getenv("MP3GPU_SEG_LEN")) ctx->seg_len = std::max(2, atoi(e));  // experiments: k_hybrid segment length
+            if (const char *e = getenv("MP3GPU_SUB")) ctx->sub_granules = std::max(0, atoi(e));
+            if (const char *e = getenv("MP3GPU_SUB_SEG")) ctx->sub_seg_len = std::max(2, atoi(e));
+            if (const char *e = getenv("MP3GPU_SUB_SYN")) ctx->sub_syn_blocks = std::max(1, atoi(e));
             if (const char *e = getenv("MP3GPU_K1_WARPS")) ctx->k1_warps_override = atoi(e);
             if (const char *e = getenv("MP3GPU_K1_STAGE_PCT")) ctx->k1_stage_pct_override = atoi(e);
         }
@@ -365,28 +372,59 @@ static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, size_t main_len, 
         else k_huffman<32><<<grid, warps * 32, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, cap16, ctx->d_counter + 1);
     }
     if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][1], s));
-    {
-        CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), s));
-        const int n_segs = (n + ctx->seg_len - 1) / ctx->seg_len;
-        const int grid = std::min((n_segs + kHybWarps - 1) / kHybWarps, ctx->sm_count * 5);
-        if (ctx->d_tap_xr) {
-            CK(cudaMemsetAsync(ctx->d_tap_xr, 0, (size_t)n * 2 * 576 * sizeof(float), s));
-            CK(cudaMemsetAsync(B.hyb, 0, (size_t)n * 2 * 576 * sizeof(float), s));  // taps of absent channels read as 0
-            k_hybrid<true><<<grid, kHybWarps * 32, kHybSmemBytes, s>>>(d_units, first, n, ctx->seg_len, n_segs, ctx->T, B);
-        } else {
-            k_hybrid<false><<<grid, kHybWarps * 32, kHybSmemBytes, s>>>(d_units, first, n, ctx->seg_len, n_segs, ctx->T, B);
+    const int sub = (ctx->sub_granules > 0 && !ctx->d_tap_xr) ? ctx->sub_granules : 0;
+    if (sub == 0) {
+        {
+            CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), s));
+            const int n_segs = (n + ctx->seg_len - 1) / ctx->seg_len;
+            const int grid = std::min((n_segs + kHybWarps - 1) / kHybWarps, ctx->sm_count * 5);
+            if (ctx->d_tap_xr) {
+                CK(cudaMemsetAsync(ctx->d_tap_xr, 0, (size_t)n * 2 * 576 * sizeof(float), s));
+                CK(cudaMemsetAsync(B.hyb, 0, (size_t)n * 2 * 576 * sizeof(float), s));  // taps of absent channels read as 0
+                k_hybrid<true><<<grid, kHybWarps * 32, kHybSmemBytes, s>>>(d_units, first, n, ctx->seg_len, n_segs, ctx->T, B, 0);
+            } else {
+                k_hybrid<false><<<grid, kHybWarps * 32, kHybSmemBytes, s>>>(d_units, first, n, ctx->seg_len, n_segs, ctx->T, B, 0);
+            }
         }
+        if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][2], s));
+        {
+            const long long slots = (long long)n * 18;
+            const long long segs = (slots + kSynSegBlocks * kSynBlock - 1) / (kSynSegBlocks * kSynBlock);
+            const int grid = (int)((segs + kSynWarps - 1) / kSynWarps);
+            k_synth<<<grid, kSynThreads, kSynSmemBytes, s>>>(d_units, first, n, B, d_pcm_wave, kSynSegBlocks);
+        }
+        if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][3], s));
+        // Carry the last granule's subband samples into the look-back slot for the next wave's k_synth halo.
+        CK(cudaMemcpyAsync(ctx->d_hyb, B.hyb + (size_t)(n - 1) * 2 * 576, 2 * 576 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    } else {
+        // L2-resident hand-off: k_hybrid and k_synth alternate over sub-waves small enough for the subband samples between them
+        // (hyb, 4,608 bytes per granule) to stay in the 126 MB L2: every sub-wave writes and reads the SAME hyb area, so the
+        // samples are overwritten in L2 before they are ever evicted to HBM.  The segments of both kernels are shortened so
+        // that one sub-wave still fills the machine.
+        if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][2], s));  // k_hybrid_ms reads 0; k_synth_ms holds both kernels
+        const int n_sub = (n + sub - 1) / sub;
+        CK(cudaMemsetAsync(ctx->d_counter + 2, 0, (size_t)std::min(n_sub, kMaxSubWaves) * sizeof(unsigned int), s));
+        for (int k = 0; k < n_sub; k++) {
+            const int g0 = k * sub, ng = std::min(sub, n - g0);
+            WaveBufs S = B;
+            S.is16 = B.is16 + (size_t)g0 * 2 * 576;
+            S.meta = B.meta + (size_t)g0 * 2;
+            S.sfpack = B.sfpack + (size_t)g0 * 2 * 8;
+            S.n_gran = ng;  // hyb stays: every sub-wave uses granule slots [-1, sub) of it
+            if (k >= kMaxSubWaves) CK(cudaMemsetAsync(ctx->d_counter + 2 + k % kMaxSubWaves, 0, sizeof(unsigned int), s));
+            const int n_segs = (ng + ctx->sub_seg_len - 1) / ctx->sub_seg_len;
+            const int grid = std::min((n_segs + kHybWarps - 1) / kHybWarps, ctx->sm_count * 5);
+            k_hybrid<false><<<grid, kHybWarps * 32, kHybSmemBytes, s>>>(d_units, first + g0, ng, ctx->sub_seg_len, n_segs, ctx->T, S, 2 + k % kMaxSubWaves);
+            const long long slots = (long long)ng * 18;
+            const long long segs = (slots + ctx->sub_syn_blocks * kSynBlock - 1) / (ctx->sub_syn_blocks * kSynBlock);
+            k_synth<<<(int)((segs + kSynWarps - 1) / kSynWarps), kSynThreads, kSynSmemBytes, s>>>(d_units, first + g0, ng, S, d_pcm_wave + (size_t)g0 * 1152,
+                                                                                                  ctx->sub_syn_blocks);
+            CK(cudaMemcpyAsync(ctx->d_hyb, S.hyb + (size_t)(ng - 1) * 2 * 576, 2 * 576 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+            ctx->last.launches += 2;
+        }
+        ctx->last.launches -= 2;  // the caller's count below adds three per wave
+        if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][3], s));
     }
-    if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][2], s));
-    {
-        const long long slots = (long long)n * 18;
-        const long long segs = (slots + kSynSegSlots - 1) / kSynSegSlots;
-        const int grid = (int)((segs + kSynWarps - 1) / kSynWarps);
-        k_synth<<<grid, kSynThreads, kSynSmemBytes, s>>>(d_units, first, n, B, d_pcm_wave);
-    }
-    if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][3], s));
-    // Carry the last granule's subband samples into the look-back slot for the next wave's k_synth halo.
-    CK(cudaMemcpyAsync(ctx->d_hyb, B.hyb + (size_t)(n - 1) * 2 * 576, 2 * 576 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     // Carry K1's outputs of the last two granules into the look-back slots for the next wave.  In order k = 0, 1
     // so that a one-granule wave shifts slot -1 to slot -2 before overwriting it.
     for (int k = 0; k < 2; k++) {
