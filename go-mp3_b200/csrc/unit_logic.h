@@ -284,8 +284,9 @@ struct StagedCursor {
     int off0;               // p at logical position 0
     int end;                // p of the frame's buffer end; bits at/after it read as 0 (bits.go:46-49,65-68)
     int lim;                // max(buf_end_rel, 0): the logical position never advances past it
-    int fast_lim;           // p <= fast_lim: the 64 bits from p on lie inside the stretch and before the buffer end, so
-                            // peek32_fast() is exact there, pos() needs no clamp and no Bits(n) <= 32 can be refused
+    int fast_end;           // min(buffer end, end of the staged words) as a p; far negative when the unit is not staged.  A step
+                            // that consumes at most n bits from p <= fast_end - n reads only staged bits in front of the buffer
+                            // end: FastWindow is exact there, pos() needs no clamp and no Bits() can be refused
 #if MP3GPU_CHECKED
     unsigned long long gword0, gwords;  // index of the word at gbase, and the words that may be loaded
     int staged_words_left;              // staged words from the word at sw on
@@ -310,19 +311,11 @@ struct StagedCursor {
         gwords = stage_readable_words(S.main_bits);
         staged_words_left = sidx0 >= 0 ? S.n_words - sidx0 : 0;
 #endif
-        fast_lim = -(1 << 30);
+        fast_end = -(1 << 30);
         if (sidx0 >= 0) {
             const int staged_end = (S.n_words - sidx0) * 32;  // p of the first bit behind the staged words
-            fast_lim = (end < staged_end ? end : staged_end) - 64;
+            fast_end = end < staged_end ? end : staged_end;
         }
-    }
-    MP3_HD uint32_t peek32_fast() const {  // requires p <= fast_lim
-        uint32_t w0 = 0, w1 = 0;
-#if MP3GPU_CHECKED
-        if (MP3_CHECK(p >= 0 && (p >> 5) + 1 < staged_words_left, p))
-#endif
-            sw.ld32x2((uint32_t)(p >> 5) * 4u, w0, w1);
-        return funnel_l(w0, w1, p);
     }
     MP3_HD uint32_t peek32() const {  // next 32 bits, MSB first
         const int idx = p >> 5, si = sidx0 + idx;
@@ -354,12 +347,13 @@ struct StagedCursor {
     }
 };
 
-// Register window over the staged stretch for the unchecked fast loops (cursor at p <= fast_lim): three consecutive
+// Register window over the staged stretch for the unchecked fast loops (see StagedCursor::fast_end): three consecutive
 // words, the third a prefetch, so that no shared-memory load sits on the code-word-to-code-word dependency chain —
 // the next code word's position depends on this one's length, and with the window read from shared memory at every
 // step K1 was bound by that latency (ncu: issue slots 51 % busy, short-scoreboard 3.9 stall cycles per issue).
 // A step consumes fewer than 32 bits, so one refill per advance() is enough; the refill is predicated, not a branch.
-// The stretch is followed by four words of padding: the prefetch may run that far past it (never consumed).
+// The stretch is followed by four words of padding: with the cursor inside the stretch, the window and its prefetch
+// reach at most that far past it (loaded, never consumed).
 struct FastWindow {
     uint32_t w0, w1, w2;
     SmemRef next;  // the word after w2
@@ -472,7 +466,7 @@ MP3_HD uint32_t huff_pair(SmemRef tree, LinbitsFn linbits_of, BC &bc) {
     return leaf_pair(e);
 }
 
-// The same pair where nothing can touch the buffer end (FastWindow: the cursor is at p <= fast_lim): no refused reads, no
+// The same pair where nothing can touch the buffer end (FastWindow: the cursor is at p <= fast_end - 47): no refused reads, no
 // clamp, no load on the dependency chain.
 template <class LinbitsFn>
 MP3_HD uint32_t huff_pair_fast(SmemRef tree, LinbitsFn linbits_of, FastWindow &fw) {
@@ -482,7 +476,7 @@ MP3_HD uint32_t huff_pair_fast(SmemRef tree, LinbitsFn linbits_of, FastWindow &f
         int x = (e & 0x20) ? 15 : other, y = (e & 0x40) ? 15 : other;
         const int linbits = linbits_of();  // >= 1 in every table that has escapes
         fw.advance(e & 31);                // at most 19 tree bits
-        uint32_t v = fw.peek();            // still inside the 64 bits fast_lim vouches for
+        uint32_t v = fw.peek();            // still in front of fast_end
         int n = 0;
         if (x == 15) { x += (int)(v >> (32 - linbits)); v <<= linbits; n = linbits; }
         if (x != 0) { if ((int32_t)v < 0) x = -x; v <<= 1; n++; }
@@ -782,16 +776,17 @@ MP3_HD uint32_t huffman_unit_t(const DeviceTables &T, SmemRef lut, const uint32_
     const int bit_pos_end = u_p23len(w0) - 1;
     const HuffRegions R = huff_regions(T, lut, huff_desc, w0, w1, w2);
     int k = 0;
+    PairSink sink;
     if constexpr (BC::kFast) {
-        // Four pairs per 16-byte store while the cursor stays clear of the buffer end and of the end of the staged
-        // stretch: a pair takes at most 19 + 2 * 13 + 2 = 47 bits, so three pairs after a check still see p <= fast_lim.
-        // No bit-budget check (quirk Q4).
+        // A pair takes at most 19 + 2 * 13 + 2 = 47 bits.  Four pairs per 16-byte store while four worst-case pairs still
+        // end in front of fast_end; then pair by pair while one does; what is left (the last bits in front of the frame's
+        // buffer end, or of the staged stretch) goes to the careful cursor.  No bit-budget check (quirk Q4).
         uint4 *dst4 = reinterpret_cast<uint4 *>(is_out);
-        const int lim4 = bc.fast_lim - 3 * 47;
-        if (4 <= R.nbig && bc.p <= lim4) {
+        const int lim4 = bc.fast_end - 4 * 47, lim1 = bc.fast_end - 47;
+        if (bc.p <= lim1 && R.nbig > 0) {
             FastWindow fw;
             fw.open(bc);
-            do {
+            while (k + 4 <= R.nbig && fw.p <= lim4) {
                 uint4 v;
                 v.x = huff_pair_fast_at(R, k, fw);
                 v.y = huff_pair_fast_at(R, k + 1, fw);
@@ -799,19 +794,27 @@ MP3_HD uint32_t huffman_unit_t(const DeviceTables &T, SmemRef lut, const uint32_
                 v.w = huff_pair_fast_at(R, k + 3, fw);
                 if (MP3_CHECK((k >> 2) < 72, k)) dst4[k >> 2] = v;  // 288 pairs = 72 stores per unit
                 k += 4;
-            } while (k + 4 <= R.nbig && fw.p <= lim4);
+            }
+            sink.init(is_out, k);
+            while (k < R.nbig && fw.p <= lim1) {
+                sink.put(huff_pair_fast_at(R, k, fw));
+                k++;
+            }
             bc.p = fw.p;
+        } else {
+            sink.init(is_out, 0);
         }
+    } else {
+        sink.init(is_out, 0);
     }
-    PairSink sink;
-    sink.init(is_out, k);
     for (; k < R.nbig; k++) sink.put(huff_pair_at(R, k, bc));  // the careful cursor: bits.go's rules at the buffer end
     int is_pos = R.nbig * 2;
     {
         const uint32_t dq = huff_desc[32 + u_c1tsel(w2)] & 0xffffffu;
         if constexpr (BC::kFast) {
-            const int p_end = bc.off0 + bit_pos_end;  // inside the fast range pos() is p - off0
-            if (is_pos <= 572 && bc.p <= p_end && bc.p <= bc.fast_lim) {
+            // a quadruple takes at most 6 + 4 = 10 bits; inside the fast range pos() is p - off0
+            const int p_end = bc.off0 + bit_pos_end, limq = bc.fast_end - 10;
+            if (is_pos <= 572 && bc.p <= p_end && bc.p <= limq) {
                 FastWindow fw;
                 fw.open(bc);
                 do {
@@ -823,7 +826,7 @@ MP3_HD uint32_t huffman_unit_t(const DeviceTables &T, SmemRef lut, const uint32_
                     sink.put((uint32_t)r);
                     sink.put((uint32_t)(r >> 32));
                     is_pos += 4;
-                } while (is_pos <= 572 && fw.p <= p_end && fw.p <= bc.fast_lim);
+                } while (is_pos <= 572 && fw.p <= p_end && fw.p <= limq);
                 bc.p = fw.p;
             }
         }

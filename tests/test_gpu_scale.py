@@ -59,7 +59,7 @@ def test_host_and_device_apis_agree(pkg):
     g.decode_device(d_main.data_ptr(), pb.main_data_len, d_units.data_ptr(), pb.n_granules, d_pcm.data_ptr())
     assert np.array_equal(host.reshape(-1), d_pcm.cpu().numpy())
     t = g.timings()
-    assert t["launches"] == 3 * t["waves"] and t["waves"] >= 2
+    assert t["launches"] >= 3 * t["waves"] and t["waves"] >= 2   # three kernels per wave (more in sub-wave mode)
     g.close()
 
 
