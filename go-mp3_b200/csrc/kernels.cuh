@@ -217,148 +217,6 @@ k_huffman(const uint8_t *__restrict__ main_data, unsigned long long main_bits, c
 }
 
 // ------------------------------------------------------------------------------------------
-// K1, wave-sorted variant: the work order is a permutation of the WHOLE wave's units by big_values (three small kernels:
-// per-CTA histograms, one scan, scatter), so that a warp's 32 lanes always hold units of nearly equal length; the staging
-// area then holds one piece per lane (the bits that lane's unit reads, packed by a warp prefix sum of their sizes) instead
-// of one contiguous stretch, because the 32 units of a batch are no longer neighbours in main_data.
-// ------------------------------------------------------------------------------------------
-constexpr int kSortBins = 40;      // keys 0..38 (kernels above); 39 unused
-constexpr int kSortThreads = 256;
-__device__ __forceinline__ int huff_sort_key(const mp3gpu_unit *__restrict__ units, long long first_unit, int ul, int n_units) {
-    if (ul >= n_units) return 38;
-    const mp3gpu_unit *u = units + first_unit + ul;
-    const uint32_t w0 = __ldg(&u->w0), w2 = __ldg(&u->w2);
-    return !u_valid(w2) ? 37 : 36 - ((u_p23len(w0) == 0 ? 0 : imin(u_bigval(w0), 288)) >> 3);
-}
-// hist[bin * gridDim.x + cta] = units of this CTA's chunk with that key
-__global__ void __launch_bounds__(kSortThreads)
-k_sort_hist(const mp3gpu_unit *__restrict__ units, long long first_unit, int n_units, int chunk, unsigned int *__restrict__ hist) {
-    __shared__ unsigned int s_h[kSortBins];
-    if (threadIdx.x < kSortBins) s_h[threadIdx.x] = 0;
-    __syncthreads();
-    const int lo = blockIdx.x * chunk, hi = min(lo + chunk, n_units);
-    for (int ul = lo + threadIdx.x; ul < hi; ul += kSortThreads) atomicAdd(&s_h[huff_sort_key(units, first_unit, ul, n_units)], 1u);
-    __syncthreads();
-    if (threadIdx.x < kSortBins) hist[threadIdx.x * gridDim.x + blockIdx.x] = s_h[threadIdx.x];
-}
-// exclusive scan of hist (bin-major) in place; one CTA
-__global__ void __launch_bounds__(1024) k_sort_scan(unsigned int *__restrict__ hist, int n) {
-    __shared__ unsigned int s_part[1024];
-    const int per = (n + 1023) / 1024, lo = threadIdx.x * per, hi = min(lo + per, n);
-    unsigned int sum = 0;
-    for (int i = lo; i < hi; i++) sum += hist[i];
-    s_part[threadIdx.x] = sum;
-    __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-        const unsigned int y = threadIdx.x >= d ? s_part[threadIdx.x - d] : 0u;
-        __syncthreads();
-        s_part[threadIdx.x] += y;
-        __syncthreads();
-    }
-    unsigned int acc = s_part[threadIdx.x] - sum;
-    for (int i = lo; i < hi; i++) {
-        const unsigned int c = hist[i];
-        hist[i] = acc;
-        acc += c;
-    }
-}
-// perm[position] = wave-local unit index, positions by key (longest first), then by CTA chunk (stream order between chunks)
-__global__ void __launch_bounds__(kSortThreads)
-k_sort_scatter(const mp3gpu_unit *__restrict__ units, long long first_unit, int n_units, int chunk, const unsigned int *__restrict__ hist,
-               uint32_t *__restrict__ perm) {
-    __shared__ unsigned int s_o[kSortBins];
-    if (threadIdx.x < kSortBins) s_o[threadIdx.x] = hist[threadIdx.x * gridDim.x + blockIdx.x];
-    __syncthreads();
-    const int lo = blockIdx.x * chunk, hi = min(lo + chunk, n_units);
-    for (int ul = lo + threadIdx.x; ul < hi; ul += kSortThreads)
-        perm[atomicAdd(&s_o[huff_sort_key(units, first_unit, ul, n_units)], 1u)] = (uint32_t)ul;
-}
-
-__global__ void __launch_bounds__(1024, 1)
-k_huffman_sorted(const uint8_t *__restrict__ main_data, unsigned long long main_bits, const mp3gpu_unit *__restrict__ units,
-                 long long first_unit, int n_units, DeviceTables T, WaveBufs B, int stage_cap16, unsigned int *__restrict__ batch_counter,
-                 const uint32_t *__restrict__ perm) {
-    extern __shared__ __align__(16) uint32_t s_dyn32[];  // pair-tree code tables (uint16 entries), then one staging area per warp
-    __shared__ uint64_t s_quad[256];
-    __shared__ uint32_t s_qlut[512];
-    __shared__ uint32_t s_desc[34];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const SmemRef s_lut = SmemRef::of(s_dyn32);
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(T.huff_lut);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_dyn32);
-#pragma unroll 4
-        for (int i = threadIdx.x; i < T.huff_lut_n / 8; i += blockDim.x) dst[i] = __ldg(src + i);
-    }
-    if (threadIdx.x < 34) s_desc[threadIdx.x] = T.huff_desc[threadIdx.x];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_quad[i] = T.quad_signs[i];
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_qlut[i] = T.quad_lut[i];
-    __syncthreads();  // the only CTA barrier: the tables are staged
-    uint32_t *const s_stage = s_dyn32 + T.huff_lut_n / 2 + warp * (stage_cap16 * 4 + 4);  // + 16 bytes the FastWindow prefetch may touch
-    const uint32_t main16 = (uint32_t)(((main_bits >> 3) + 48) >> 4);  // 16-byte chunks that may be read: main_data is followed by 64 bytes of padding
-    const int n_batches = (n_units + 31) / 32;
-#pragma unroll 1
-    for (;;) {
-        int batch = 0;
-        if (lane == 0) batch = (int)atomicAdd(batch_counter, 1u);
-        batch = __shfl_sync(0xffffffffu, batch, 0);
-        if (batch >= n_batches) break;
-        const int slot = batch * 32 + lane;
-        const int ul = slot < n_units ? (int)__ldg(perm + slot) : n_units;  // wave-local unit index
-        const bool in_wave = ul < n_units && MP3_CHECK(ul >= 0 && ul < 2 * B.n_gran && first_unit + ul < B.units_total, ul);
-        const bool live = in_wave && u_valid(__ldg(&units[first_unit + (in_wave ? ul : 0)].w2));
-        // the lane's piece of the staging area
-        uint32_t lo16 = 0, n16 = 0;
-        if (live) {
-            uint32_t hi16;
-            stage_reach(units[first_unit + ul], main_bits, &lo16, &hi16);
-            hi16 = hi16 < main16 ? hi16 : main16;
-            n16 = hi16 > lo16 ? hi16 - lo16 : 0u;
-        }
-        uint32_t off16 = n16;  // inclusive scan ...
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, off16, d);
-            if (lane >= d) off16 += y;
-        }
-        off16 -= n16;          // ... made exclusive
-        if (off16 >= (uint32_t)stage_cap16) n16 = 0;                                              // the batch is larger than the staging area:
-        else if (off16 + n16 > (uint32_t)stage_cap16) n16 = (uint32_t)stage_cap16 - off16;        // the rest is read from global memory
-        {
-            const uint4 *src = reinterpret_cast<const uint4 *>(main_data) + lo16;
-            uint4 *dst = reinterpret_cast<uint4 *>(s_stage) + off16;
-#pragma unroll 4
-            for (uint32_t i = 0; i < n16; i++) {
-                uint4 v = __ldg(src + i);
-                v.x = be32(v.x); v.y = be32(v.y); v.z = be32(v.z); v.w = be32(v.w);
-                dst[i] = v;
-            }
-        }
-        // no barrier: a lane reads its own piece only (and the four padding words behind it, whoever they belong to)
-        if (in_wave) {
-            if (!live) {
-                B.meta[ul] = 0;
-            } else {
-                StageCtx S;
-                S.sw = SmemRef::of(s_stage + off16 * 4);
-                S.n_words = (int)(n16 * 4);
-                S.lo_word = (unsigned long long)lo16 * 4ull;
-                S.gw = reinterpret_cast<const uint32_t *>(main_data);
-                S.main_bits = main_bits;
-                uint32_t pk[8];
-                uint32_t *out = reinterpret_cast<uint32_t *>(B.is16 + (size_t)ul * 576);
-                const uint32_t meta = huffman_unit_staged(T, s_lut, s_qlut, s_desc, s_quad, S, units, first_unit + ul, pk, out);
-                uint4 *dst = reinterpret_cast<uint4 *>(B.sfpack + (size_t)ul * 8);
-                dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                B.meta[ul] = meta;
-            }
-        }
-        __syncwarp();  // the next batch overwrites the staging area
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // k_hybrid = K2 + K3: one warp marches through a segment of consecutive granules (both channels).
 //
 //   K2  requantise + reorder + stereo + alias reduction      frame.go:140-452   lane = spectral line (mod 32)

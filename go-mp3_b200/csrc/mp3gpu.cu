@@ -32,7 +32,6 @@ static_assert(sizeof(mp3gpu_unit) == 32, "mp3gpu_unit must be 32 bytes");
     } while (0)
 
 namespace {
-constexpr int kSortGridMax = 592;   // CTAs of the two sort passes of k_huffman_sorted
 constexpr int kMaxSubWaves = 1024;  // dynamic-scheduler counters of k_hybrid in sub-wave mode
 constexpr int kTimingSlots = 64;  // per-kernel event pairs kept per call (waves beyond this are not timed individually)
 }
@@ -58,9 +57,6 @@ struct mp3gpu_ctx {
     float *d_tap_xr = nullptr;       // debug tap (opts.keep_intermediates)
     float *d_synth = nullptr;        // synth_d[512]
     unsigned int *d_counter = nullptr;
-    unsigned int *d_sort_hist = nullptr;  // k_huffman_sorted: [kSortBins][sort_grid] histograms / offsets
-    uint32_t *d_perm = nullptr;           // work order of the wave's units (2 * ws_granules entries)
-    int k1_mode = 1;                      // 1: per-warp tiles of consecutive units (k_huffman); 2: wave-sorted (k_huffman_sorted)
     int sm_count = 0;
     int seg_len = 32;
     int sub_granules = 0;     // > 0: k_hybrid / k_synth alternate over sub-waves of this many granules (L2-resident hand-off)
@@ -93,8 +89,7 @@ static int ensure_workspace(mp3gpu_ctx *ctx, size_t granules) {
     const size_t W = std::min<size_t>(ctx->wave, std::max<size_t>(granules, 1));
     if (W <= ctx->ws_granules) return MP3GPU_OK;
     CK(cudaStreamSynchronize(ctx->s_compute));
-    cudaFree(ctx->d_is16); cudaFree(ctx->d_meta); cudaFree(ctx->d_sfpack); cudaFree(ctx->d_hyb); cudaFree(ctx->d_tap_xr); cudaFree(ctx->d_perm);
-    ctx->d_perm = nullptr;
+    cudaFree(ctx->d_is16); cudaFree(ctx->d_meta); cudaFree(ctx->d_sfpack); cudaFree(ctx->d_hyb); cudaFree(ctx->d_tap_xr);
 
     ctx->d_is16 = nullptr; ctx->d_meta = nullptr; ctx->d_sfpack = nullptr; ctx->d_hyb = nullptr; ctx->d_tap_xr = nullptr;
     ctx->ws_granules = 0;
@@ -108,7 +103,6 @@ static int ensure_workspace(mp3gpu_ctx *ctx, size_t granules) {
     CK(cudaMalloc(&ctx->d_hyb, (W + 1) * 2 * 576 * sizeof(float)));
     CK(cudaMemset(ctx->d_hyb, 0, 2 * 576 * sizeof(float)));
     if (ctx->opts.keep_intermediates) CK(cudaMalloc(&ctx->d_tap_xr, W * 2 * 576 * sizeof(float)));
-    CK(cudaMalloc(&ctx->d_perm, W * 2 * sizeof(uint32_t)));
     ctx->ws_granules = W;
     return MP3GPU_OK;
 }
@@ -255,7 +249,6 @@ extern "C" int mp3gpu_create(int device, const mp3gpu_opts *opts, mp3gpu_ctx **o
         int rc = upload_tables(ctx);
         if (rc) return rc;
         CK(cudaMalloc(&ctx->d_counter, (2 + kMaxSubWaves) * sizeof(unsigned int)));
-        CK(cudaMalloc(&ctx->d_sort_hist, (size_t)kSortBins * kSortGridMax * sizeof(unsigned int)));
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, device));
         ctx->sm_count = prop.multiProcessorCount;
@@ -281,8 +274,6 @@ extern "C" int mp3gpu_create(int device, const mp3gpu_opts *opts, mp3gpu_ctx **o
             if (const char *e = getenv("MP3GPU_SUB")) ctx->sub_granules = std::max(0, atoi(e));
             if (const char *e = getenv("MP3GPU_SUB_SEG")) ctx->sub_seg_len = std::max(2, atoi(e));
             if (const char *e = getenv("MP3GPU_SUB_SYN")) ctx->sub_syn_blocks = std::max(1, atoi(e));
-            CK(cudaFuncSetAttribute(k_huffman_sorted, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_per_cta_max - ctx->huff_static_smem));
-            if (const char *e = getenv("MP3GPU_K1_MODE")) ctx->k1_mode = atoi(e) == 2 ? 2 : 1;
             if (const char *e = getenv("MP3GPU_K1_WARPS")) ctx->k1_warps_override = atoi(e);
             if (const char *e = getenv("MP3GPU_K1_STAGE_PCT")) ctx->k1_stage_pct_override = atoi(e);
         }
@@ -309,8 +300,6 @@ extern "C" void mp3gpu_destroy(mp3gpu_ctx *ctx) {
     cudaFree(ctx->d_tap_xr);
     cudaFree(ctx->d_synth);
     cudaFree(ctx->d_counter);
-    cudaFree(ctx->d_sort_hist);
-    cudaFree(ctx->d_perm);
     cudaFree(ctx->d_main);
     cudaFree(ctx->d_units);
     for (int i = 0; i < 3; i++) {
@@ -360,28 +349,6 @@ static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, size_t main_len, 
         const unsigned long long main_bits = (unsigned long long)main_len * 8ull;
         const double avg = bytes_per_unit > 1.0 ? bytes_per_unit : 1.0;
         const int budget = ctx->smem_per_cta_max - ctx->huff_static_smem - ctx->lut_bytes;
-        if (ctx->k1_mode == 2) {
-            // wave-sorted: work order first (three small kernels), then one persistent CTA per SM whose warps pull batches of
-            // 32 equally long units.  A warp's staging area holds the pieces of its 32 units: the average bytes per unit
-            // (+ 24: a piece starts and ends on 16-byte chunks and reads 64 bits ahead) x 32 x 1.6, since the first batches
-            // are the longest units of the wave; what does not fit is read from global memory.
-            const int sort_grid = std::max(1, std::min(kSortGridMax, (nu + 4095) / 4096));
-            const int chunk = (nu + sort_grid - 1) / sort_grid;
-            k_sort_hist<<<sort_grid, kSortThreads, 0, s>>>(d_units, first * 2, nu, chunk, ctx->d_sort_hist);
-            k_sort_scan<<<1, 1024, 0, s>>>(ctx->d_sort_hist, kSortBins * sort_grid);
-            k_sort_scatter<<<sort_grid, kSortThreads, 0, s>>>(d_units, first * 2, nu, chunk, ctx->d_sort_hist, ctx->d_perm);
-            const int pct2 = ctx->k1_stage_pct_override ? ctx->k1_stage_pct_override : 160;
-            int stage = (int)((avg + 24.0) * 32.0 * pct2 / 100.0);
-            stage = std::max(1024, std::min(stage, budget / 8 - 16)) & ~15;  // at least eight warps
-            int warps = std::min(32, budget / (stage + 16));
-            if (ctx->k1_warps_override) warps = std::min(warps, ctx->k1_warps_override);
-            if (warps < 1) warps = 1;
-            const int batches = (nu + 31) / 32;
-            const int grid = std::min((batches + warps - 1) / warps, ctx->sm_count);
-            const size_t dyn = (size_t)ctx->lut_bytes + (size_t)warps * (size_t)(stage + 16);
-            CK(cudaMemsetAsync(ctx->d_counter + 1, 0, sizeof(unsigned int), s));
-            k_huffman_sorted<<<grid, warps * 32, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, stage / 16, ctx->d_counter + 1, ctx->d_perm);
-        } else {
         const int pct = ctx->k1_stage_pct_override ? ctx->k1_stage_pct_override : 125;
         int upw = 64, warps = 0, cap16 = 0;
         for (int pass = 0; pass < 2; pass++) {
@@ -403,7 +370,6 @@ static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, size_t main_len, 
         CK(cudaMemsetAsync(ctx->d_counter + 1, 0, sizeof(unsigned int), s));
         if (upw == 64) k_huffman<64><<<grid, warps * 32, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, cap16, ctx->d_counter + 1);
         else k_huffman<32><<<grid, warps * 32, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, cap16, ctx->d_counter + 1);
-        }
     }
     if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][1], s));
     const int sub = (ctx->sub_granules > 0 && !ctx->d_tap_xr) ? ctx->sub_granules : 0;
