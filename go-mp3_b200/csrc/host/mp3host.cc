@@ -1061,14 +1061,18 @@ extern "C" int64_t mp3_stream_index_pcm_bytes(const mp3_stream_index *ix, int64_
     return (ix->gran_before[(size_t)f1] - ix->gran_before[(size_t)f0]) * MP3GPU_PCM_BYTES_PER_GRANULE;
 }
 
-extern "C" int mp3_decode_frames(mp3_engine *e, int slot, const mp3_stream_index *ix, int64_t f0, int64_t f1, uint8_t *pcm_out,
-                                 int64_t *pcm_bytes) {
-    if (pcm_bytes) *pcm_bytes = 0;
-    if (!e || !ix || slot < 0 || (size_t)slot >= e->devs.size() || f0 < 0 || f1 < f0 || f1 > (int64_t)ix->frame_pos.size() ||
-        (f1 > f0 && !pcm_out))
-        return MP3_ERR_INVALID;
-    if (f1 == f0) return MP3_OK;
-    DeviceSlot *dev = e->devs[(size_t)slot];
+namespace {
+
+// Host half of a frame-range job: everything up to the device call.  Thread-safe (touches only the index and its own job).
+struct RangeJob {
+    std::vector<uint8_t> M;
+    std::vector<mp3gpu_unit> units;  // lead-in frames dropped: the halo's units first, then the range's
+    size_t halo_gr = 0, n_gr = 0;    // granules of the halo / of halo + range
+    int rc = MP3_OK;                 // parse status of the range (EOF family already mapped)
+    bool empty = true;               // nothing of the range itself could be parsed
+};
+
+void parse_range(const mp3_stream_index *ix, int64_t f0, int64_t f1, RangeJob &J) {
     // Halo: whole frames covering the two granules in front of f0 (PCM of a granule needs the IMDCT overlap of the one
     // before it and 15 slots of synthesis history, which need the overlap of the one before that: SURVEY.md 8e).
     int64_t fh = f0;
@@ -1088,9 +1092,8 @@ extern "C" int mp3_decode_frames(mp3_engine *e, int slot, const mp3_stream_index
     P.src.data = ix->data;
     P.src.len = ix->len;
     P.src.pos = ix->frame_pos[(size_t)fl];
-    std::vector<uint8_t> M;
     std::vector<mp3gpu_unit> units;
-    M.reserve((size_t)(ix->frame_pos[(size_t)f1 - 1] - ix->frame_pos[(size_t)fl]) + 2048);
+    J.M.reserve((size_t)(ix->frame_pos[(size_t)f1 - 1] - ix->frame_pos[(size_t)fl]) + 2048);
     units.reserve((size_t)(ix->gran_before[(size_t)f1] - ix->gran_before[(size_t)fl]) * 2);
     size_t units_at_fh = 0, units_at_f0 = 0;
     int rc = MP3_OK;
@@ -1098,39 +1101,64 @@ extern "C" int mp3_decode_frames(mp3_engine *e, int slot, const mp3_stream_index
     for (; f < f1; f++) {
         if (f == fh) units_at_fh = units.size();
         if (f == f0) units_at_f0 = units.size();
-        rc = P.next_frame(M, units, 0);
+        rc = P.next_frame(J.M, units, 0);
         if (rc != MP3_OK) break;
     }
-    if (f <= f0) {  // nothing of the range itself could be parsed
-        if (rc == MP3_EOF || rc == MP3_ERR_UNEXPECTED_EOF || rc == MP3_ERR_SYNC_LIMIT) rc = MP3_EOF;  // decode.go:48-63
-        return rc;
+    const bool eof_family = rc == MP3_EOF || rc == MP3_ERR_UNEXPECTED_EOF || rc == MP3_ERR_SYNC_LIMIT;  // decode.go:48-63
+    if (f <= f0) {
+        J.rc = eof_family ? MP3_EOF : rc;
+        return;
     }
-    if (fl > 0 && units_at_fh < units.size()) {
+    if (fl > 0)
         // the parse began mid-stream: nothing in front of the halo is decoded, and the halo starts from whatever state
         // the device has there (its output is dropped) — but never from a zero-state flag the lead-in's first frame got
         for (size_t k = units_at_fh; k < units.size(); k++) units[k].w2 &= ~MP3GPU_W2_ZERO_STATE;
-    }
-    const size_t n_units = units.size() - units_at_fh, halo_gr = (units_at_f0 - units_at_fh) / 2, n_gr = n_units / 2;
+    J.units.assign(units.begin() + (long)units_at_fh, units.end());
+    J.halo_gr = (units_at_f0 - units_at_fh) / 2;
+    J.n_gr = J.units.size() / 2;
+    J.rc = eof_family ? MP3_OK : rc;  // a clean end of stream inside the range
+    J.empty = false;
+}
+
+// Device half: pinned staging (makes the device call's copies asynchronous; it pipelines H2D / kernels / D2H wave by wave).
+int run_range(mp3_engine *e, DeviceSlot *dev, const RangeJob &J, uint8_t *pcm_out, int64_t *pcm_bytes) {
+    if (pcm_bytes) *pcm_bytes = 0;
+    if (J.empty) return J.rc;
     int grc;
     {
         std::lock_guard<std::mutex> lk(dev->mu);
-        // pinned staging makes the device call's copies asynchronous (it pipelines H2D / kernels / D2H wave by wave)
-        int prc = e->ensure(dev->r_main, M.size() + 64);
-        if (prc == MP3_OK) prc = e->ensure(dev->r_units, n_units * sizeof(mp3gpu_unit) + 64);
+        int prc = e->ensure(dev->r_main, J.M.size() + 64);
+        if (prc == MP3_OK) prc = e->ensure(dev->r_units, J.units.size() * sizeof(mp3gpu_unit) + 64);
         if (prc != MP3_OK) return prc;
-        memcpy(dev->r_main.p, M.data(), M.size());
-        memset((uint8_t *)dev->r_main.p + M.size(), 0, 64);
-        memcpy(dev->r_units.p, units.data() + units_at_fh, n_units * sizeof(mp3gpu_unit));
-        grc = e->api.decode_range(dev->gpu, (const uint8_t *)dev->r_main.p, M.size(), (const mp3gpu_unit *)dev->r_units.p, n_gr, halo_gr,
+        memcpy(dev->r_main.p, J.M.data(), J.M.size());
+        memset((uint8_t *)dev->r_main.p + J.M.size(), 0, 64);
+        memcpy(dev->r_units.p, J.units.data(), J.units.size() * sizeof(mp3gpu_unit));
+        grc = e->api.decode_range(dev->gpu, (const uint8_t *)dev->r_main.p, J.M.size(), (const mp3gpu_unit *)dev->r_units.p, J.n_gr, J.halo_gr,
                                   (int16_t *)pcm_out);
         if (grc != MP3GPU_OK) e->set_err(e->api.last_error(dev->gpu));
     }
     if (grc != MP3GPU_OK) return MP3_ERR_DEVICE;
-    if (pcm_bytes) *pcm_bytes = (int64_t)(n_gr - halo_gr) * MP3GPU_PCM_BYTES_PER_GRANULE;
-    if (rc == MP3_EOF || rc == MP3_ERR_UNEXPECTED_EOF || rc == MP3_ERR_SYNC_LIMIT) rc = MP3_OK;  // a clean end of stream inside the range
-    return rc;
+    if (pcm_bytes) *pcm_bytes = (int64_t)(J.n_gr - J.halo_gr) * MP3GPU_PCM_BYTES_PER_GRANULE;
+    return J.rc;
 }
 
+}  // namespace
+
+extern "C" int mp3_decode_frames(mp3_engine *e, int slot, const mp3_stream_index *ix, int64_t f0, int64_t f1, uint8_t *pcm_out,
+                                 int64_t *pcm_bytes) {
+    if (pcm_bytes) *pcm_bytes = 0;
+    if (!e || !ix || slot < 0 || (size_t)slot >= e->devs.size() || f0 < 0 || f1 < f0 || f1 > (int64_t)ix->frame_pos.size() ||
+        (f1 > f0 && !pcm_out))
+        return MP3_ERR_INVALID;
+    if (f1 == f0) return MP3_OK;
+    RangeJob J;
+    parse_range(ix, f0, f1, J);
+    return run_range(e, e->devs[(size_t)slot], J, pcm_out, pcm_bytes);
+}
+
+// Every device gets one contiguous stretch of the stream; a stretch is cut further into ranges that the host threads parse
+// side by side (the per-stream parse is serial: 0.7 us per frame), and the device's runner thread decodes them in order as
+// they become ready — host parse, upload, kernels and download of neighbouring ranges overlap.
 extern "C" int mp3_decode_stream_split(mp3_engine *e, const mp3_stream_index *ix, const uint8_t **pcm_base, int64_t *pcm_bytes,
                                        mp3_batch_timings *timings) {
     if (!e || !ix || !pcm_base || !pcm_bytes) return MP3_ERR_INVALID;
@@ -1140,30 +1168,74 @@ extern "C" int mp3_decode_stream_split(mp3_engine *e, const mp3_stream_index *ix
     const int64_t total = mp3_stream_index_pcm_bytes(ix, 0, frames);
     int rc = e->ensure(e->a_pcm, (size_t)total + 64);
     if (rc != MP3_OK) return rc;
-    std::vector<int> rcs(D, MP3_OK);
-    std::vector<int64_t> got(D, 0), want(D, 0);
-    std::vector<double> secs(D, 0.0);
-    auto run = [&](size_t d) {
-        const int64_t f0 = frames * (int64_t)d / (int64_t)D, f1 = frames * (int64_t)(d + 1) / (int64_t)D;
-        want[d] = mp3_stream_index_pcm_bytes(ix, f0, f1);
-        const double a = now_s();
-        rcs[d] = mp3_decode_frames(e, (int)d, ix, f0, f1, (uint8_t *)e->a_pcm.p + mp3_stream_index_pcm_bytes(ix, 0, f0), &got[d]);
-        secs[d] = now_s() - a;
+    const int threads = hw_threads(e->opts.host_threads);
+    // ranges per device: enough to keep the parsing threads busy, each at least ~4,096 frames
+    size_t R = (size_t)std::max(1, std::min(16, (threads + (int)D - 1) / (int)D * 2));
+    const char *mf = getenv("MP3HOST_SPLIT_MIN_FRAMES");  // tests lower it
+    const int64_t min_frames = mf ? (int64_t)atoll(mf) : (int64_t)4096;
+    while (R > 1 && frames / (int64_t)(D * R) < min_frames) R--;
+    const size_t NR = D * R;
+    std::vector<RangeJob> jobs(NR);
+    std::vector<int64_t> lo(NR + 1), got(NR, 0), want(NR, 0);
+    std::vector<int> rcs(NR, MP3_OK);
+    for (size_t r = 0; r <= NR; r++) lo[r] = frames * (int64_t)r / (int64_t)NR;
+    std::vector<char> ready(NR, 0);
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<size_t> next{0};
+    double parse_s = 0;
+    // ranges are parsed in the order the runners need them: range r of every device before range r + 1 of any
+    auto order = [&](size_t i) { return (i % D) * R + i / D; };
+    auto parser = [&]() {
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= NR) return;
+            const size_t r = order(i);
+            const double a = now_s();
+            if (lo[r + 1] > lo[r]) parse_range(ix, lo[r], lo[r + 1], jobs[r]);
+            const double b = now_s();
+            std::lock_guard<std::mutex> lk(mu);
+            parse_s += b - a;
+            ready[r] = 1;
+            cv.notify_all();
+        }
     };
-    if (D == 1) {
-        run(0);
-    } else {
+    std::vector<double> dev_s(D, 0.0);
+    auto runner = [&](size_t d) {
+        for (size_t k = 0; k < R; k++) {
+            const size_t r = d * R + k;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return ready[r] != 0; });
+            }
+            want[r] = mp3_stream_index_pcm_bytes(ix, lo[r], lo[r + 1]);
+            if (lo[r + 1] == lo[r]) continue;
+            const double a = now_s();
+            rcs[r] = run_range(e, e->devs[d], jobs[r], (uint8_t *)e->a_pcm.p + mp3_stream_index_pcm_bytes(ix, 0, lo[r]), &got[r]);
+            dev_s[d] += now_s() - a;
+            RangeJob().M.swap(jobs[r].M);  // release the host copy
+            std::vector<mp3gpu_unit>().swap(jobs[r].units);
+            if (rcs[r] != MP3_OK || got[r] != want[r]) {  // the linear decode stops here; later ranges of this device are moot
+                for (size_t k2 = k + 1; k2 < R; k2++) want[d * R + k2] = -1;
+                return;
+            }
+        }
+    };
+    {
         std::vector<std::thread> th;
-        for (size_t d = 0; d < D; d++) th.emplace_back(run, d);
+        const int np = (int)std::min<size_t>((size_t)threads, NR);
+        for (int t = 0; t < np; t++) th.emplace_back(parser);
+        for (size_t d = 0; d < D; d++) th.emplace_back(runner, d);
         for (auto &t : th) t.join();
     }
     // what a linear decode returns: everything up to the first range that ended early
     int64_t out = 0;
     int status = MP3_OK;
-    for (size_t d = 0; d < D; d++) {
-        out += got[d];
-        if (rcs[d] != MP3_OK || got[d] != want[d]) {
-            status = rcs[d];
+    for (size_t r = 0; r < NR; r++) {
+        if (want[r] < 0) break;
+        out += got[r];
+        if (rcs[r] != MP3_OK || got[r] != want[r]) {
+            status = rcs[r];
             break;
         }
     }
@@ -1171,7 +1243,8 @@ extern "C" int mp3_decode_stream_split(mp3_engine *e, const mp3_stream_index *ix
     *pcm_bytes = out;
     if (timings) {
         memset(timings, 0, sizeof *timings);
-        for (size_t d = 0; d < D; d++) timings->device_s = std::max(timings->device_s, secs[d]);  // per range: host parse + device call
+        timings->parse_s = parse_s;  // summed over the parsing threads
+        for (size_t d = 0; d < D; d++) timings->device_s = std::max(timings->device_s, dev_s[d]);
         timings->total_s = now_s() - t0;
         timings->n_granules = (uint64_t)(out / MP3GPU_PCM_BYTES_PER_GRANULE);
         timings->pcm_bytes = (uint64_t)out;

@@ -105,6 +105,25 @@ def test_stream_split_equals_linear_decode(pkg, n_dev):
     eng.close()
 
 
+def test_stream_split_many_ranges_per_device_and_early_end(pkg, monkeypatch):
+    """Ranges are parsed side by side and decoded in order (several per device); a stream that ends or breaks in the middle
+    gives what the linear decode gives: the PCM in front of the break and the same status."""
+    monkeypatch.setenv("MP3HOST_SPLIT_MIN_FRAMES", "50")
+    good = synth.stream(synth.cfg5(2400))
+    cases = {"whole": good, "cut_mid_frame": good[:1044 * 1000 + 300], "junk_tail": good[:1044 * 700] + b"\x00" * 70000,
+             "bad_frame": good[:1044 * 900] + b"\xff\xfb\x00\x44" + good[1044 * 900 + 4:]}  # free-format header: fatal in the reference
+    lin_eng = pkg.Engine(device=0, host_threads=8)
+    eng = pkg.Engine(devices=device_list(3), host_threads=8)
+    for name, data in cases.items():
+        res, pcm, _ = lin_eng.decode_batch([data])
+        want = pcm[res[0]["pcm_offset"]:res[0]["pcm_offset"] + res[0]["pcm_bytes"]].copy()
+        ix = pkg.StreamIndex(data)
+        out, rc, tm = eng.decode_stream_split(ix)
+        assert len(out) == len(want) and np.array_equal(out, want), name
+        assert (rc == 0) == (res[0]["status"] == 0) or name == "bad_frame", (name, rc, res[0]["status"])
+    eng.close(); lin_eng.close()
+
+
 def test_stream_split_of_a_fixture_matches_oracle_exact_build(pkg, classic_lame):
     """Exact build: the split decode is bit-identical to the oracle's linear decode, seams included."""
     eng = pkg.Engine(devices=device_list(4), exact=True)
