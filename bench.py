@@ -210,6 +210,15 @@ def run_reference(args, rank, world):
 class Dist:
     def __init__(self, world, dev):
         self.world, self.dev = world, dev
+        self.cpu_group = None
+        if world > 1:
+            import torch.distributed as dist
+            self.cpu_group = dist.new_group(backend="gloo")  # host-side waits: an NCCL barrier spins a kernel on the waiting GPUs
+
+    def barrier_cpu(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.cpu_group)
 
     def barrier(self):
         if self.world > 1:
@@ -421,6 +430,8 @@ def run_ours(args, rank, world, local_rank):
                                          max(3, args.steps // 2), 3, rank, par, 0 if args.no_cpu_baseline else max(cores * 4, 16))
     eng.close()
     D.barrier()
+    torch.cuda.synchronize()
+    D.barrier_cpu()
 
     # ---- rank 0 alone from here on: the product API (one process, one engine over all N devices) -------------------
     e2e = e2e_cfg4 = cfg5 = None
@@ -455,7 +466,7 @@ def run_ours(args, rank, world, local_rank):
         if not args.no_cfg5:
             cfg5 = run_cfg5(pkg, synth, heng, args, cores, world)
         heng.close()
-    D.barrier()
+    D.barrier_cpu()  # the other ranks wait on the host: their GPUs are idle while rank 0's engine drives them
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
