@@ -227,7 +227,10 @@ k_huffman(const uint8_t *__restrict__ main_data, unsigned long long main_bits, c
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void group_barrier(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
-template <int GW>
+// STAGED = false: nothing is staged; the cursors read main_data itself (GlobalCursor / GlobalWindow, unit_logic.h), whose
+// prefetching register window makes the per-lane global loads as harmless as the shared-memory ones; without staging
+// areas the CTA holds 32 warps next to the code tables instead of about 24.
+template <int GW, bool STAGED>
 __global__ void __launch_bounds__(1024, 1)
 k_huffman_groups(const uint8_t *__restrict__ main_data, unsigned long long main_bits, const mp3gpu_unit *__restrict__ units,
                  long long first_unit, int n_units, DeviceTables T, WaveBufs B, int stage_cap16, unsigned int *__restrict__ tile_counter) {
@@ -250,9 +253,10 @@ k_huffman_groups(const uint8_t *__restrict__ main_data, unsigned long long main_
     for (int i = threadIdx.x; i < 512; i += blockDim.x) s_qlut[i] = T.quad_lut[i];
     __syncthreads();  // the only CTA barrier: the tables are staged
     // this group's block: staging area (+ 16 bytes the FastWindow prefetch may touch), sort bins, lo / hi / tile, work order
-    const int group_words = stage_cap16 * 4 + 4 + 40 + 4 + TILE / 2;
+    const int stage_words = STAGED ? stage_cap16 * 4 + 4 : 0;
+    const int group_words = stage_words + 40 + 4 + TILE / 2;
     uint32_t *const s_stage = s_dyn32 + T.huff_lut_n / 2 + group * group_words;  // huff_lut_n is a multiple of 8 entries: 16-byte aligned
-    unsigned int *const s_bin = s_stage + stage_cap16 * 4 + 4;
+    unsigned int *const s_bin = s_stage + stage_words;
     unsigned int *const s_misc = s_bin + 40;  // [0] lo16, [1] hi16, [2] tile
     uint16_t *const s_order = reinterpret_cast<uint16_t *>(s_misc + 4);
     const int bar = 1 + group;  // named barrier of this group (0 is __syncthreads)
@@ -283,19 +287,23 @@ k_huffman_groups(const uint8_t *__restrict__ main_data, unsigned long long main_
                 key[j] = 37;
                 if (u_valid(u.w2)) {
                     key[j] = 36 - ((u_p23len(u.w0) == 0 ? 0 : imin(u_bigval(u.w0), 288)) >> 3);
-                    uint32_t l, h;
-                    stage_reach(u, main_bits, &l, &h);
-                    lo16 = l < lo16 ? l : lo16;
-                    hi16 = h > hi16 ? h : hi16;
+                    if (STAGED) {
+                        uint32_t l, h;
+                        stage_reach(u, main_bits, &l, &h);
+                        lo16 = l < lo16 ? l : lo16;
+                        hi16 = h > hi16 ? h : hi16;
+                    }
                 }
             }
             rank[j] = atomicAdd(&s_bin[key[j]], 1u);
         }
-        lo16 = __reduce_min_sync(0xffffffffu, lo16);
-        hi16 = __reduce_max_sync(0xffffffffu, hi16);
-        if (lane == 0) {
-            atomicMin(&s_misc[0], lo16);
-            atomicMax(&s_misc[1], hi16);
+        if (STAGED) {
+            lo16 = __reduce_min_sync(0xffffffffu, lo16);
+            hi16 = __reduce_max_sync(0xffffffffu, hi16);
+            if (lane == 0) {
+                atomicMin(&s_misc[0], lo16);
+                atomicMax(&s_misc[1], hi16);
+            }
         }
         group_barrier(bar, GT);
         if (wg == 0) {  // exclusive scan of the 39 bins: lanes 0..31 hold bins 0..31, lanes 0..6 also bins 32..38
@@ -322,7 +330,9 @@ k_huffman_groups(const uint8_t *__restrict__ main_data, unsigned long long main_
         S.sw = SmemRef::of(s_stage);
         S.gw = reinterpret_cast<const uint32_t *>(main_data);
         S.main_bits = main_bits;
-        {
+        S.n_words = 0;
+        S.lo_word = 0;
+        if (STAGED) {
             const uint32_t lo = s_misc[0];
             const uint32_t hi = s_misc[1] < main16 ? s_misc[1] : main16;
             uint32_t n16 = hi > lo ? hi - lo : 0u;  // no valid unit in the tile: lo = ~0
@@ -354,7 +364,8 @@ k_huffman_groups(const uint8_t *__restrict__ main_data, unsigned long long main_
                 } else {
                     uint32_t pk[8];
                     uint32_t *out = reinterpret_cast<uint32_t *>(B.is16 + (size_t)ul * 576);
-                    const uint32_t meta = huffman_unit_staged(T, s_lut, s_qlut, s_desc, s_quad, S, units, first_unit + ul, pk, out);
+                    const uint32_t meta = STAGED ? huffman_unit_staged(T, s_lut, s_qlut, s_desc, s_quad, S, units, first_unit + ul, pk, out)
+                                                 : huffman_unit_global(T, s_lut, s_qlut, s_desc, s_quad, S, units, first_unit + ul, pk, out);
                     uint4 *dst = reinterpret_cast<uint4 *>(B.sfpack + (size_t)ul * 8);
                     dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
