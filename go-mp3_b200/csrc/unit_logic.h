@@ -397,8 +397,10 @@ struct FastWindow {
 // used, which covers an L1 or L2 hit; the refill is predicated here too.  A cursor in front of the frame's buffer end
 // reads at most four words past it: inside main_data's 64 bytes of tail padding.
 struct GlobalWindow {
-    uint32_t w0, w1, w2;
-    const uint32_t *next;  // the word after w2
+    uint32_t w0, w1;       // current window, big-endian bit order
+    uint32_t w2raw;        // the word after w1 AS LOADED: it is byte-swapped when it moves into the window, a whole word of code
+                           // bits later, so that nothing waits for the load (a swap right behind the load would)
+    const uint32_t *next;  // the word after w2raw
     int off;               // cursor inside w0
     int p;                 // the cursor's p, kept alongside for the loop bounds
 #if MP3GPU_CHECKED
@@ -408,11 +410,11 @@ struct GlobalWindow {
         const uint32_t *q = bc.gbase + (bc.p >> 5);
 #if MP3GPU_CHECKED
         words_left = (long long)bc.gwords - (long long)bc.gword0 - (bc.p >> 5) - 3;
-        if (!MP3_CHECK(bc.p >= 0 && words_left >= 0, bc.p)) { w0 = w1 = w2 = 0; next = bc.gbase; off = 0; p = bc.p; words_left = 0; return; }
+        if (!MP3_CHECK(bc.p >= 0 && words_left >= 0, bc.p)) { w0 = w1 = w2raw = 0; next = bc.gbase; off = 0; p = bc.p; words_left = 0; return; }
 #endif
         w0 = be32(load_raw32(q));
         w1 = be32(load_raw32(q + 1));
-        w2 = be32(load_raw32(q + 2));
+        w2raw = load_raw32(q + 2);
         next = q + 3;
         off = bc.p & 31;
         p = bc.p;
@@ -424,12 +426,12 @@ struct GlobalWindow {
         if (off >= 32) {
             off -= 32;
             w0 = w1;
-            w1 = w2;
+            w1 = be32(w2raw);
 #if MP3GPU_CHECKED
             if (!MP3_CHECK(words_left > 0, p)) return;
             words_left--;
 #endif
-            w2 = be32(load_raw32(next));
+            w2raw = load_raw32(next);
             next++;
         }
     }
