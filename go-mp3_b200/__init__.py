@@ -214,7 +214,8 @@ def gpu_lib(exact=False) -> C.CDLL:
     libmp3gpu_checked.so ("checked"), with prototypes set."""
     if exact in _gpu:
         return _gpu[exact]
-    L = C.CDLL(_lib_path({False: "libmp3gpu.so", True: "libmp3gpu_exact.so", "checked": "libmp3gpu_checked.so"}[exact]))
+    name = {False: "libmp3gpu.so", True: "libmp3gpu_exact.so", "checked": "libmp3gpu_checked.so"}[exact]
+    L = C.CDLL(_lib_path(name))
     vp, sz = C.c_void_p, C.c_size_t
     L.mp3gpu_create.argtypes = [C.c_int, C.POINTER(GpuOpts), C.POINTER(vp)]
     L.mp3gpu_create.restype = C.c_int

@@ -217,167 +217,6 @@ k_huffman(const uint8_t *__restrict__ main_data, unsigned long long main_bits, c
 }
 
 // ------------------------------------------------------------------------------------------
-// K1, group tiles: GW warps share one tile of GW * 64 consecutive units — one contiguous staged stretch, one counting
-// sort over the whole tile — and synchronise among themselves only (named barrier of GW * 32 threads); the groups of a
-// CTA share nothing but the code tables.  The tile's units sorted by length form 2 * GW batches of 32; warp w decodes
-// batch w and then batch 2 GW - 1 - w (a long one and a short one), so the warps of a group finish together and the
-// lanes of a batch hold units of nearly equal length.  This keeps what the per-CTA version had (sorting over 256 units:
-// lanes per instruction 19.6 against 16 with 64-unit tiles) without what killed it (CTA-wide barriers with one batch
-// per warp: a third of the stall samples), at the same shared memory per warp as the 64-unit tiles.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void group_barrier(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
-
-// STAGED = false: nothing is staged; the cursors read main_data itself (GlobalCursor / GlobalWindow, unit_logic.h), whose
-// prefetching register window makes the per-lane global loads as harmless as the shared-memory ones; without staging
-// areas the CTA holds 32 warps next to the code tables instead of about 24.
-template <int GW, bool STAGED>
-__global__ void __launch_bounds__(1024, 1)
-k_huffman_groups(const uint8_t *__restrict__ main_data, unsigned long long main_bits, const mp3gpu_unit *__restrict__ units,
-                 long long first_unit, int n_units, DeviceTables T, WaveBufs B, int stage_cap16, unsigned int *__restrict__ tile_counter) {
-    extern __shared__ __align__(16) uint32_t s_dyn32[];  // pair-tree code tables (uint16 entries), then one block per group
-    __shared__ uint64_t s_quad[256];
-    __shared__ uint32_t s_qlut[512];
-    __shared__ uint32_t s_desc[34];
-    constexpr int GT = GW * 32;        // threads of a group
-    constexpr int TILE = GW * 64;      // units of a tile: two per thread
-    const int lane = threadIdx.x & 31, group = threadIdx.x / GT, tg = threadIdx.x % GT, wg = tg >> 5;
-    const SmemRef s_lut = SmemRef::of(s_dyn32);
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(T.huff_lut);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_dyn32);
-#pragma unroll 4
-        for (int i = threadIdx.x; i < T.huff_lut_n / 8; i += blockDim.x) dst[i] = __ldg(src + i);
-    }
-    if (threadIdx.x < 34) s_desc[threadIdx.x] = T.huff_desc[threadIdx.x];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_quad[i] = T.quad_signs[i];
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_qlut[i] = T.quad_lut[i];
-    __syncthreads();  // the only CTA barrier: the tables are staged
-    // this group's block: staging area (+ 16 bytes the FastWindow prefetch may touch), sort bins, lo / hi / tile, work order
-    const int stage_words = STAGED ? stage_cap16 * 4 + 4 : 0;
-    const int group_words = stage_words + 40 + 4 + TILE / 2;
-    uint32_t *const s_stage = s_dyn32 + T.huff_lut_n / 2 + group * group_words;  // huff_lut_n is a multiple of 8 entries: 16-byte aligned
-    unsigned int *const s_bin = s_stage + stage_words;
-    unsigned int *const s_misc = s_bin + 40;  // [0] lo16, [1] hi16, [2] tile
-    uint16_t *const s_order = reinterpret_cast<uint16_t *>(s_misc + 4);
-    const int bar = 1 + group;  // named barrier of this group (0 is __syncthreads)
-    const uint32_t main16 = (uint32_t)(((main_bits >> 3) + 48) >> 4);  // 16-byte chunks that may be read: main_data is followed by 64 bytes of padding
-    const int n_tiles = (n_units + TILE - 1) / TILE;
-#pragma unroll 1
-    for (;;) {
-        if (tg < 40) s_bin[tg] = 0;
-        if (tg == 0) {
-            s_misc[0] = 0xffffffffu;
-            s_misc[1] = 0u;
-            s_misc[2] = atomicAdd(tile_counter, 1u);
-        }
-        group_barrier(bar, GT);  // also: the previous tile's s_order / s_stage reads are done
-        const int tile = (int)s_misc[2];
-        if (tile >= n_tiles) break;
-        const int base = tile * TILE;
-        // ---- the stretch of main data the tile reads, and the work order inside the tile ---------------------
-        int key[2];
-        unsigned int rank[2];
-        uint32_t lo16 = 0xffffffffu, hi16 = 0u;
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            key[j] = 38;  // beyond the wave
-            const int ul0 = base + j * GT + tg;
-            if (ul0 < n_units && MP3_CHECK(first_unit + ul0 >= 0 && first_unit + ul0 < B.units_total, first_unit + ul0)) {
-                const mp3gpu_unit u = units[first_unit + ul0];
-                key[j] = 37;
-                if (u_valid(u.w2)) {
-                    key[j] = 36 - ((u_p23len(u.w0) == 0 ? 0 : imin(u_bigval(u.w0), 288)) >> 3);
-                    if (STAGED) {
-                        uint32_t l, h;
-                        stage_reach(u, main_bits, &l, &h);
-                        lo16 = l < lo16 ? l : lo16;
-                        hi16 = h > hi16 ? h : hi16;
-                    }
-                }
-            }
-            rank[j] = atomicAdd(&s_bin[key[j]], 1u);
-        }
-        if (STAGED) {
-            lo16 = __reduce_min_sync(0xffffffffu, lo16);
-            hi16 = __reduce_max_sync(0xffffffffu, hi16);
-            if (lane == 0) {
-                atomicMin(&s_misc[0], lo16);
-                atomicMax(&s_misc[1], hi16);
-            }
-        }
-        group_barrier(bar, GT);
-        if (wg == 0) {  // exclusive scan of the 39 bins: lanes 0..31 hold bins 0..31, lanes 0..6 also bins 32..38
-            const unsigned int c0 = s_bin[lane];
-            unsigned int x = c0;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned int y = __shfl_up_sync(0xffffffffu, x, d);
-                if (lane >= d) x += y;
-            }
-            const unsigned int total32 = __shfl_sync(0xffffffffu, x, 31);
-            const unsigned int c1 = lane < 7 ? s_bin[32 + lane] : 0u;
-            unsigned int z = c1;
-#pragma unroll
-            for (int d = 1; d < 8; d <<= 1) {
-                const unsigned int y = __shfl_up_sync(0xffffffffu, z, d);
-                if (lane >= d) z += y;
-            }
-            __syncwarp();
-            s_bin[lane] = x - c0;
-            if (lane < 7) s_bin[32 + lane] = total32 + z - c1;
-        }
-        StageCtx S;
-        S.sw = SmemRef::of(s_stage);
-        S.gw = reinterpret_cast<const uint32_t *>(main_data);
-        S.main_bits = main_bits;
-        S.n_words = 0;
-        S.lo_word = 0;
-        if (STAGED) {
-            const uint32_t lo = s_misc[0];
-            const uint32_t hi = s_misc[1] < main16 ? s_misc[1] : main16;
-            uint32_t n16 = hi > lo ? hi - lo : 0u;  // no valid unit in the tile: lo = ~0
-            if (n16 > (uint32_t)stage_cap16) n16 = (uint32_t)stage_cap16;
-            S.n_words = (int)(n16 * 4);
-            S.lo_word = (unsigned long long)lo * 4ull;
-            const uint4 *src = reinterpret_cast<const uint4 *>(main_data) + lo;
-            uint4 *dst = reinterpret_cast<uint4 *>(s_stage);
-#pragma unroll 4
-            for (uint32_t i = tg; i < n16; i += GT) {
-                if (!MP3_CHECK(lo + i < main16, lo + i)) continue;
-                uint4 v = __ldg(src + i);
-                v.x = be32(v.x); v.y = be32(v.y); v.z = be32(v.z); v.w = be32(v.w);
-                dst[i] = v;
-            }
-        }
-        group_barrier(bar, GT);
-#pragma unroll
-        for (int j = 0; j < 2; j++) s_order[s_bin[key[j]] + rank[j]] = (uint16_t)(j * GT + tg);
-        group_barrier(bar, GT);
-        // ---- decode: warp w takes batch w (long units), then batch 2 GW - 1 - w (short ones) ------------------
-#pragma unroll 1
-        for (int pass = 0; pass < 2; pass++) {
-            const int batch = pass == 0 ? wg : 2 * GW - 1 - wg;
-            const int ul = base + (int)s_order[batch * 32 + lane];  // wave-local unit index
-            if (ul < n_units && MP3_CHECK(ul >= 0 && ul < 2 * B.n_gran && first_unit + ul < B.units_total, ul)) {
-                if (!u_valid(units[first_unit + ul].w2)) {
-                    B.meta[ul] = 0;
-                } else {
-                    uint32_t pk[8];
-                    uint32_t *out = reinterpret_cast<uint32_t *>(B.is16 + (size_t)ul * 576);
-                    const uint32_t meta = STAGED ? huffman_unit_staged(T, s_lut, s_qlut, s_desc, s_quad, S, units, first_unit + ul, pk, out)
-                                                 : huffman_unit_global(T, s_lut, s_qlut, s_desc, s_quad, S, units, first_unit + ul, pk, out);
-                    uint4 *dst = reinterpret_cast<uint4 *>(B.sfpack + (size_t)ul * 8);
-                    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                    B.meta[ul] = meta;
-                }
-            }
-            __syncwarp();
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // k_hybrid = K2 + K3: one warp marches through a segment of consecutive granules (both channels).
 //
 //   K2  requantise + reorder + stereo + alias reduction      frame.go:140-452   lane = spectral line (mod 32)

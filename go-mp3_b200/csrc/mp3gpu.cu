@@ -48,8 +48,6 @@ struct mp3gpu_ctx {
     int lut_bytes = 0;
     int smem_per_sm = 0, smem_per_cta_max = 0;  // shared-memory budget (bytes) of an SM / of one CTA (opt-in maximum)
     int huff_static_smem = 0;                   // static shared memory of k_huffman
-    int k1_group_warps = 4;  // warps sharing a tile in k_huffman_groups (0: per-warp tiles, k_huffman)
-    bool k1_staged = true;   // k_huffman_groups: stage the tile's stretch in shared memory (false: read main_data through register windows)
     int k1_upw_override = 0, k1_warps_override = 0, k1_stage_pct_override = 0;  // experiments: MP3GPU_K1_UPW / _WARPS / _STAGE_PCT
     // workspace for one wave (+1 granule look-back where needed)
     int16_t *d_is16 = nullptr;
@@ -276,15 +274,6 @@ extern "C" int mp3gpu_create(int device, const mp3gpu_opts *opts, mp3gpu_ctx **o
             if (const char *e = getenv("MP3GPU_SUB")) ctx->sub_granules = std::max(0, atoi(e));
             if (const char *e = getenv("MP3GPU_SUB_SEG")) ctx->sub_seg_len = std::max(2, atoi(e));
             if (const char *e = getenv("MP3GPU_SUB_SYN")) ctx->sub_syn_blocks = std::max(1, atoi(e));
-            const int dyn_max = ctx->smem_per_cta_max - ctx->huff_static_smem;
-            CK(cudaFuncSetAttribute(k_huffman_groups<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
-            CK(cudaFuncSetAttribute(k_huffman_groups<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
-            CK(cudaFuncSetAttribute(k_huffman_groups<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
-            CK(cudaFuncSetAttribute(k_huffman_groups<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
-            CK(cudaFuncSetAttribute(k_huffman_groups<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
-            CK(cudaFuncSetAttribute(k_huffman_groups<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
-            if (const char *e = getenv("MP3GPU_K1_GROUP")) ctx->k1_group_warps = atoi(e);
-            if (const char *e = getenv("MP3GPU_K1_STAGED")) ctx->k1_staged = atoi(e) != 0;
             if (const char *e = getenv("MP3GPU_K1_WARPS")) ctx->k1_warps_override = atoi(e);
             if (const char *e = getenv("MP3GPU_K1_STAGE_PCT")) ctx->k1_stage_pct_override = atoi(e);
         }
@@ -361,40 +350,6 @@ static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, size_t main_len, 
         const double avg = bytes_per_unit > 1.0 ? bytes_per_unit : 1.0;
         const int budget = ctx->smem_per_cta_max - ctx->huff_static_smem - ctx->lut_bytes;
         const int pct = ctx->k1_stage_pct_override ? ctx->k1_stage_pct_override : 125;
-        const int gw = ctx->k1_group_warps;
-        if (!ctx->k1_staged && (gw == 4 || gw == 8 || gw == 16)) {
-            // nothing staged: groups of gw warps sort a tile of gw * 64 units and read main_data through register windows
-            const int tile = gw * 64;
-            const int fixed = 160 + 16 + tile * 2;
-            int groups = std::min(32 / gw, 15);
-            if (ctx->k1_warps_override) groups = std::min(groups, std::max(1, ctx->k1_warps_override / gw));
-            const int tiles = (nu + tile - 1) / tile;
-            const int grid = std::min((tiles + groups - 1) / groups, ctx->sm_count);
-            const size_t dyn = (size_t)ctx->lut_bytes + (size_t)groups * (size_t)fixed;
-            CK(cudaMemsetAsync(ctx->d_counter + 1, 0, sizeof(unsigned int), s));
-            if (gw == 4) k_huffman_groups<4, false><<<grid, groups * gw * 32, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, 0, ctx->d_counter + 1);
-            else if (gw == 8) k_huffman_groups<8, false><<<grid, groups * gw * 32, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, 0, ctx->d_counter + 1);
-            else k_huffman_groups<16, false><<<grid, groups * gw * 32, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, 0, ctx->d_counter + 1);
-        } else if (gw == 2 || gw == 4 || gw == 8) {
-            // groups of gw warps share a tile of gw * 64 units: staging sized from the call's average bytes per unit (x 1.25 for
-            // tile-to-tile variation; a tile that needs more reads its tail from global memory); as many groups as fit
-            // next to the code tables (at most 15: named barriers)
-            const int tile = gw * 64;
-            int stage = ((int)(avg * tile * pct / 100.0) + 1024 + 15) & ~15;
-            const int fixed = 16 + 160 + 16 + tile * 2;
-            const int max_stage = budget / 2 - fixed;
-            if (stage > max_stage) stage = max_stage & ~15;
-            int groups = std::min(std::min(32 / gw, 15), budget / (stage + fixed));
-            if (ctx->k1_warps_override) groups = std::min(groups, std::max(1, ctx->k1_warps_override / gw));
-            if (groups < 1) groups = 1;
-            const int tiles = (nu + tile - 1) / tile;
-            const int grid = std::min((tiles + groups - 1) / groups, ctx->sm_count);
-            const size_t dyn = (size_t)ctx->lut_bytes + (size_t)groups * (size_t)(stage + fixed);
-            CK(cudaMemsetAsync(ctx->d_counter + 1, 0, sizeof(unsigned int), s));
-            if (gw == 2) k_huffman_groups<2, true><<<grid, groups * gw * 32, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, stage / 16, ctx->d_counter + 1);
-            else if (gw == 4) k_huffman_groups<4, true><<<grid, groups * gw * 32, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, stage / 16, ctx->d_counter + 1);
-            else k_huffman_groups<8, true><<<grid, groups * gw * 32, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, stage / 16, ctx->d_counter + 1);
-        } else {
         int upw = 64, warps = 0, cap16 = 0;
         for (int pass = 0; pass < 2; pass++) {
             upw = pass == 0 ? 64 : 32;
@@ -415,7 +370,6 @@ static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, size_t main_len, 
         CK(cudaMemsetAsync(ctx->d_counter + 1, 0, sizeof(unsigned int), s));
         if (upw == 64) k_huffman<64><<<grid, warps * 32, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, cap16, ctx->d_counter + 1);
         else k_huffman<32><<<grid, warps * 32, dyn, s>>>(d_main, main_bits, d_units, first * 2, nu, ctx->T, B, cap16, ctx->d_counter + 1);
-        }
     }
     if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][1], s));
     const int sub = (ctx->sub_granules > 0 && !ctx->d_tap_xr) ? ctx->sub_granules : 0;

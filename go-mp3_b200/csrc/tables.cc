@@ -115,10 +115,10 @@ uint32_t quad_leaf(const huff_code_t &c) {
     return (uint32_t)q | ((uint32_t)c.hlen << 16) | ((uint32_t)(c.hlen + signs) << 26);
 }
 void fill_quad_root(uint32_t *root, const huff_code_t *codes, int n) {
-    for (uint32_t idx = 0; idx < (1u << kHuffRootBits); idx++) {
+    for (uint32_t idx = 0; idx < (1u << kQuadRootBits); idx++) {
         int found = -1;
         for (int i = 0; i < n; i++)
-            if (codes[i].hlen <= kHuffRootBits && (idx >> (kHuffRootBits - codes[i].hlen)) == codes[i].hcod) { found = i; break; }
+            if (codes[i].hlen <= kQuadRootBits && (idx >> (kQuadRootBits - codes[i].hlen)) == codes[i].hcod) { found = i; break; }
         if (found < 0) throw std::runtime_error("count1 tree not complete within the root table");
         root[idx] = quad_leaf(codes[found]);
     }

@@ -37,7 +37,11 @@ constexpr int kNumCfg = 6;      // cfg = lsf*3 + sampling_frequency index
 //          bits 16..20 tree bits of the code word
 //          bits 26..30 tree bits + sign bits
 // Table descriptor (uint32): bits 0..23 = byte offset of the tree's root table in its LUT, bits 24..27 = linbits.
-constexpr int kHuffRootBits = 8;
+#ifndef MP3_HUFF_ROOT_BITS
+#define MP3_HUFF_ROOT_BITS 8
+#endif
+constexpr int kHuffRootBits = MP3_HUFF_ROOT_BITS;  // pair trees
+constexpr int kQuadRootBits = 8;                   // count1 trees (at most 6 tree bits)
 #ifndef MP3_HUFF_SUB_BITS
 #define MP3_HUFF_SUB_BITS 8
 #endif

@@ -392,62 +392,6 @@ struct FastWindow {
     }
 };
 
-// The same window over main_data itself (no staging): the words come from global memory through L1, byte-swapped as
-// they arrive.  The prefetched third word is requested a whole word of code bits (several code words) before it is
-// used, which covers an L1 or L2 hit; the refill is predicated here too.  A cursor in front of the frame's buffer end
-// reads at most four words past it: inside main_data's 64 bytes of tail padding.
-struct GlobalWindow {
-    uint32_t w0, w1;       // current window, big-endian bit order
-    uint32_t w2raw;        // the word after w1 AS LOADED: it is byte-swapped when it moves into the window, a whole word of code
-                           // bits later, so that nothing waits for the load (a swap right behind the load would)
-    const uint32_t *next;  // the word after w2raw
-    int off;               // cursor inside w0
-    int p;                 // the cursor's p, kept alongside for the loop bounds
-#if MP3GPU_CHECKED
-    long long words_left;  // words that may still be loaded from `next` on
-#endif
-    MP3_HD void open(const StagedCursor &bc) {
-        const uint32_t *q = bc.gbase + (bc.p >> 5);
-#if MP3GPU_CHECKED
-        words_left = (long long)bc.gwords - (long long)bc.gword0 - (bc.p >> 5) - 3;
-        if (!MP3_CHECK(bc.p >= 0 && words_left >= 0, bc.p)) { w0 = w1 = w2raw = 0; next = bc.gbase; off = 0; p = bc.p; words_left = 0; return; }
-#endif
-        w0 = be32(load_raw32(q));
-        w1 = be32(load_raw32(q + 1));
-        w2raw = load_raw32(q + 2);
-        next = q + 3;
-        off = bc.p & 31;
-        p = bc.p;
-    }
-    MP3_HD uint32_t peek() const { return funnel_l(w0, w1, off); }
-    MP3_HD void advance(int n) {  // 0 <= n < 32
-        off += n;
-        p += n;
-        if (off >= 32) {
-            off -= 32;
-            w0 = w1;
-            w1 = be32(w2raw);
-#if MP3GPU_CHECKED
-            if (!MP3_CHECK(words_left > 0, p)) return;
-            words_left--;
-#endif
-            w2raw = load_raw32(next);
-            next++;
-        }
-    }
-};
-
-// A StagedCursor with nothing staged: the careful reads go to main_data word by word (its fallback), the fast loops run
-// on a GlobalWindow, bounded by the frame's buffer end alone.
-struct GlobalCursor : StagedCursor {
-    MP3_HD void init(const StageCtx &S, unsigned long long bit_start, int buf_end_rel) {
-        StagedCursor::init(S, bit_start, buf_end_rel);  // S.n_words == 0: sidx0 is "not staged"
-        fast_end = lim > 0 ? end : -(1 << 30);
-    }
-};
-template <class BC> struct WindowOf { typedef FastWindow type; };
-template <> struct WindowOf<GlobalCursor> { typedef GlobalWindow type; };
-
 // ---- Huffman code words (LUT entry layout: tables.h) -------------------------------------------------------------
 // the top (n mod 32) bits of x, as a number
 #if defined(__CUDA_ARCH__)
@@ -455,7 +399,11 @@ MP3_HD uint32_t hi_bits_mod32(uint32_t x, uint32_t n) { return __funnelshift_l(x
 #else
 MP3_HD uint32_t hi_bits_mod32(uint32_t x, uint32_t n) { n &= 31; return n ? x >> (32 - n) : 0u; }
 #endif
-constexpr int kRootBits = 8;  // == tables.h kHuffRootBits
+#ifndef MP3_HUFF_ROOT_BITS
+#define MP3_HUFF_ROOT_BITS 8
+#endif
+constexpr int kRootBits = MP3_HUFF_ROOT_BITS;  // == tables.h kHuffRootBits (pair trees)
+constexpr int kQuadBits = 8;                   // == tables.h kQuadRootBits (count1 trees)
 // x << (n mod 32): the LUT's shift-count fields are used without masking their neighbours off
 #if defined(__CUDA_ARCH__)
 MP3_HD uint32_t shl_mod32(uint32_t x, uint32_t n) { return __funnelshift_l(0u, x, n); }  // the funnel shift wraps its count itself
@@ -524,8 +472,8 @@ MP3_HD uint32_t huff_pair(SmemRef tree, LinbitsFn linbits_of, BC &bc) {
 
 // The same pair where nothing can touch the buffer end (FastWindow: the cursor is at p <= fast_end - 47): no refused reads, no
 // clamp, no load on the dependency chain.
-template <class WIN, class LinbitsFn>
-MP3_HD uint32_t huff_pair_fast(SmemRef tree, LinbitsFn linbits_of, WIN &fw) {
+template <class LinbitsFn>
+MP3_HD uint32_t huff_pair_fast(SmemRef tree, LinbitsFn linbits_of, FastWindow &fw) {
     const int e = huff_lookup16(tree, fw.peek());
     if (e < 0) {
         const int other = (e >> 7) & 15;
@@ -550,7 +498,7 @@ MP3_HD uint32_t huff_pair_fast(SmemRef tree, LinbitsFn linbits_of, WIN &fw) {
 template <class BC>
 MP3_HD void huff_quad(const uint32_t *qlut, const uint64_t *quad_signs, uint32_t d, BC &bc, uint32_t &vw, uint32_t &xy) {
     const uint32_t wd = bc.peek32();
-    const uint32_t e = lut_at(qlut, d + ((wd >> (32 - kRootBits)) << 2));  // <= 6 tree bits, then up to 4 sign bits
+    const uint32_t e = lut_at(qlut, d + ((wd >> (32 - kQuadBits)) << 2));  // <= 6 tree bits, then up to 4 sign bits
     const uint32_t four = shl_mod32(wd, e >> 16) >> 28;
     const uint64_t r = quad_signs[((e & 0xf) << 4) | four];
     bc.skip((int)(e >> 26));
@@ -742,8 +690,7 @@ MP3_HD uint32_t huff_pair_at(const HuffRegions &R, int k, BC &bc) {
     return huff_pair(in0 ? R.t0 : (in1 ? R.t1 : R.t2),
                      [&] { return (int)((R.lin >> (in0 ? 0 : (in1 ? 4 : 8))) & 0xf); }, bc);
 }
-template <class WIN>
-MP3_HD uint32_t huff_pair_fast_at(const HuffRegions &R, int k, WIN &fw) {
+MP3_HD uint32_t huff_pair_fast_at(const HuffRegions &R, int k, FastWindow &fw) {
     const bool in0 = k < R.r1h, in1 = k < R.r2h;
     return huff_pair_fast(in0 ? R.t0 : (in1 ? R.t1 : R.t2),
                           [&] { return (int)((R.lin >> (in0 ? 0 : (in1 ? 4 : 8))) & 0xf); }, fw);
@@ -841,7 +788,7 @@ MP3_HD uint32_t huffman_unit_t(const DeviceTables &T, SmemRef lut, const uint32_
         uint4 *dst4 = reinterpret_cast<uint4 *>(is_out);
         const int lim4 = bc.fast_end - 4 * 47, lim1 = bc.fast_end - 47;
         if (bc.p <= lim1 && R.nbig > 0) {
-            typename WindowOf<BC>::type fw;
+            FastWindow fw;
             fw.open(bc);
             while (k + 4 <= R.nbig && fw.p <= lim4) {
                 uint4 v;
@@ -872,11 +819,11 @@ MP3_HD uint32_t huffman_unit_t(const DeviceTables &T, SmemRef lut, const uint32_
             // a quadruple takes at most 6 + 4 = 10 bits; inside the fast range pos() is p - off0
             const int p_end = bc.off0 + bit_pos_end, limq = bc.fast_end - 10;
             if (is_pos <= 572 && bc.p <= p_end && bc.p <= limq) {
-                typename WindowOf<BC>::type fw;
+                FastWindow fw;
                 fw.open(bc);
                 do {
                     const uint32_t wd = fw.peek();
-                    const uint32_t e = lut_at(qlut, dq + ((wd >> (32 - kRootBits)) << 2));
+                    const uint32_t e = lut_at(qlut, dq + ((wd >> (32 - kQuadBits)) << 2));
                     const uint32_t four = shl_mod32(wd, e >> 16) >> 28;
                     const uint64_t r = quad_signs[((e & 0xf) << 4) | four];
                     fw.advance((int)(e >> 26));
@@ -908,13 +855,6 @@ MP3_HD uint32_t huffman_unit(const DeviceTables &T, SmemRef lut, const uint32_t 
     return huffman_unit_t<BitCursor>(T, lut, qlut, huff_desc, quad_signs, units, unit_index,
                                      [&](BitCursor &c, uint64_t bit_start, int buf_end_rel) { c.init(main_data, main_bits, bit_start, buf_end_rel); },
                                      pk, is_out);
-}
-// Nothing staged: careful reads and fast windows straight from main_data (S.n_words must be 0).
-MP3_HD uint32_t huffman_unit_global(const DeviceTables &T, SmemRef lut, const uint32_t *qlut, const uint32_t *huff_desc, const uint64_t *quad_signs,
-                                    const StageCtx &S, const mp3gpu_unit *units, long long unit_index, uint32_t *pk, uint32_t *is_out) {
-    return huffman_unit_t<GlobalCursor>(T, lut, qlut, huff_desc, quad_signs, units, unit_index,
-                                        [&](GlobalCursor &c, uint64_t bit_start, int buf_end_rel) { c.init(S, bit_start, buf_end_rel); },
-                                        pk, is_out);
 }
 // The staged cursor over one stretch (k_huffman's per-unit call; tests/hostemu emulates the tiling).
 MP3_HD uint32_t huffman_unit_staged(const DeviceTables &T, SmemRef lut, const uint32_t *qlut, const uint32_t *huff_desc, const uint64_t *quad_signs,

@@ -124,33 +124,6 @@ void emu_huffman_staged(const uint8_t *main_data, unsigned long long main_bits, 
     }
 }
 
-// K1 with nothing staged: GlobalCursor / GlobalWindow straight over main_data (k_huffman_groups<GW, false>).
-void emu_huffman_global(const uint8_t *main_data, unsigned long long main_bits, const mp3gpu_unit *units, long long n_units, int16_t *is16,
-                        uint32_t *meta, uint8_t *scalefac) {
-    ensure();
-    StageCtx S;
-    S.sw = SmemRef::of(main_data);
-    S.n_words = 0;
-    S.lo_word = 0;
-    S.gw = reinterpret_cast<const uint32_t *>(main_data);
-    S.main_bits = main_bits;
-    for (long long u = 0; u < n_units; u++) {
-        memset(is16 + u * 576, 0, 576 * sizeof(int16_t));
-        memset(scalefac + u * 64, 0, 64);
-        meta[u] = 0;
-        if (!u_valid(units[u].w2)) continue;
-        uint32_t pk[8];
-        alignas(16) uint32_t out[288 + 4];
-        memset(out, 0, sizeof out);
-        uint32_t m = huffman_unit_global(g_T, SmemRef::of(g_T.huff_lut), g_T.quad_lut, g_T.huff_desc, g_T.quad_signs, S, units, u, pk, out);
-        meta[u] = m;
-        int c1 = (int)(m & 0x3ff);
-        for (int i = 0; i < c1; i++) is16[u * 576 + i] = (int16_t)((out[i >> 1] >> (16 * (i & 1))) & 0xffff);
-        for (int k = 0; k < 64; k++) scalefac[u * 64 + k] = (uint8_t)sf_nib(pk, k);
-        scalefac[u * 64 + 61] = (uint8_t)((m >> 10) & 1);
-    }
-}
-
 // K2 on the CPU, same order of operations as k_requant: xr [n_granules][2][576] after
 // requantise + reorder + stereo + alias reduction, index sb*18+i.
 void emu_requant(const mp3gpu_unit *units, long long n_granules, const int16_t *is16, const uint32_t *meta,

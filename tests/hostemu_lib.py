@@ -19,8 +19,6 @@ def lib():
         L.emu_huffman.restype = None
         L.emu_huffman_staged.argtypes = [vp, C.c_ulonglong, vp, C.c_longlong, C.c_int, C.c_int, vp, vp, vp]
         L.emu_huffman_staged.restype = None
-        L.emu_huffman_global.argtypes = [vp, C.c_ulonglong, vp, C.c_longlong, vp, vp, vp]
-        L.emu_huffman_global.restype = None
         L.emu_requant.argtypes = [vp, C.c_longlong, vp, vp, vp, vp]
         L.emu_requant.restype = None
         L.emu_table.argtypes = [C.c_int, C.POINTER(C.c_int)]
@@ -53,18 +51,6 @@ def huffman_staged(main_data: np.ndarray, units: np.ndarray, tile: int = 256, ca
     units = np.ascontiguousarray(units)
     lib().emu_huffman_staged(main_data.ctypes.data, (len(main_data) - 64) * 8, units.ctypes.data, n, tile, cap16, is16.ctypes.data,
                              meta.ctypes.data, sf.ctypes.data)
-    return is16, meta, sf
-
-
-def huffman_global(main_data: np.ndarray, units: np.ndarray):
-    """K1 with nothing staged (GlobalCursor / GlobalWindow over main_data itself)."""
-    n = len(units)
-    is16 = np.zeros((n, 576), np.int16)
-    meta = np.zeros(n, np.uint32)
-    sf = np.zeros((n, 64), np.uint8)
-    main_data = np.ascontiguousarray(main_data)
-    units = np.ascontiguousarray(units)
-    lib().emu_huffman_global(main_data.ctypes.data, (len(main_data) - 64) * 8, units.ctypes.data, n, is16.ctypes.data, meta.ctypes.data, sf.ctypes.data)
     return is16, meta, sf
 
 
