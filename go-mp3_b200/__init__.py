@@ -215,6 +215,8 @@ def gpu_lib(exact=False) -> C.CDLL:
     if exact in _gpu:
         return _gpu[exact]
     name = {False: "libmp3gpu.so", True: "libmp3gpu_exact.so", "checked": "libmp3gpu_checked.so"}[exact]
+    if exact is False and os.environ.get("MP3GPU_LIB_VARIANT"):  # tools/ only: a diagnostic build of the product library (make probe)
+        name = "libmp3gpu_%s.so" % os.environ["MP3GPU_LIB_VARIANT"]
     L = C.CDLL(_lib_path(name))
     vp, sz = C.c_void_p, C.c_size_t
     L.mp3gpu_create.argtypes = [C.c_int, C.POINTER(GpuOpts), C.POINTER(vp)]

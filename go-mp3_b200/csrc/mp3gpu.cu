@@ -337,6 +337,9 @@ static int launch_wave(mp3gpu_ctx *ctx, const uint8_t *d_main, size_t main_len, 
     B.work_counter = ctx->d_counter;
     B.units_total = (long long)n_granules_total * 2;
     B.n_gran = n;
+#if MP3GPU_PROBE
+    B.probe = getenv("MP3GPU_PROBE") ? atoi(getenv("MP3GPU_PROBE")) : 0;
+#endif
     cudaStream_t s = ctx->s_compute;
     if (slot >= 0) CK(cudaEventRecord(ctx->ev_t[slot][0], s));
     {
