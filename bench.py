@@ -572,6 +572,7 @@ def run_cfg5(pkg, synth, heng, args, cores, world):
     for _ in range(2):
         pcm, rc, tm = one.decode_stream_split(ix)
         lin_s.append(tm["total_s"])
+        print("[cfg5] one-device split decode:", {k: round(v, 4) if isinstance(v, float) else v for k, v in tm.items()}, file=sys.stderr)
     # oracle parity on three stretches of the stream (the oracle needs ~45 s for the whole of it): a sub-stream starting 40
     # frames earlier converges to the linear decode's state (reservoir <= 511 bytes back, overlap/V history two granules)
     worst, fracs = 0, []

@@ -43,10 +43,21 @@ type Slicer struct {
 // Reset is d.frame = nil (decode.go:47,108): the next frame ignores main_data_begin and starts from zero state.
 func (s *Slicer) Reset() { s.havePrev = false }
 
-// AppendFrame resolves the frame's reservoir window and appends its units.  part2Bits(gr, ch) returns the
-// scalefactor bit count of a unit (a pure function of side info; only consulted for zero-length units, whose
-// cursor stays after the scalefactor bits: maindata/huffman.go:29-34).
-func (s *Slicer) AppendFrame(h Header, si *SideInfo, own []byte, part2Bits func(gr, ch int) int) {
+// Rebase drops the bytes in front of the current reservoir window once the units appended so far have been submitted
+// (mp3_decoder::fill in csrc/host/mp3host.cc does the same), so that a streaming decoder's buffer stays bounded:
+// later units' BitStart are relative to the new M.
+func (s *Slicer) Rebase() {
+	s.M = append(s.M[:0], s.M[s.winStart:]...)
+	s.winStart = 0
+	s.Units = s.Units[:0]
+}
+
+// AppendFrame resolves the frame's reservoir window and appends its units.  part2Reads(gr, ch) returns the sizes of
+// the individual Bits(n) reads of the unit's scalefactors in stream order (a pure function of side info; only
+// consulted for zero-length units, whose cursor stays after the scalefactor bits: maindata/huffman.go:29-34).
+// Every read is refused on its own when it would cross the buffer end (bits.go:45-60), exactly like
+// ScalefacCursor in csrc/host/stream_parser.h — NOT all-or-nothing for the unit.
+func (s *Slicer) AppendFrame(h Header, si *SideInfo, own []byte, part2Reads func(gr, ch int) []int) {
 	mEnd := len(s.M)
 	start := mEnd
 	if s.havePrev {
@@ -82,8 +93,12 @@ func (s *Slicer) AppendFrame(h Header, si *SideInfo, own []byte, part2Bits func(
 				}
 				if si.Part2_3Length[gr][ch] != 0 {
 					cursor += si.Part2_3Length[gr][ch] // SetPos(bitPosEnd+1), maindata/huffman.go:136
-				} else if c := cursor + part2Bits(gr, ch); c <= total {
-					cursor = c // (per-read clamping at the buffer end: see stream_parser.h ScalefacCursor)
+				} else {
+					for _, n := range part2Reads(gr, ch) {
+						if n > 0 && cursor+n <= total {
+							cursor += n
+						}
+					}
 				}
 			}
 			s.Units = append(s.Units, u)
