@@ -370,6 +370,14 @@ def unit_slots_upper_bound(stream: bytes) -> int:
     return int(L.mp3_debug_unit_slots_upper_bound(stream, len(stream)))
 
 
+def main_bytes_upper_bound(stream: bytes) -> int:
+    """The same walk's bound of the stream's main-data bytes (mp3_debug_main_bytes_upper_bound; test hook)."""
+    L = host_lib()
+    L.mp3_debug_main_bytes_upper_bound.argtypes = [C.c_char_p, C.c_size_t]
+    L.mp3_debug_main_bytes_upper_bound.restype = C.c_size_t
+    return int(L.mp3_debug_main_bytes_upper_bound(stream, len(stream)))
+
+
 def parse_streams(streams: Sequence[bytes], host_threads: int = 0) -> ParsedBatch:
     """Host half of DecodeBatch: tags, headers, side info, reservoir -> bit-slices (mp3_parse_streams)."""
     L = host_lib()

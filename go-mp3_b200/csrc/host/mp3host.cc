@@ -343,12 +343,16 @@ namespace {
 
 // Upper bound of the unit slots a stream will produce: the frame walk of parse_whole_stream without side info
 // and main data (a frame that later fails to parse only makes the real count smaller).
-size_t unit_slots_upper_bound(const uint8_t *data, size_t len) {
+struct StreamBound {
+    size_t slots = 0;  // unit slots (2 per granule)
+    size_t m_bytes = 0;  // main-data bytes (frame size - header - CRC - side info of every walked frame)
+};
+StreamBound stream_upper_bound(const uint8_t *data, size_t len) {
     Source s;
     s.data = data;
     s.len = len;
-    if (s.skip_tags() != MP3_OK) return 0;
-    size_t slots = 0;
+    StreamBound b;
+    if (s.skip_tags() != MP3_OK) return b;
     for (;;) {
         Header h;
         int64_t fpos;
@@ -357,10 +361,13 @@ size_t unit_slots_upper_bound(const uint8_t *data, size_t len) {
         const int fs = h.frame_size();
         if (fs > 2000 || fs < 4 || s.pos + (fs - 4) > (int64_t)len) break;
         s.pos += fs - 4;
-        slots += (size_t)h.granules() * 2;
+        b.slots += (size_t)h.granules() * 2;
+        const int md = fs - 4 - h.side_info_size() - (h.protection_bit() == 0 ? 2 : 0);
+        if (md > 0) b.m_bytes += (size_t)md;
     }
-    return slots;
+    return b;
 }
+size_t unit_slots_upper_bound(const uint8_t *data, size_t len) { return stream_upper_bound(data, len).slots; }
 
 struct DeviceJob {
     const uint8_t *main_data;
@@ -374,6 +381,7 @@ struct DeviceJob {
 
 // Test hook (tests/test_host_and_emulation.py): the arena bound DecodeBatch relies on.
 extern "C" size_t mp3_debug_unit_slots_upper_bound(const uint8_t *data, size_t len) { return unit_slots_upper_bound(data, len); }
+extern "C" size_t mp3_debug_main_bytes_upper_bound(const uint8_t *data, size_t len) { return stream_upper_bound(data, len).m_bytes; }
 
 namespace {
 
@@ -396,8 +404,8 @@ size_t shard_chunks(size_t n) {
 
 // Large shards are cut into chunks of streams: while the device decodes chunk k (the PCIe-bound part), the host
 // threads parse and gather chunk k+1 straight behind it in the same pinned arenas.
-void decode_shard(mp3_engine *e, DeviceSlot *dev, const uint8_t *const *data, const size_t *lens, mp3_stream_result *results, Shard &S,
-                  int threads) {
+void decode_shard(mp3_engine *e, DeviceSlot *dev, const uint8_t *const *data, const size_t *lens, const StreamBound *bounds,
+                  mp3_stream_result *results, Shard &S, int threads) {
     const size_t n = S.i1 - S.i0;
     if (n == 0) return;
     const size_t n_chunks = shard_chunks(n);
@@ -453,27 +461,72 @@ void decode_shard(mp3_engine *e, DeviceSlot *dev, const uint8_t *const *data, co
                     run_job(j, w);
                 }
             });
-    std::vector<ParsedStream> ps;  // reused by every chunk: the per-stream vectors keep their (already touched) capacity
+    // Every stream of a chunk is parsed STRAIGHT into the pinned arenas, at the place its bounds give it: stream i's main
+    // data starts where the bounds of the streams in front of it end (4-byte aligned), its units likewise.  For well-formed
+    // streams the bounds are exact, so the streams lie back to back as the device kernels like them; a stream that ends
+    // early (truncated, garbage) leaves unit slots that are marked invalid and a hole in the PCM that its result does not
+    // cover.  No per-stream vectors, no gather copy.
+    std::vector<size_t> m_at, u_at;
     for (size_t c = 0; c < n_chunks; c++) {
         const size_t i0 = S.i0 + n * c / n_chunks, i1 = S.i0 + n * (c + 1) / n_chunks;
         const double ta = now_s();
-        parse_all(data + i0, lens + i0, i1 - i0, threads, ps);
-        const double tb = now_s();
-        S.parse_s += tb - ta;
-        BatchLayout L = layout_batch(ps);
-        if (m_cursor + L.m_total + 64 > S.m_off + S.m_cap || u_cursor + L.u_total > S.u_off + S.u_cap) {
-            // cannot happen (the bounds are bounds: tests/test_host_and_emulation.py); refuse rather than overrun
-            S.rc = MP3_ERR_INVALID;
+        const size_t nc = i1 - i0;
+        m_at.assign(nc + 1, 0);
+        u_at.assign(nc + 1, 0);
+        for (size_t k = 0; k < nc; k++) {
+            m_at[k + 1] = m_at[k] + ((bounds[i0 + k].m_bytes + 3) & ~size_t(3));
+            u_at[k + 1] = u_at[k] + bounds[i0 + k].slots;
+        }
+        const size_t m_total = m_at[nc], u_total = u_at[nc];
+        if (m_cursor + m_total + 64 > S.m_off + S.m_cap || u_cursor + u_total > S.u_off + S.u_cap) {
+            S.rc = MP3_ERR_INVALID;  // cannot happen: the caps are the sums of the same bounds
             S.err = "DecodeBatch arena bound exceeded";
             break;
         }
         uint8_t *m_dst = (uint8_t *)e->a_main.p + m_cursor;
         mp3gpu_unit *u_dst = (mp3gpu_unit *)e->a_units.p + u_cursor;
-        gather_batch(ps, L, m_dst, u_dst, results + i0, threads);
         const int64_t pcm_off = (int64_t)(u_cursor / 2) * MP3GPU_PCM_BYTES_PER_GRANULE;
-        for (size_t i = i0; i < i1; i++) results[i].pcm_offset += pcm_off;
-        S.gather_s += now_s() - tb;
-        DeviceJob j{m_dst, L.m_total, u_dst, L.u_total / 2, (int16_t *)((uint8_t *)e->a_pcm.p + pcm_off)};
+        std::atomic<size_t> next{0};
+        std::atomic<bool> overflow{false};
+        auto work = [&]() {
+            for (;;) {
+                const size_t k = next.fetch_add(1);
+                if (k >= nc) break;
+                const size_t i = i0 + k;
+                SpanVec<uint8_t> M;
+                M.p = m_dst + m_at[k];
+                M.cap = bounds[i].m_bytes;
+                SpanVec<mp3gpu_unit> U;
+                U.p = u_dst + u_at[k];
+                U.cap = bounds[i].slots;
+                StreamMeta meta;
+                parse_whole_stream_into(data[i], lens[i], M, U, meta, (int64_t)m_at[k] * 8);
+                if (M.overflow || U.overflow) overflow = true;
+                for (size_t q = M.n; q < m_at[k + 1] - m_at[k]; q++) M.p[q] = 0;      // up to the next stream's start
+                if (U.n < U.cap) memset(U.p + U.n, 0, (U.cap - U.n) * sizeof(mp3gpu_unit));  // invalid slots: no VALID bit
+                results[i].pcm_offset = pcm_off + (int64_t)(u_at[k] / 2) * MP3GPU_PCM_BYTES_PER_GRANULE;
+                results[i].pcm_bytes = (int64_t)(U.n / 2) * MP3GPU_PCM_BYTES_PER_GRANULE;
+                results[i].sample_rate = meta.sample_rate;
+                results[i].status = meta.status;
+                results[i].frames = meta.frames;
+            }
+        };
+        const int nt = (int)std::min<size_t>((size_t)hw_threads(threads), nc ? nc : 1);
+        if (nt <= 1) {
+            work();
+        } else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nt; t++) th.emplace_back(work);
+            for (auto &t : th) t.join();
+        }
+        memset(m_dst + m_total, 0, 64);
+        S.parse_s += now_s() - ta;
+        if (overflow) {
+            S.rc = MP3_ERR_INVALID;  // cannot happen (the bounds are bounds: tests/test_host_and_emulation.py); refuse rather than decode garbage
+            S.err = "DecodeBatch stream bound exceeded";
+            break;
+        }
+        DeviceJob j{m_dst, m_total, u_dst, u_total / 2, (int16_t *)((uint8_t *)e->a_pcm.p + pcm_off)};
         if (n_chunks == 1) {
             run_job(j, 0);
         } else {
@@ -483,8 +536,8 @@ void decode_shard(mp3_engine *e, DeviceSlot *dev, const uint8_t *const *data, co
             }
             cv.notify_one();
         }
-        m_cursor += (L.m_total + 64 + 63) & ~size_t(63);
-        u_cursor += L.u_total;
+        m_cursor += (m_total + 64 + 63) & ~size_t(63);
+        u_cursor += u_total;
     }
     if (!workers.empty()) {
         {
@@ -529,15 +582,15 @@ extern "C" int mp3_decode_batch(mp3_engine *e, const uint8_t *const *data, const
     const double t0 = now_s();
     const size_t D = e->devs.size();
     const int threads = hw_threads(e->opts.host_threads);
-    // ---- arena bounds: main data never exceeds the input bytes; unit slots from a header-only frame walk ----
-    std::vector<size_t> ub(n);
+    // ---- arena bounds from a header-only frame walk: unit slots and main-data bytes per stream (exact for well-formed streams) ----
+    std::vector<StreamBound> ub(n);
     {
         std::atomic<size_t> next{0};
         auto work = [&]() {
             for (;;) {
                 size_t i = next.fetch_add(1);
                 if (i >= n) break;
-                ub[i] = unit_slots_upper_bound(data[i], lens[i]);
+                ub[i] = stream_upper_bound(data[i], lens[i]);
             }
         };
         int nt = (int)std::min<size_t>((size_t)threads, n ? n : 1);
@@ -561,10 +614,10 @@ extern "C" int mp3_decode_batch(mp3_engine *e, const uint8_t *const *data, const
             const size_t target = (size_t)((double)total * (double)(d + 1) / (double)D);
             while (i < n && (d + 1 == D || acc + lens[i] / 2 < target)) acc += lens[i++];
             S.i1 = i;
-            size_t mb = 64 * (shard_chunks(S.i1 - S.i0) + 1), us = 0;
+            size_t mb = 128 * (shard_chunks(S.i1 - S.i0) + 1), us = 0;  // per chunk: 64 bytes of zero padding + rounding up to 64
             for (size_t k = S.i0; k < S.i1; k++) {
-                mb += (lens[k] + 3) & ~size_t(3);
-                us += ub[k];
+                mb += (ub[k].m_bytes + 3) & ~size_t(3);
+                us += ub[k].slots;
             }
             mb = (mb + 63) & ~size_t(63);
             S.m_off = m_off;
@@ -580,12 +633,12 @@ extern "C" int mp3_decode_batch(mp3_engine *e, const uint8_t *const *data, const
         if (rc != MP3_OK) return rc;
     }
     if (D == 1) {
-        decode_shard(e, e->devs[0], data, lens, results, shards[0], threads);
+        decode_shard(e, e->devs[0], data, lens, ub.data(), results, shards[0], threads);
     } else {
         const int per = std::max(1, threads / (int)D);
         std::vector<std::thread> th;
         for (size_t d = 0; d < D; d++)
-            th.emplace_back([&, d]() { decode_shard(e, e->devs[d], data, lens, results, shards[d], per); });
+            th.emplace_back([&, d]() { decode_shard(e, e->devs[d], data, lens, ub.data(), results, shards[d], per); });
         for (auto &t : th) t.join();
     }
     const double t3 = now_s();

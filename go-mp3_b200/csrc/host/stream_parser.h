@@ -181,6 +181,29 @@ struct ScalefacCursor {
     }
 };
 
+// A fixed-capacity stand-in for std::vector over caller-owned memory (DecodeBatch parses straight into its pinned arenas).
+// An append past the capacity is dropped and recorded; the caller sized the span from a bound and treats that as a bug.
+template <class T>
+struct SpanVec {
+    T *p = nullptr;
+    size_t n = 0, cap = 0;
+    bool overflow = false;
+    size_t size() const { return n; }
+    T *end() { return p + n; }
+    T &operator[](size_t i) { return p[i]; }
+    void insert(T *at, const T *b, const T *e) {  // only ever called with at == end()
+        (void)at;
+        const size_t k = (size_t)(e - b);
+        if (n + k > cap) { overflow = true; return; }
+        if (k) memcpy(p + n, b, k * sizeof(T));
+        n += k;
+    }
+    void resize(size_t m) {
+        if (m > cap) { overflow = true; return; }
+        n = m;
+    }
+};
+
 // One parsed stream: appended-to by StreamParser.
 struct ParsedStream {
     std::vector<uint8_t> main_data;   // M
@@ -213,7 +236,8 @@ public:
 
     // Returns MP3_OK and appends; MP3_EOF for io.EOF at a frame boundary; or a negative error.
     // `zero_state` marks the frame's first granule (first frame after reset).
-    int next_frame(std::vector<uint8_t> &M, std::vector<mp3gpu_unit> &units, int64_t bit_base = 0) {
+    template <class MV, class UV>
+    int next_frame(MV &M, UV &units, int64_t bit_base = 0) {
         Header h;
         int64_t fpos;
         int rc = read_frame_header(src, &h, &fpos);
@@ -287,6 +311,7 @@ public:
         int err = MP3_OK;
         const size_t u0 = units.size();
         units.resize(u0 + (size_t)ngr * 2);
+        if (units.size() != u0 + (size_t)ngr * 2) return MP3_ERR_INVALID;  // a SpanVec that is full (never: the caller's bound)
         memset(&units[u0], 0, sizeof(mp3gpu_unit) * (size_t)ngr * 2);
         for (int gr = 0; gr < ngr && err == MP3_OK; gr++)
             for (int ch = 0; ch < nch; ch++) {
@@ -357,8 +382,15 @@ public:
 
 // Whole-stream parse with the reference's open/read loop semantics:
 // NewDecoder = skipTags + first readFrame (decode.go:361-376); then Read until EOF (io.ReadAll).
-inline void parse_whole_stream(const uint8_t *data, size_t len, ParsedStream &out, int64_t bit_base = 0) {
-    out.clear();
+struct StreamMeta {
+    int64_t frames = 0;
+    int sample_rate = 0;
+    int status = MP3_OK;   // as ParsedStream::status
+    bool opened = false;
+};
+template <class MV, class UV>
+inline void parse_whole_stream_into(const uint8_t *data, size_t len, MV &M, UV &units, StreamMeta &out, int64_t bit_base = 0) {
+    out = StreamMeta();
     StreamParser p;
     p.src.data = data;
     p.src.len = len;
@@ -368,7 +400,7 @@ inline void parse_whole_stream(const uint8_t *data, size_t len, ParsedStream &ou
         return;
     }
     for (;;) {
-        rc = p.next_frame(out.main_data, out.units, bit_base);
+        rc = p.next_frame(M, units, bit_base);
         if (rc != MP3_OK) break;
         if (out.frames == 0) {
             out.sample_rate = p.last_header.sampling_frequency_value();
@@ -382,6 +414,15 @@ inline void parse_whole_stream(const uint8_t *data, size_t len, ParsedStream &ou
         out.status = eof_family ? MP3_EOF : rc;  // NewDecoder fails with io.EOF / the error
     else
         out.status = eof_family ? MP3_OK : rc;   // io.ReadAll: nil on EOF, else the error (PCM so far is kept)
+}
+inline void parse_whole_stream(const uint8_t *data, size_t len, ParsedStream &out, int64_t bit_base = 0) {
+    out.clear();
+    StreamMeta m;
+    parse_whole_stream_into(data, len, out.main_data, out.units, m, bit_base);
+    out.frames = m.frames;
+    out.sample_rate = m.sample_rate;
+    out.status = m.status;
+    out.opened = m.opened;
 }
 
 }  // namespace mp3host

@@ -112,7 +112,7 @@ typedef struct mp3_stream_result {
 } mp3_stream_result;
 
 typedef struct mp3_batch_timings {
-    double parse_s, gather_s, device_s, total_s;
+    double parse_s, gather_s, device_s, total_s;  /* gather_s: 0 since the parse writes straight into the arenas */
     uint64_t main_data_bytes, n_granules, pcm_bytes;
 } mp3_batch_timings;
 
@@ -179,6 +179,8 @@ int mp3_lameinfo_is_lame_version(const uint8_t *s, size_t n); /* isLAMEVersion, 
 /* Test hook: upper bound of the unit slots (2 per granule) mp3_parse_streams / mp3_decode_batch produce for one
  * stream, from a header-only frame walk; DecodeBatch sizes its pinned arenas with it. */
 size_t mp3_debug_unit_slots_upper_bound(const uint8_t *data, size_t len);
+/* The same walk's bound of the stream's main-data bytes (DecodeBatch parses every stream straight into its arena slot). */
+size_t mp3_debug_main_bytes_upper_bound(const uint8_t *data, size_t len);
 
 /* Host-only stage of DecodeBatch (no GPU): parse + reservoir resolution into caller-visible arrays.
  * Used by tests (host logic) and by bench.py to stage device-resident inputs.  Buffers are owned by

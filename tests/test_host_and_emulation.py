@@ -152,9 +152,12 @@ def test_decode_batch_arena_bound_covers_every_stream(pkg, classic_lame, mpeg2):
     exact = 0
     for name, data in cases.items():
         ub = pkg.unit_slots_upper_bound(data)
-        n = pkg.parse_streams([data]).n_granules * 2
+        mb = pkg.main_bytes_upper_bound(data)
+        pb = pkg.parse_streams([data])
+        n = pb.n_granules * 2
         assert ub >= n, (name, ub, n)
-        exact += ub == n
+        assert mb >= pb.main_data_len - 3, (name, mb, pb.main_data_len)  # main_data_len is padded to 4 bytes
+        exact += ub == n and mb <= pb.main_data_len <= mb + 3
     assert exact >= len(cases) // 2
 
 
