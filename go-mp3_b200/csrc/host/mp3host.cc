@@ -385,13 +385,17 @@ extern "C" size_t mp3_debug_main_bytes_upper_bound(const uint8_t *data, size_t l
 
 namespace {
 
-// Streams [i0, i1) of a batch on one device, in that device's region of the shared arenas.
-struct Shard {
+// A chunk = streams [i0, i1) of a batch with its fixed place in the shared pinned arenas (computed from the streams' bounds,
+// so the place does not depend on which device ends up decoding the chunk).
+struct Chunk {
     size_t i0 = 0, i1 = 0;
-    size_t m_off = 0, m_cap = 0;  // bytes into a_main
-    size_t u_off = 0, u_cap = 0;  // unit slots into a_units (PCM: slot / 2 * 2304 bytes into a_pcm)
+    size_t m_off = 0, m_total = 0;  // bytes into a_main (m_total excludes the 64 bytes of zero padding that follow)
+    size_t u_off = 0, u_total = 0;  // unit slots into a_units (PCM: slot / 2 * 2304 bytes into a_pcm)
+};
+// What one device did in a DecodeBatch call.
+struct Shard {
     double parse_s = 0, gather_s = 0, device_s = 0;
-    size_t m_used = 0, u_used = 0;
+    size_t m_used = 0, u_used = 0, chunks = 0;
     int rc = MP3_OK;
     std::string err;
 };
@@ -402,14 +406,13 @@ size_t shard_chunks(size_t n) {
     return n >= 256 ? std::min<size_t>(32, n / 32) : 1;  // measured (1,024 x 30 s streams): 8 / 16 / 32 chunks = 0.83 / 0.86 / 0.90 of the plain-copy ceiling
 }
 
-// Large shards are cut into chunks of streams: while the device decodes chunk k (the PCIe-bound part), the host
-// threads parse and gather chunk k+1 straight behind it in the same pinned arenas.
+// One device's share of a DecodeBatch call.  The batch is cut into chunks of streams and the devices PULL chunks from a
+// common counter (a device behind a slower PCIe link simply takes fewer): while the device decodes chunk k (the PCIe-bound
+// part), the host threads parse chunk k+1 straight behind it into the pinned arenas.
 void decode_shard(mp3_engine *e, DeviceSlot *dev, const uint8_t *const *data, const size_t *lens, const StreamBound *bounds,
-                  mp3_stream_result *results, Shard &S, int threads) {
-    const size_t n = S.i1 - S.i0;
-    if (n == 0) return;
-    const size_t n_chunks = shard_chunks(n);
-    size_t m_cursor = S.m_off, u_cursor = S.u_off;
+                  mp3_stream_result *results, const std::vector<Chunk> &chunks, std::atomic<size_t> &next_chunk, Shard &S, int threads) {
+    const size_t n_chunks = chunks.size();
+    if (n_chunks == 0) return;
     int dev_rc = MP3GPU_OK;
     std::string dev_err;
     std::mutex mu;
@@ -458,6 +461,7 @@ void decode_shard(mp3_engine *e, DeviceSlot *dev, const uint8_t *const *data, co
                         j = jobs.front();
                         jobs.pop_front();
                     }
+                    cv.notify_all();  // the producer may pull the next chunk
                     run_job(j, w);
                 }
             });
@@ -467,8 +471,15 @@ void decode_shard(mp3_engine *e, DeviceSlot *dev, const uint8_t *const *data, co
     // early (truncated, garbage) leaves unit slots that are marked invalid and a hole in the PCM that its result does not
     // cover.  No per-stream vectors, no gather copy.
     std::vector<size_t> m_at, u_at;
-    for (size_t c = 0; c < n_chunks; c++) {
-        const size_t i0 = S.i0 + n * c / n_chunks, i1 = S.i0 + n * (c + 1) / n_chunks;
+    for (;;) {
+        if (n_chunks > 1) {  // do not pull chunks faster than this device decodes them: at most two parsed chunks waiting
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return jobs.size() < 2; });
+        }
+        const size_t c = next_chunk.fetch_add(1);
+        if (c >= n_chunks) break;
+        const Chunk &K = chunks[c];
+        const size_t i0 = K.i0, i1 = K.i1;
         const double ta = now_s();
         const size_t nc = i1 - i0;
         m_at.assign(nc + 1, 0);
@@ -478,14 +489,14 @@ void decode_shard(mp3_engine *e, DeviceSlot *dev, const uint8_t *const *data, co
             u_at[k + 1] = u_at[k] + bounds[i0 + k].slots;
         }
         const size_t m_total = m_at[nc], u_total = u_at[nc];
-        if (m_cursor + m_total + 64 > S.m_off + S.m_cap || u_cursor + u_total > S.u_off + S.u_cap) {
-            S.rc = MP3_ERR_INVALID;  // cannot happen: the caps are the sums of the same bounds
-            S.err = "DecodeBatch arena bound exceeded";
+        if (m_total != K.m_total || u_total != K.u_total) {
+            S.rc = MP3_ERR_INVALID;  // cannot happen: the chunk table was built from the same bounds
+            S.err = "DecodeBatch chunk table mismatch";
             break;
         }
-        uint8_t *m_dst = (uint8_t *)e->a_main.p + m_cursor;
-        mp3gpu_unit *u_dst = (mp3gpu_unit *)e->a_units.p + u_cursor;
-        const int64_t pcm_off = (int64_t)(u_cursor / 2) * MP3GPU_PCM_BYTES_PER_GRANULE;
+        uint8_t *m_dst = (uint8_t *)e->a_main.p + K.m_off;
+        mp3gpu_unit *u_dst = (mp3gpu_unit *)e->a_units.p + K.u_off;
+        const int64_t pcm_off = (int64_t)(K.u_off / 2) * MP3GPU_PCM_BYTES_PER_GRANULE;
         std::atomic<size_t> next{0};
         std::atomic<bool> overflow{false};
         auto work = [&]() {
@@ -526,6 +537,9 @@ void decode_shard(mp3_engine *e, DeviceSlot *dev, const uint8_t *const *data, co
             S.err = "DecodeBatch stream bound exceeded";
             break;
         }
+        S.m_used += m_total;
+        S.u_used += u_total;
+        S.chunks++;
         DeviceJob j{m_dst, m_total, u_dst, u_total / 2, (int16_t *)((uint8_t *)e->a_pcm.p + pcm_off)};
         if (n_chunks == 1) {
             run_job(j, 0);
@@ -534,10 +548,8 @@ void decode_shard(mp3_engine *e, DeviceSlot *dev, const uint8_t *const *data, co
                 std::lock_guard<std::mutex> lk(mu);
                 jobs.push_back(j);
             }
-            cv.notify_one();
+            cv.notify_all();
         }
-        m_cursor += (m_total + 64 + 63) & ~size_t(63);
-        u_cursor += u_total;
     }
     if (!workers.empty()) {
         {
@@ -547,8 +559,6 @@ void decode_shard(mp3_engine *e, DeviceSlot *dev, const uint8_t *const *data, co
         cv.notify_all();
         for (auto &t : workers) t.join();
     }
-    S.m_used = m_cursor - S.m_off;
-    S.u_used = u_cursor - S.u_off;
     if (S.rc == MP3_OK && dev_rc != MP3GPU_OK) {
         S.rc = MP3_ERR_DEVICE;
         S.err = dev_err;
@@ -573,9 +583,9 @@ void trim_gapless(const uint8_t *data, size_t len, mp3_stream_result &r) {
 
 }  // namespace
 
-// DecodeBatch.  The streams are dealt to the engine's devices in contiguous blocks balanced by input bytes (streams share
-// nothing: no collective); every device runs the chunked parse -> gather -> device pipeline above on its
-// own host thread, with its share of the parsing threads, in its own region of the pinned arenas.
+// DecodeBatch.  The batch is cut into chunks of streams of about equal input bytes; the engine's devices pull chunks from a
+// common counter (streams share nothing: no collective).  Every device runs the parse -> device pipeline above
+// on its own host thread, with its share of the parsing threads; a chunk's place in the pinned arenas is fixed by the bounds.
 extern "C" int mp3_decode_batch(mp3_engine *e, const uint8_t *const *data, const size_t *lens, size_t n,
                                 mp3_stream_result *results, const uint8_t **pcm_base, mp3_batch_timings *timings) {
     if (!e || !results || !pcm_base || (n && (!data || !lens))) return MP3_ERR_INVALID;
@@ -602,43 +612,46 @@ extern "C" int mp3_decode_batch(mp3_engine *e, const uint8_t *const *data, const
             work();
         }
     }
-    // ---- shards: contiguous blocks of streams, balanced by bytes ----
-    std::vector<Shard> shards(D);
+    // ---- chunks: contiguous blocks of streams of about equal input bytes, each with its place in the arenas ----
+    std::vector<Chunk> chunks;
+    size_t u_end = 0;
     {
         size_t total = 0;
         for (size_t i = 0; i < n; i++) total += lens[i];
+        size_t nck = D == 1 ? shard_chunks(n) : (n >= 256 * D ? std::min<size_t>(32 * D, n / 32) : std::min<size_t>(D, n));
+        if (nck < 1) nck = 1;
         size_t i = 0, acc = 0, m_off = 0, u_off = 0;
-        for (size_t d = 0; d < D; d++) {
-            Shard &S = shards[d];
-            S.i0 = i;
-            const size_t target = (size_t)((double)total * (double)(d + 1) / (double)D);
-            while (i < n && (d + 1 == D || acc + lens[i] / 2 < target)) acc += lens[i++];
-            S.i1 = i;
-            size_t mb = 128 * (shard_chunks(S.i1 - S.i0) + 1), us = 0;  // per chunk: 64 bytes of zero padding + rounding up to 64
-            for (size_t k = S.i0; k < S.i1; k++) {
-                mb += (ub[k].m_bytes + 3) & ~size_t(3);
-                us += ub[k].slots;
+        for (size_t c = 0; c < nck; c++) {
+            Chunk K;
+            K.i0 = i;
+            const size_t target = (size_t)((double)total * (double)(c + 1) / (double)nck);
+            while (i < n && (c + 1 == nck || acc + lens[i] / 2 < target)) acc += lens[i++];
+            K.i1 = i;
+            for (size_t k = K.i0; k < K.i1; k++) {
+                K.m_total += (ub[k].m_bytes + 3) & ~size_t(3);
+                K.u_total += ub[k].slots;
             }
-            mb = (mb + 63) & ~size_t(63);
-            S.m_off = m_off;
-            S.m_cap = mb;
-            S.u_off = u_off;
-            S.u_cap = us;
-            m_off += mb;
-            u_off += us;
+            K.m_off = m_off;
+            K.u_off = u_off;
+            m_off += (K.m_total + 64 + 63) & ~size_t(63);  // 64 bytes of zero padding behind every chunk's main data
+            u_off += K.u_total;
+            if (K.i1 > K.i0) chunks.push_back(K);
         }
+        u_end = u_off;
         int rc = e->ensure(e->a_main, m_off + 64);
         if (rc == MP3_OK) rc = e->ensure(e->a_units, sizeof(mp3gpu_unit) * u_off + 64);
         if (rc == MP3_OK) rc = e->ensure(e->a_pcm, (u_off / 2) * MP3GPU_PCM_BYTES_PER_GRANULE + 64);
         if (rc != MP3_OK) return rc;
     }
-    if (D == 1) {
-        decode_shard(e, e->devs[0], data, lens, ub.data(), results, shards[0], threads);
+    std::vector<Shard> shards(D);
+    std::atomic<size_t> next_chunk{0};
+    if (D == 1 || chunks.size() <= 1) {
+        decode_shard(e, e->devs[0], data, lens, ub.data(), results, chunks, next_chunk, shards[0], threads);
     } else {
         const int per = std::max(1, threads / (int)D);
         std::vector<std::thread> th;
         for (size_t d = 0; d < D; d++)
-            th.emplace_back([&, d]() { decode_shard(e, e->devs[d], data, lens, ub.data(), results, shards[d], per); });
+            th.emplace_back([&, d]() { decode_shard(e, e->devs[d], data, lens, ub.data(), results, chunks, next_chunk, shards[d], per); });
         for (auto &t : th) t.join();
     }
     const double t3 = now_s();
@@ -664,8 +677,7 @@ extern "C" int mp3_decode_batch(mp3_engine *e, const uint8_t *const *data, const
         timings->n_granules = granules;
         // the span of the PCM buffer that holds results (regions of devices are laid out by their bounds: for well-formed
         // streams the bound is exact and the span is dense)
-        const Shard &last = shards[D - 1];
-        timings->pcm_bytes = (uint64_t)((last.u_off + last.u_used) / 2) * MP3GPU_PCM_BYTES_PER_GRANULE;
+        timings->pcm_bytes = (uint64_t)(u_end / 2) * MP3GPU_PCM_BYTES_PER_GRANULE;
     }
     return MP3_OK;
 }
