@@ -777,6 +777,13 @@ class LameInfo:
         """The 9 bytes of the version field (b"" if there is no LAME tag); may end in NULs (e.g. b"LAME3.99\x00")."""
         return C.string_at(C.addressof(self._raw) + LameInfoStruct.lame_version.offset, 9) if self._raw.has_lame_info else b""
 
+    def toc_offset(self, fraction: float, stream_bytes: int = 0) -> int:
+        """Byte offset (from the first audio frame) at `fraction` of the playing time, interpolated in the TOC; -1 without one."""
+        L = host_lib()
+        L.mp3_lameinfo_toc_offset.argtypes = [C.POINTER(LameInfoStruct), C.c_double, C.c_uint64]
+        L.mp3_lameinfo_toc_offset.restype = C.c_int64
+        return int(L.mp3_lameinfo_toc_offset(C.byref(self._raw), float(fraction), int(stream_bytes)))
+
     def has_frame_count(self): return bool(self.flags & LAME_FLAG_FRAME_COUNT)
     def has_byte_count(self): return bool(self.flags & LAME_FLAG_BYTE_COUNT)
     def has_toc(self): return bool(self.flags & LAME_FLAG_TOC)

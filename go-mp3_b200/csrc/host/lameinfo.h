@@ -117,4 +117,20 @@ inline int lameinfo_total_padding(const mp3_lame_info *i) {  // lameinfo.go:97-1
     return padding < 0 ? 0 : padding;
 }
 
+// Coarse seek for sources without a frame index (the reference parses the TOC but never uses it): the
+// byte offset, from the start of the audio frames, at which `fraction` (0..1) of the playing time has passed, by linear
+// interpolation between the TOC's 100 entries (entry k = 256 * offset / size at k percent).  -1 without a TOC.
+inline int64_t lameinfo_toc_offset(const mp3_lame_info *i, double fraction, uint64_t stream_bytes) {
+    if (!(i->flags & MP3_LAME_FLAG_TOC)) return -1;
+    const uint64_t total = (i->flags & MP3_LAME_FLAG_BYTE_COUNT) ? (uint64_t)i->byte_count : stream_bytes;
+    double pct = fraction * 100.0;
+    if (!(pct > 0.0)) pct = 0.0;   // also NaN
+    if (pct > 100.0) pct = 100.0;
+    int a = (int)pct;
+    if (a > 99) a = 99;
+    const double fa = (double)i->toc[a], fb = a < 99 ? (double)i->toc[a + 1] : 256.0;
+    const double fx = fa + (fb - fa) * (pct - (double)a);
+    return (int64_t)(fx / 256.0 * (double)total);
+}
+
 }  // namespace mp3host

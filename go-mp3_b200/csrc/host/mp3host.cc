@@ -307,6 +307,9 @@ extern "C" int mp3_lameinfo_parse_from_reader(const uint8_t *data, size_t len, m
 extern "C" int mp3_lameinfo_total_delay(const mp3_lame_info *info) { return info ? lameinfo_total_delay(info) : MP3_LAME_DECODER_DELAY; }
 extern "C" int mp3_lameinfo_total_padding(const mp3_lame_info *info) { return info ? lameinfo_total_padding(info) : 0; }
 extern "C" int mp3_lameinfo_is_lame_version(const uint8_t *s, size_t n) { return is_lame_version(s, n) ? 1 : 0; }
+extern "C" int64_t mp3_lameinfo_toc_offset(const mp3_lame_info *info, double fraction, uint64_t stream_bytes) {
+    return info ? lameinfo_toc_offset(info, fraction, stream_bytes) : -1;
+}
 
 // ---- host-only parse (tests, bench staging) ---------------------------------------------------------
 extern "C" int mp3_parse_streams(const uint8_t *const *data, const size_t *lens, size_t n, int host_threads, mp3_parsed **out) {

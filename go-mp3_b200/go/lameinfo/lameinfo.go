@@ -64,6 +64,19 @@ func (i *Info) TotalPadding() int {
 	return 0
 }
 
+// TOCOffset returns the byte offset (from the first audio frame) at which `fraction` (0..1) of the playing time has passed,
+// interpolated in the TOC (coarse seek for sources without a frame index); -1 if the tag has no TOC.  streamBytes is used
+// when the tag carries no byte count.  Not part of the reference, which parses the TOC and never uses it.
+func (i *Info) TOCOffset(fraction float64, streamBytes uint64) int64 {
+	var c C.mp3_lame_info
+	c.flags = C.uint32_t(i.Flags)
+	c.byte_count = C.uint32_t(i.ByteCount)
+	for k := 0; k < 100; k++ {
+		c.toc[k] = C.uint8_t(i.TOC[k])
+	}
+	return int64(C.mp3_lameinfo_toc_offset(&c, C.double(fraction), C.uint64_t(streamBytes)))
+}
+
 func fromC(rc C.int, c *C.mp3_lame_info) (*Info, error) {
 	switch rc {
 	case C.MP3_OK:

@@ -175,6 +175,10 @@ int mp3_lameinfo_parse_from_reader(const uint8_t *data, size_t len, mp3_lame_inf
 int mp3_lameinfo_total_delay(const mp3_lame_info *info);   /* TotalDelay(), lameinfo.go:88-93 */
 int mp3_lameinfo_total_padding(const mp3_lame_info *info); /* TotalPadding(), lameinfo.go:97-108 */
 int mp3_lameinfo_is_lame_version(const uint8_t *s, size_t n); /* isLAMEVersion, lameinfo.go:273-282 (exported for its test) */
+/* Coarse seek without a frame index (not in the reference, which parses the TOC and never uses it): byte offset from the
+ * first audio frame at which `fraction` (0..1) of the playing time has passed, interpolated in the 100-entry TOC;
+ * `stream_bytes` is used when the tag carries no byte count.  -1 if the tag has no TOC. */
+int64_t mp3_lameinfo_toc_offset(const mp3_lame_info *info, double fraction, uint64_t stream_bytes);
 
 /* Test hook: upper bound of the unit slots (2 per granule) mp3_parse_streams / mp3_decode_batch produce for one
  * stream, from a header-only frame walk; DecodeBatch sizes its pinned arenas with it. */

@@ -157,3 +157,32 @@ def test_parse_real_mpeg2_file():  # :575 (no LAME header); :560 needs example/c
         data = f.read()
     with pytest.raises(pkg.NoXingHeader):
         pkg.lameinfo_parse_from_reader(data)
+
+
+def test_toc_offset_interpolates_like_the_xing_spec():
+    """mp3_lameinfo_toc_offset (not in the reference, which never uses the TOC it parses)."""
+    toc = bytes(min(255, int(256 * (k / 100.0) ** 1.5)) for k in range(100))  # a VBR-like, monotonic table
+    info = pkg.LameInfo(flags=pkg.LAME_FLAG_TOC | pkg.LAME_FLAG_BYTE_COUNT, byte_count=1_000_000)
+    for k in range(100):
+        info._raw.toc[k] = toc[k]
+    assert info.toc_offset(0.0) == 0
+    assert info.toc_offset(1.0) == 1_000_000                       # entry "100" is 256 by definition
+    assert info.toc_offset(0.50) == int(toc[50] / 256 * 1_000_000)
+    mid = info.toc_offset(0.505)                                      # half-way between entries 50 and 51
+    assert mid == int((toc[50] + (toc[51] - toc[50]) * 0.5) / 256 * 1_000_000)
+    assert info.toc_offset(-3.0) == 0 and info.toc_offset(7.0) == 1_000_000 and info.toc_offset(float("nan")) == 0
+    offs = [info.toc_offset(k / 1000.0) for k in range(1001)]
+    assert offs == sorted(offs)
+    # no byte count in the tag: the caller's stream size is used; no TOC: -1
+    info2 = pkg.LameInfo(flags=pkg.LAME_FLAG_TOC)
+    for k in range(100):
+        info2._raw.toc[k] = toc[k]
+    assert info2.toc_offset(1.0, stream_bytes=5000) == 5000
+    assert pkg.LameInfo(flags=pkg.LAME_FLAG_BYTE_COUNT, byte_count=10).toc_offset(0.5) == -1
+    # the real LAME file's TOC leads to frame boundaries' neighbourhood: offsets are monotonic and within the file
+    with open(f"{FIX}/classic_lame.mp3", "rb") as f:
+        data = f.read()
+    real = pkg.lameinfo_parse_from_reader(data)
+    assert real.has_toc()
+    o = [real.toc_offset(k / 20.0, len(data)) for k in range(21)]
+    assert o == sorted(o) and o[0] == 0 and 0 < o[10] < o[20] <= len(data)
