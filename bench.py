@@ -513,6 +513,11 @@ def run_ours(args, rank, world, local_rank):
                                   "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one full-wave launch (ncu --set full)")
     roofline["also"] = {"hbm_frac": kd["hbm_frac"], "fp32_frac": kd["fp32_frac"], "hbm_peak_gbs": hbm_peak,
                         "fp32_peak_tflops": fp32_peak}
+    # what the kernel actually waits for, measured once per round with the probe build / ncu (not in this run)
+    roofline["limiter"] = {
+        "k_hybrid": "SM: issue slots 76 % busy; 4 % faster with all DRAM traffic removed (probe build, profiles/r02_probe_bound.md)",
+        "k_synth": "SM: issue slots 75 % busy, FMA pipe 53 %; 3 % faster with all DRAM traffic removed (probe build, profiles/r02_probe_bound.md)",
+        "k1_huffman": "SM: dependent chain per code word, 16 of 32 lanes per instruction (profiles/r02_k1_history.md)"}.get(dom)
     # whole-pipeline view: algorithmic bytes of the fused minimum (bits + descriptor in, PCM out) and all flops
     pipe_bytes = main["main_data_bytes_per_gpu"] + main["granules_per_gpu"] * 2 * 32 + main["pcm_bytes_per_gpu"]
     pipe_flops = sum(FLOPS.values()) * n_units_main
