@@ -116,8 +116,12 @@ typedef struct mp3_batch_timings {
     uint64_t main_data_bytes, n_granules, pcm_bytes;
 } mp3_batch_timings;
 
-/* Decodes n streams.  PCM lands in an engine-owned pinned host buffer that stays valid until the
- * next mp3_decode_batch / mp3_engine_destroy on this engine; *pcm_base receives its address. */
+/* Decodes n streams on all devices of the engine (chunks of streams are pulled by the devices from a common queue; which
+ * device decodes a stream does not change its PCM).  PCM lands in an engine-owned pinned host buffer that stays valid
+ * until the next mp3_decode_batch / mp3_decode_stream_split / mp3_engine_destroy on this engine; *pcm_base receives its
+ * address.  Stream i's PCM is results[i].pcm_bytes bytes at results[i].pcm_offset, in stream order; for well-formed
+ * streams the buffer is dense, a stream that ends early (truncated, garbage) leaves a hole behind its PCM that no
+ * result covers.  One call at a time per engine. */
 int mp3_decode_batch(mp3_engine *e, const uint8_t *const *data, const size_t *lens, size_t n,
                      mp3_stream_result *results, const uint8_t **pcm_base, mp3_batch_timings *timings);
 
