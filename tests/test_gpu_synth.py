@@ -73,4 +73,6 @@ def test_synthetic_stream(pkg, engines, name, cfg):
             elif finite:
                 # |is| up to 8206 and gains up to 255 drive float32 sums to 1e30: fused rounding differences stay
                 # relative (1e-7) but are no longer below 1 LSB after the +-32767 clamp boundary; bound them loosely
-                assert frac > 0.95, (mx, frac)
+                # observed on B200 over wild0..11 (round 2): max|diff| 2..51 LSB, exact fraction 0.9978..0.9996
+                print(f"[pathological] {name}: max|diff| {mx} LSB, exact fraction {frac:.5f}")
+                assert frac > 0.995 and mx <= 128, (mx, frac)
