@@ -181,7 +181,7 @@ def run_reference(args, rank, world):
     import oracle
     from tools.synth import synth
     cores = os.cpu_count() or 1
-    per_step = max(cores * 4, 16)
+    per_step = max(cores * 8, 32)
     buf, offs, lens = make_workload(synth, 0, per_step, args.frames, cores, args.workload)
     streams = [buf[o:o + l].tobytes() for o, l in zip(offs, lens)]
     for _ in range(min(args.warmup, 1)):
@@ -417,7 +417,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- headline: configs[2] (or --workload cfg4), device-resident ------------------------------------------------
     main, sb_main = measure_resident(pkg, synth, D, eng, args.workload, args.streams, args.frames, rank * args.streams, threads,
                                      args.steps, args.warmup, rank, sorted({0, args.streams // 2, args.streams - 1}),
-                                     0 if args.no_cpu_baseline else max(cores * 4, 16), sampler)
+                                     0 if args.no_cpu_baseline else max(cores * 8, 32), sampler)
     clocks = sampler.stop()
     fp32_peak = eng.fp32_peak_tflops()
 
@@ -427,7 +427,7 @@ def run_ours(args, rank, world, local_rank):
         # streams 19 + 20 k are LSF (k % 3 == 1: mono); every non-LSF stream has short, mixed and long blocks and joint stereo
         par = sorted({0, 3, 19, 39, args.cfg4_streams - 1} & set(range(args.cfg4_streams)))
         cfg4, sb_cfg4 = measure_resident(pkg, synth, D, eng, "cfg4", args.cfg4_streams, args.frames, rank * args.cfg4_streams, threads,
-                                         max(3, args.steps // 2), 3, rank, par, 0 if args.no_cpu_baseline else max(cores * 4, 16))
+                                         max(3, args.steps // 2), 3, rank, par, 0 if args.no_cpu_baseline else max(cores * 8, 32))
     eng.close()
     D.barrier()
     torch.cuda.synchronize()
